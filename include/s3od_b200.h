@@ -1,0 +1,111 @@
+/*
+ * s3od_b200 - C ABI of the B200-native S3OD background-removal path.
+ *
+ * The reference (trflorian/s3od) is pure Python and has no FFI of its own; its seam is the class
+ * `s3od.BackgroundRemoval` (/root/reference/src/s3od/predictor.py:24-139).  This header is the boundary a host
+ * language binds instead of that class' internals; each entry point names the reference code it replaces.
+ * INTEGRATION.md shows the ctypes binding the Python drop-in (`s3od_b200.BackgroundRemoval`) uses.
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure; `s3od_last_error()` returns
+ * a thread-local message.  Pointers named d_* are device pointers owned by the caller; the context owns its
+ * weights and workspace.  Nothing synchronises the stream: the caller does.  A context is not re-entrant.
+ */
+#ifndef S3OD_B200_H
+#define S3OD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s3od_ctx s3od_ctx;
+typedef void* s3od_stream;            /* a cudaStream_t */
+
+enum { S3OD_ARCH_VITB = 0, S3OD_ARCH_VITL = 1 };
+enum { S3OD_OK = 0, S3OD_ERR_ARG = -1, S3OD_ERR_CUDA = -2, S3OD_ERR_STATE = -3, S3OD_ERR_MISSING = -4 };
+
+/* One source image for s3od_preprocess_u8: the letterbox geometry of utils.py:6-29 and, for general scales, the
+ * cv2 INTER_LINEAR coefficient tables (device int32 arrays [i0 | i1 | c0 | c1] x new_w / new_h). */
+typedef struct {
+  const uint8_t* d_src;      /* (h, w, 3) uint8 RGB on the device */
+  int32_t h, w;
+  int32_t new_h, new_w;
+  int32_t pad_h, pad_w;
+  int32_t mode;              /* 0 copy, 1 exact 2x box filter, 2 fixed-point bilinear */
+  const int32_t* d_xtab;
+  const int32_t* d_ytab;
+} s3od_image;
+
+/* One output image for s3od_postprocess: antialias filter taps precomputed by the host exactly as ATen does. */
+typedef struct {
+  const uint8_t* d_src;      /* (H, W, 3) source RGB */
+  float* d_all_masks;        /* (K, H, W) fp32 out   - RemovalResult.all_masks */
+  uint8_t* d_rgba;           /* (H, W, 4) uint8 out  - RemovalResult.rgba_image */
+  int32_t H, W;
+  int32_t pad_h, pad_w;
+  int32_t ky, kx;
+  const int32_t* d_ystart;   /* [H]      */
+  const float* d_yw;         /* [H, ky]  */
+  const int32_t* d_xstart;   /* [W]      */
+  const float* d_xw;         /* [W, kx]  */
+} s3od_post;
+
+/* Replaces BackgroundRemoval.__init__/_load_model's model construction (predictor.py:28-47, 67-74).
+ * micro_batch images are pushed through the network at a time; max_batch bounds one s3od_forward call. */
+int s3od_create(s3od_ctx** ctx, int device, int arch, int num_outputs, int image_size, int max_batch, int micro_batch);
+
+/* Replaces model.load_state_dict (predictor.py:76): one packed tensor by name, copied to the device.
+ * The packing (BN folding, QKV fusion, K-major bf16) is s3od_b200/weights.py; names are listed in DESIGN.md. */
+int s3od_set_tensor(s3od_ctx* ctx, const char* name, const void* host_data, size_t bytes);
+
+/* Checks every required tensor is present and builds the launch plan (TMA descriptors, workspace). */
+int s3od_finalize(s3od_ctx* ctx);
+
+/* Replaces BackgroundRemoval._preprocess (predictor.py:79-94) for B images already on the device. */
+int s3od_preprocess_u8(s3od_ctx* ctx, const s3od_image* images, int batch, s3od_stream stream);
+
+/* The reference's inner seam takes a float (B,3,S,S) tensor (model.py:99-106): pack it as the model input. */
+int s3od_pack_input_f32(s3od_ctx* ctx, const float* d_x, int batch, s3od_stream stream);
+
+/* Replaces DPTSegmentation.forward (model.py:99-106) on the input staged by one of the two calls above:
+ * d_mask_logits (B, K, S, S) fp32 = outputs['pred_masks'], d_iou_logits (B, K) fp32 = outputs['pred_iou']. */
+int s3od_forward(s3od_ctx* ctx, int batch, float* d_mask_logits, float* d_iou_logits, s3od_stream stream);
+
+/* Replaces the tail of remove_background (predictor.py:113-132): sigmoid, crop, antialiased resize to the source
+ * size, argmax over IoU, alpha composite.  d_ious (B, K) fp32 = all_ious, d_best_idx (B) int32. */
+int s3od_postprocess(s3od_ctx* ctx, const float* d_mask_logits, const float* d_iou_logits, const s3od_post* images,
+                     int batch, float* d_ious, int32_t* d_best_idx, s3od_stream stream);
+
+/* Internal activation by name (stage-wise parity tests): device pointer + size of the most recent micro-batch. */
+int s3od_get_stage(s3od_ctx* ctx, const char* name, void** d_ptr, size_t* bytes);
+
+/* Copy the first `bytes` of an internal activation into a caller buffer (device to device, on `stream`). */
+int s3od_read_stage(s3od_ctx* ctx, const char* name, void* d_dst, size_t bytes, s3od_stream stream);
+
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+long long s3od_launch_count(s3od_ctx* ctx);
+
+void s3od_destroy(s3od_ctx* ctx);
+const char* s3od_last_error(void);
+const char* s3od_version(void);
+
+/* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
+/* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */
+int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream);
+/* y bf16 = LayerNorm(x fp32) */
+int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void* d_y, int M, int D, float eps,
+                      s3od_stream stream);
+/* out[B*ntok, heads*64] bf16 = softmax(Q K^T) V ; q,k [B*heads, ntok, 64] bf16 (q pre-scaled by log2e/8),
+ * vt [B*heads, 64, vt_pitch] bf16 */
+int s3od_op_attention(const void* d_q, const void* d_k, const void* d_vt, void* d_out, int batch, int heads, int ntok,
+                      int vt_pitch, s3od_stream stream);
+/* NHWC bf16 3x3 / stride 1 / pad 1 convolution, weights [cout, 9*cin] bf16 (tap-major), fp32 bias or NULL */
+int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin,
+                    int cout, int relu, s3od_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3OD_B200_H */

@@ -1,0 +1,295 @@
+// Bandwidth-bound kernels of the S3OD path: preprocess, LayerNorm, prefix tokens, 2x bilinear up-sampling (+ average
+// pool partial sums), IoU head, and the fused post-process (sigmoid, crop, antialiased resize, argmax, RGBA composite).
+// All use 128-bit vector accesses on the contiguous (channel / x) dimension and warp-shuffle reductions.
+#pragma once
+#include "common.cuh"
+#include "types.h"
+
+namespace s3od {
+
+// ------------------------------------------------------------------------------------------------------------------
+// Image descriptors shared with the host (mirrors include/s3od_b200.h)
+// ------------------------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------------------------
+// Preprocess: uint8 HWC source -> letterboxed S x S canvas -> (x/255 - mean)/std -> bf16 patch rows.
+// Output row (b, py, px), column c*256 + ky*16 + kx : the im2col of the 16x16/stride-16 patch embedding, so the
+// patch-embed convolution (HF:71-81) is a plain GEMM.  The 3x256 normalisation LUT holds bf16(float32(reference value)).
+// predictor.py:79-94;  cv2.resize INTER_LINEAR arithmetic restated in oracle/prepost.py.
+// ------------------------------------------------------------------------------------------------------------------
+S3OD_DEVICE int resized_px(const ImageDesc& d, int y, int x, int c) {
+  if (d.mode == 0) return d.src[(static_cast<size_t>(y) * d.w + x) * 3 + c];
+  if (d.mode == 1) {
+    const uint8_t* r0 = d.src + (static_cast<size_t>(2 * y) * d.w + 2 * x) * 3 + c;
+    const uint8_t* r1 = r0 + static_cast<size_t>(d.w) * 3;
+    return (r0[0] + r0[3] + r1[0] + r1[3] + 2) >> 2;
+  }
+  const int x0 = d.xtab[x], x1 = d.xtab[d.new_w + x], a0 = d.xtab[2 * d.new_w + x], a1 = d.xtab[3 * d.new_w + x];
+  const int y0 = d.ytab[y], y1 = d.ytab[d.new_h + y], b0 = d.ytab[2 * d.new_h + y], b1 = d.ytab[3 * d.new_h + y];
+  const uint8_t* r0 = d.src + static_cast<size_t>(y0) * d.w * 3 + c;
+  const uint8_t* r1 = d.src + static_cast<size_t>(y1) * d.w * 3 + c;
+  const int s0 = r0[x0 * 3] * a0 + r0[x1 * 3] * a1;
+  const int s1 = r1[x0 * 3] * a0 + r1[x1 * 3] * a1;
+  return (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const ImageDesc* __restrict__ descs, const __nv_bfloat16* __restrict__ lut,
+                                                         __nv_bfloat16* __restrict__ patches, int S) {
+  __shared__ __nv_bfloat16 s_lut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const ImageDesc d = descs[b];
+  const int g = S >> 4;
+  const int x8_per_row = S >> 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * x8_per_row) return;
+  const int Y = idx / x8_per_row;
+  const int X = (idx % x8_per_row) << 3;
+  const int ry = Y - d.pad_h;
+  const bool row_in = ry >= 0 && ry < d.new_h;
+  const size_t prow = static_cast<size_t>(b) * g * g + (Y >> 4) * g + (X >> 4);
+  __nv_bfloat16* dst = patches + prow * 768 + (Y & 15) * 16 + (X & 15);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rx = X + i - d.pad_w;
+      const int px = (row_in && rx >= 0 && rx < d.new_w) ? resized_px(d, ry, rx, c) : 0;
+      v[i] = s_lut[c * 256 + px];
+    }
+    *reinterpret_cast<uint4*>(dst + c * 256) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// fp32 NCHW model input (the reference's inner seam `model(x)`, model.py:99-106) -> bf16 patch rows
+__global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ patches, int S) {
+  const int b = blockIdx.y;
+  const int g = S >> 4;
+  const int x8_per_row = S >> 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 3 * S * x8_per_row) return;
+  const int c = idx / (S * x8_per_row);
+  const int r = idx % (S * x8_per_row);
+  const int Y = r / x8_per_row, X = (r % x8_per_row) << 3;
+  const float4* src = reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * 3 + c) * S + Y) * S + X);
+  const float4 a = src[0], bb = src[1];
+  uint4 u;
+  u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(bb.x, bb.y); u.w = pack_bf16x2(bb.z, bb.w);
+  const size_t prow = static_cast<size_t>(b) * g * g + (Y >> 4) * g + (X >> 4);
+  *reinterpret_cast<uint4*>(patches + prow * 768 + c * 256 + (Y & 15) * 16 + (X & 15)) = u;
+}
+
+// cls + register tokens into rows 0..4 of every image (HF:88-90)
+__global__ void fill_prefix_kernel(float* __restrict__ x, const float* __restrict__ prefix, int ntok, int D, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = 5 * D;
+  if (i >= B * per) return;
+  const int b = i / per, r = i % per;
+  x[static_cast<size_t>(b) * ntok * D + r] = prefix[r];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5) over D of fp32 rows -> bf16 rows (the A operand of the following GEMM).  One warp per row,
+// the row lives in registers (two-pass mean / variance, fp32).  HF:411,416,433,445.
+// ------------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, __nv_bfloat16* __restrict__ y, int M,
+                                                        float eps) {
+  constexpr int V = D / 128;      // float4 per lane
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  float4 v[V];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 ww = __ldg(w4 + lane + 32 * i), bv = __ldg(b4 + lane + 32 * i);
+    uint2 o;
+    o.x = pack_bf16x2((v[i].x - mean) * rstd * ww.x + bv.x, (v[i].y - mean) * rstd * ww.y + bv.y);
+    o.y = pack_bf16x2((v[i].z - mean) * rstd * ww.z + bv.z, (v[i].w - mean) * rstd * ww.w + bv.w);
+    yr[lane + 32 * i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 2x bilinear up-sampling, align_corners=False, NHWC bf16 (FeatureFusionBlock, model.py:394-402; the following 1x1
+// out_conv has been applied at low resolution - it commutes with the interpolation because the weights sum to 1).
+// Thread = one output pixel x 8 channels.  With `pool` != nullptr each block also writes per-channel partial sums of
+// its outputs (deterministic two-stage average pool for the IoU head, model.py:185-191).
+// grid = (blocks_per_image, B), block = 256 threads = (C/8) channel groups x (256 / (C/8)) pixels per step.
+// ------------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                         float* __restrict__ pool, int h, int w) {
+  constexpr int CG = C / 8;                 // channel groups (threads along channels)
+  constexpr int PP = 256 / CG;              // pixels per block step
+  const int b = blockIdx.y;
+  const int cg = threadIdx.x % CG;
+  const int pl = threadIdx.x / CG;
+  const int OH = 2 * h, OW = 2 * w;
+  const int npix = OH * OW;
+  const int per_block = (npix + gridDim.x - 1) / gridDim.x;
+  const int p_begin = blockIdx.x * per_block;
+  const int p_end = min(npix, p_begin + per_block);
+  const __nv_bfloat16* ib = in + static_cast<size_t>(b) * h * w * C + cg * 8;
+  __nv_bfloat16* ob = out + static_cast<size_t>(b) * npix * C + cg * 8;
+  float psum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) psum[i] = 0.0f;
+  for (int pix = p_begin + pl; pix < p_end; pix += PP) {
+    const int oy = pix / OW, ox = pix % OW;
+    // source coordinate (o + 0.5)/2 - 0.5, clamped at 0:  even o=2i -> taps (i-1: .25, i: .75), odd -> (i: .75, i+1: .25)
+    const int iy = oy >> 1, ix = ox >> 1;
+    const int y0 = (oy & 1) ? iy : max(iy - 1, 0), y1 = (oy & 1) ? min(iy + 1, h - 1) : iy;
+    const int x0 = (ox & 1) ? ix : max(ix - 1, 0), x1 = (ox & 1) ? min(ix + 1, w - 1) : ix;
+    const float wy0 = (oy & 1) ? 0.75f : (iy == 0 ? 0.0f : 0.25f), wy1 = 1.0f - wy0;
+    const float wx0 = (ox & 1) ? 0.75f : (ix == 0 ? 0.0f : 0.25f), wx1 = 1.0f - wx0;
+    const uint4 a = *reinterpret_cast<const uint4*>(ib + (static_cast<size_t>(y0) * w + x0) * C);
+    const uint4 bq = *reinterpret_cast<const uint4*>(ib + (static_cast<size_t>(y0) * w + x1) * C);
+    const uint4 c = *reinterpret_cast<const uint4*>(ib + (static_cast<size_t>(y1) * w + x0) * C);
+    const uint4 d = *reinterpret_cast<const uint4*>(ib + (static_cast<size_t>(y1) * w + x1) * C);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {c.x, c.y, c.z, c.w},
+                   dv[4] = {d.x, d.y, d.z, d.w};
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r[2 * i] = wy0 * (wx0 * bf16_lo(av[i]) + wx1 * bf16_lo(bv[i])) + wy1 * (wx0 * bf16_lo(cv[i]) + wx1 * bf16_lo(dv[i]));
+      r[2 * i + 1] = wy0 * (wx0 * bf16_hi(av[i]) + wx1 * bf16_hi(bv[i])) + wy1 * (wx0 * bf16_hi(cv[i]) + wx1 * bf16_hi(dv[i]));
+    }
+    uint4 o;
+    o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]); o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
+    *reinterpret_cast<uint4*>(ob + static_cast<size_t>(pix) * C) = o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) psum[i] += r[i];
+  }
+  if (pool != nullptr) {
+    __shared__ float red[PP][C + 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl][cg * 8 + i] = psum[i];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += 256) {
+      float s = 0.0f;
+      for (int k = 0; k < PP; ++k) s += red[k][ch];
+      pool[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C + ch] = s;
+    }
+  }
+}
+
+// IoU head finisher: mean over pixels (fixed summation order), Linear(256,64) + ReLU, Linear(64,K).  model.py:185-191.
+__global__ void __launch_bounds__(256) iou_head_kernel(const float* __restrict__ pool, int nblocks, float inv_npix,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       float* __restrict__ iou_logits, int K) {
+  __shared__ float mean[256];
+  __shared__ float hid[64];
+  const int b = blockIdx.x;
+  {
+    const int ch = threadIdx.x;
+    float s = 0.0f;
+    const float* pb = pool + static_cast<size_t>(b) * nblocks * 256 + ch;
+    for (int k = 0; k < nblocks; ++k) s += pb[static_cast<size_t>(k) * 256];
+    mean[ch] = s * inv_npix;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = b1[threadIdx.x];
+    const float* wr = w1 + threadIdx.x * 256;
+    for (int i = 0; i < 256; ++i) s = fmaf(mean[i], wr[i], s);
+    hid[threadIdx.x] = fmaxf(s, 0.0f);
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float s = b2[threadIdx.x];
+    const float* wr = w2 + threadIdx.x * 64;
+    for (int i = 0; i < 64; ++i) s = fmaf(hid[i], wr[i], s);
+    iou_logits[b * K + threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Post-process (predictor.py:113-132): sigmoid of the mask logits at model resolution, crop of the letterbox padding,
+// antialiased bilinear resize to the source size (separable triangle filter, weights precomputed on the host exactly as
+// ATen does), sigmoid of the IoU logits, first-max argmax, alpha = trunc(best * 255), RGBA = [R, G, B, alpha].
+// Thread = one output pixel; grid = (ceil(W/128), H, B)... x is the fastest dimension for coalesced stores.
+// ------------------------------------------------------------------------------------------------------------------
+S3OD_DEVICE float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int K>
+__global__ void __launch_bounds__(128) postprocess_kernel(const PostDesc* __restrict__ descs, const float* __restrict__ mask_logits,
+                                                          const float* __restrict__ iou_logits, float* __restrict__ ious,
+                                                          int* __restrict__ best_idx, int S) {
+  const int b = blockIdx.z;
+  const PostDesc d = descs[b];
+  const int oy = blockIdx.y;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (oy >= d.H) return;
+  // IoU scores + first-max argmax (every thread computes the same 3 values; thread 0 of block (0,0) publishes them)
+  float sc[K];
+  int best = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    sc[k] = sigmoidf_acc(iou_logits[b * K + k]);
+    if (sc[k] > sc[best]) best = k;
+  }
+  if (blockIdx.x == 0 && oy == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) ious[b * K + k] = sc[k];
+    best_idx[b] = best;
+  }
+  if (ox >= d.W) return;
+  const int ys = d.ystart[oy] + d.pad_h;
+  const int xs = d.xstart[ox] + d.pad_w;
+  const float* yw = d.yw + static_cast<size_t>(oy) * d.ky;
+  const float* xw = d.xw + static_cast<size_t>(ox) * d.kx;
+  float res[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float* plane = mask_logits + (static_cast<size_t>(b) * K + k) * S * S;
+    float acc = 0.0f;
+    for (int ty = 0; ty < d.ky; ++ty) {
+      const float wy = yw[ty];
+      if (wy == 0.0f && ty > 0) continue;              // zero-padded tail taps
+      const float* rowp = plane + static_cast<size_t>(min(ys + ty, S - 1)) * S;
+      float hsum = 0.0f;
+      for (int tx = 0; tx < d.kx; ++tx) {
+        const float wx = xw[tx];
+        if (wx != 0.0f || tx == 0) {
+          const float pv = sigmoidf_acc(rowp[min(xs + tx, S - 1)]);
+          hsum = (tx == 0) ? pv * wx : hsum + pv * wx;
+        }
+      }
+      acc = (ty == 0) ? hsum * wy : acc + hsum * wy;
+    }
+    res[k] = acc;
+    d.all_masks[(static_cast<size_t>(k) * d.H + oy) * d.W + ox] = acc;
+  }
+  float bestv = res[0];
+#pragma unroll
+  for (int k = 1; k < K; ++k) bestv = (best == k) ? res[k] : bestv;
+  const uint8_t* sp = d.src + (static_cast<size_t>(oy) * d.W + ox) * 3;
+  uchar4 px;
+  px.x = sp[0]; px.y = sp[1]; px.z = sp[2];
+  px.w = static_cast<uint8_t>(static_cast<int>(bestv * 255.0f));     // truncation, predictor.py:130
+  reinterpret_cast<uchar4*>(d.rgba)[static_cast<size_t>(oy) * d.W + ox] = px;
+}
+
+}  // namespace s3od

@@ -1,0 +1,772 @@
+// Context, launch plan and C ABI of the B200-native S3OD forward path (see include/s3od_b200.h).
+//
+// Data layout in HBM (nb = images of the current micro-batch, g = S/16, P = g*g patches, ntok = P + 5):
+//   patches  bf16 [B*P, 768]            im2col of the letterboxed, normalised input (whole batch)
+//   x        fp32 [nb*ntok, D]          residual stream          xn / ctx bf16 [nb*ntok, D]   LN output / attention output
+//   q, k     bf16 [nb*H, ntok, 64]      vt bf16 [nb*H, 64, vt_pitch]                          hmid bf16 [nb*ntok, I]
+//   taps     bf16 [nb*P, D] x 4         == NHWC (nb, g, g, D): token-major IS channels-last, no permute (model.py:206)
+//   head     bf16 NHWC everywhere; mask logits fp32 planar (B, K, S, S) straight into the caller's buffer.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/s3od_b200.h"
+#include "launch.h"
+
+using namespace s3od;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(expr)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      return fail(S3OD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------- TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map with 128B swizzle; dims[0] is the contiguous dimension, strides in BYTES for dims 1..rank-1.
+bool make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    g_err = "cuTensorMapEncodeTiled entry point not available";
+    return false;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_err = "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r));
+    return false;
+  }
+  return true;
+}
+
+// row-major [rows, cols] bf16 matrix, box = 64 columns x box_rows rows
+bool tmap_matrix(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {cols * 2};
+  const uint32_t box[2] = {64, box_rows};
+  return make_tmap(m, base, 2, dims, strides, box);
+}
+
+// NHWC (B, H, W, C) activation as the 5-D (C, W, 1, H, B) view, box = 64 ch x 16 x 1 x 8 x 1
+bool tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, 1, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint32_t box[5] = {64, kTileW, 1, kTileH, 1};
+  return make_tmap(m, base, 5, dims, strides, box);
+}
+
+// the same tensor viewed as (2C, W/2, 2, H/2, B): element (c + px*C, w2, py, h2, b) = in[b, 2*h2+py, 2*w2+px, c]
+bool tmap_nhwc_s2(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
+  const uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)B};
+  const uint64_t strides[4] = {(uint64_t)2 * C * 2, (uint64_t)W * C * 2, (uint64_t)2 * W * C * 2, (uint64_t)H * W * C * 2};
+  const uint32_t box[5] = {64, kTileW, 1, kTileH, 1};
+  return make_tmap(m, base, 5, dims, strides, box);
+}
+
+ConvGeom geom_3x3(int H, int W, int cin) {
+  ConvGeom g{};
+  g.H = H; g.W = W;
+  g.tiles_h = (H + kTileH - 1) / kTileH;
+  g.tiles_w = (W + kTileW - 1) / kTileW;
+  g.cin_blocks = cin / 64;
+  g.ntaps = 9;
+  for (int t = 0; t < 9; ++t) {
+    g.dc[t] = 0; g.dp[t] = 0;
+    g.dh[t] = t / 3 - 1;
+    g.dw[t] = t % 3 - 1;
+  }
+  return g;
+}
+
+// 3x3 stride 2 pad 1 on the (2C, W/2, 2, H/2, B) view: input row 2*oh + ky - 1 -> (h2, py) = (oh-1,1), (oh,0), (oh,1)
+ConvGeom geom_3x3_s2(int OH, int OW, int cin) {
+  ConvGeom g{};
+  g.H = OH; g.W = OW;
+  g.tiles_h = (OH + kTileH - 1) / kTileH;
+  g.tiles_w = (OW + kTileW - 1) / kTileW;
+  g.cin_blocks = cin / 64;
+  g.ntaps = 9;
+  const int d2[3] = {-1, 0, 0}, par[3] = {1, 0, 1};
+  for (int t = 0; t < 9; ++t) {
+    const int ky = t / 3, kx = t % 3;
+    g.dh[t] = d2[ky]; g.dp[t] = par[ky];
+    g.dw[t] = d2[kx]; g.dc[t] = par[kx] * cin;
+  }
+  return g;
+}
+
+// ConvTranspose2d k4 s2 p1 as four 2x2 sub-pixel convolutions: output (2i+a, 2j+b); for a = 0 the two row taps are
+// input rows (i, i-1) with kernel rows (1, 3); for a = 1 rows (i+1, i) with kernel rows (0, 2); same for columns.
+// weights.py packs tap (r, c) = r*2 + c in the same order.
+ConvGeom geom_convt_phase(int H, int W, int cin, int a, int b) {
+  ConvGeom g{};
+  g.H = H; g.W = W;
+  g.tiles_h = (H + kTileH - 1) / kTileH;
+  g.tiles_w = (W + kTileW - 1) / kTileW;
+  g.cin_blocks = cin / 64;
+  g.ntaps = 4;
+  const int off[2][2] = {{0, -1}, {1, 0}};
+  for (int t = 0; t < 4; ++t) {
+    g.dc[t] = 0; g.dp[t] = 0;
+    g.dh[t] = off[a][t / 2];
+    g.dw[t] = off[b][t % 2];
+  }
+  return g;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+// ================================================================================================ context
+struct s3od_ctx {
+  int device = 0, arch = 0, K = 3, S = 1024, max_batch = 1, mb = 1;
+  int g = 64, P = 4096, ntok = 4101, D = 768, H = 12, I = 3072, L = 11, vt_pitch = 4104;
+  int taps[4] = {2, 5, 8, 11};
+  int oc[4] = {256, 512, 1024, 1024};
+  int num_sms = 148;
+  int pool_blocks = 1;
+  bool finalized = false;
+  long long launches = 0;
+  std::unordered_map<std::string, DevBuf> w;     // packed weights by name
+  std::unordered_map<std::string, DevBuf> act;   // activations by name
+  std::vector<void*> allocs;
+  ImageDesc* d_img = nullptr;
+  PostDesc* d_post = nullptr;
+  int last_nb = 0;
+  // launch plan: every op takes (nb images, first image index b0, mask-logit out, iou-logit out, stream)
+  using Op = std::function<cudaError_t(int, int, float*, float*, cudaStream_t)>;
+  std::vector<std::pair<std::string, Op>> plan;
+};
+
+namespace {
+
+template <class T>
+T* wptr(s3od_ctx* c, const std::string& name) {
+  auto it = c->w.find(name);
+  return it == c->w.end() ? nullptr : reinterpret_cast<T*>(it->second.p);
+}
+
+bool alloc_act(s3od_ctx* c, const std::string& name, size_t bytes) {
+  void* p = nullptr;
+  bytes = (bytes + 255) & ~size_t(255);
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    g_err = "cudaMalloc failed for activation " + name + " (" + std::to_string(bytes) + " bytes)";
+    return false;
+  }
+  cudaMemset(p, 0, bytes);
+  c->allocs.push_back(p);
+  c->act[name] = DevBuf{p, bytes};
+  return true;
+}
+
+template <class T>
+T* aptr(s3od_ctx* c, const std::string& name) {
+  return reinterpret_cast<T*>(c->act.at(name).p);
+}
+
+using bf16 = __nv_bfloat16;
+
+// ---- plan builders -----------------------------------------------------------------------------------------------
+template <int BN, class Epi, int EW>
+bool add_linear(s3od_ctx* c, const std::string& label, const void* a, uint64_t a_rows_total, int rows_per_image, int Kdim,
+                const void* bw, int N, typename Epi::Params ep, bool a_is_batch_window = false,
+                std::function<void(typename Epi::Params&, int, int, float*, float*)> patch = nullptr) {
+  if (N % BN != 0 || Kdim % 64 != 0) {
+    g_err = "bad GEMM shape for " + label;
+    return false;
+  }
+  GemmParams<Epi> p{};
+  if (!tmap_matrix(&p.tma_a, a, a_rows_total, Kdim, kBM)) return false;
+  if (!tmap_matrix(&p.tma_b, bw, N, Kdim, BN)) return false;
+  p.n_tiles = N / BN;
+  p.num_k_blocks = Kdim / 64;
+  p.b_row_offset = 0;
+  p.a_row_offset = 0;
+  p.epi = ep;
+  const int sms = c->num_sms;
+  c->plan.emplace_back(label, [=](int nb, int b0, float* mo, float* io, cudaStream_t st) mutable -> cudaError_t {
+    GemmParams<Epi> q = p;
+    q.M = nb * rows_per_image;
+    q.m_tiles = (q.M + kBM - 1) / kBM;
+    q.a_row_offset = a_is_batch_window ? b0 * rows_per_image : 0;
+    if (patch) patch(q.epi, nb, b0, mo, io);
+    return launch_gemm<BN, A_LINEAR, Epi, EW>(q, sms, st);
+  });
+  return true;
+}
+
+template <int BN, class Epi, int EW>
+bool add_conv(s3od_ctx* c, const std::string& label, const CUtensorMap& tma_a, const ConvGeom& geom, const void* bw,
+              int b_rows_total, int b_row_offset, int Kdim, int N, typename Epi::Params ep,
+              std::function<void(typename Epi::Params&, int, int, float*, float*)> patch = nullptr) {
+  if (N % BN != 0 || Kdim % 64 != 0 || Kdim != geom.ntaps * geom.cin_blocks * 64) {
+    g_err = "bad conv shape for " + label;
+    return false;
+  }
+  GemmParams<Epi> p{};
+  p.tma_a = tma_a;
+  if (!tmap_matrix(&p.tma_b, bw, b_rows_total, Kdim, BN)) return false;
+  p.n_tiles = N / BN;
+  p.num_k_blocks = Kdim / 64;
+  p.b_row_offset = b_row_offset;
+  p.geom = geom;
+  p.epi = ep;
+  const int sms = c->num_sms;
+  c->plan.emplace_back(label, [=](int nb, int b0, float* mo, float* io, cudaStream_t st) mutable -> cudaError_t {
+    GemmParams<Epi> q = p;
+    q.M = 0;
+    q.m_tiles = nb * geom.tiles_h * geom.tiles_w;
+    if (patch) patch(q.epi, nb, b0, mo, io);
+    return launch_gemm<BN, A_CONV, Epi, EW>(q, sms, st);
+  });
+  return true;
+}
+
+EpiConv::Params conv_epi(bf16* out, bf16* out_relu, const float* bias, const bf16* res1, const bf16* res2, int relu, int cout,
+                         int oh, int ow) {
+  EpiConv::Params e{};
+  e.out = out; e.out_relu = out_relu; e.bias = bias; e.res1 = res1; e.res2 = res2; e.relu = relu;
+  e.linear = 0; e.hin = 0; e.win = 0; e.up = 1; e.ph_h = 0; e.ph_w = 0; e.cout = cout; e.oh = oh; e.ow = ow;
+  return e;
+}
+
+// 3x3 / stride 1 / pad 1 convolution on an NHWC activation of c->mb images
+template <int BN, int EW>
+bool add_conv3x3(s3od_ctx* c, const std::string& label, const bf16* in, int Hs, int Ws, int cin, const std::string& wname,
+                 int cout, EpiConv::Params ep) {
+  CUtensorMap ta;
+  if (!tmap_nhwc(&ta, in, c->mb, Hs, Ws, cin)) return false;
+  const bf16* wt = wptr<bf16>(c, wname);
+  return add_conv<BN, EpiConv, EW>(c, label, ta, geom_3x3(Hs, Ws, cin), wt, cout, 0, 9 * cin, cout, ep);
+}
+
+bool build_plan(s3od_ctx* c) {
+  const int mb = c->mb, g = c->g, P = c->P, ntok = c->ntok, D = c->D, H = c->H, I = c->I, K = c->K, S = c->S;
+  const size_t MT = static_cast<size_t>(mb) * ntok;
+  // ---- activations
+  bool ok = true;
+  ok = ok && alloc_act(c, "patches", static_cast<size_t>(c->max_batch) * P * 768 * 2);
+  ok = ok && alloc_act(c, "x", MT * D * 4);
+  ok = ok && alloc_act(c, "xn", MT * D * 2);
+  ok = ok && alloc_act(c, "ctx", MT * D * 2);
+  ok = ok && alloc_act(c, "q", MT * D * 2);
+  ok = ok && alloc_act(c, "k", MT * D * 2);
+  ok = ok && alloc_act(c, "vt", static_cast<size_t>(mb) * H * 64 * c->vt_pitch * 2);
+  ok = ok && alloc_act(c, "hmid", MT * I * 2);
+  for (int j = 0; j < 4; ++j) ok = ok && alloc_act(c, "tap" + std::to_string(j), static_cast<size_t>(mb) * P * D * 2);
+  const int R[5] = {0, 4 * g, 2 * g, g, g / 2};     // resolution of layer_k_rn, k = 1..4
+  for (int j = 0; j < 4; ++j) ok = ok && alloc_act(c, "f" + std::to_string(j), static_cast<size_t>(mb) * P * c->oc[j] * 2);
+  ok = ok && alloc_act(c, "r0", static_cast<size_t>(mb) * R[1] * R[1] * c->oc[0] * 2);
+  ok = ok && alloc_act(c, "r1", static_cast<size_t>(mb) * R[2] * R[2] * c->oc[1] * 2);
+  ok = ok && alloc_act(c, "r3", static_cast<size_t>(mb) * R[4] * R[4] * c->oc[3] * 2);
+  for (int k = 1; k <= 4; ++k) {
+    const size_t n = static_cast<size_t>(mb) * R[k] * R[k] * 256 * 2;
+    ok = ok && alloc_act(c, "l" + std::to_string(k), n);
+    ok = ok && alloc_act(c, "l" + std::to_string(k) + "r", n);
+  }
+  const size_t tmax = static_cast<size_t>(mb) * R[1] * R[1] * 256 * 2;
+  for (const char* nm : {"tA", "tB", "tC", "tD"}) ok = ok && alloc_act(c, nm, tmax);
+  ok = ok && alloc_act(c, "p4", static_cast<size_t>(mb) * R[3] * R[3] * 256 * 2);
+  ok = ok && alloc_act(c, "p3", static_cast<size_t>(mb) * R[2] * R[2] * 256 * 2);
+  ok = ok && alloc_act(c, "p2", static_cast<size_t>(mb) * R[1] * R[1] * 256 * 2);
+  const int R0 = 8 * g;                              // path_1 resolution (S/2)
+  ok = ok && alloc_act(c, "p1", static_cast<size_t>(mb) * R0 * R0 * 256 * 2);
+  ok = ok && alloc_act(c, "mh1", static_cast<size_t>(mb) * R0 * R0 * 128 * 2);
+  ok = ok && alloc_act(c, "feat0", static_cast<size_t>(mb) * S * S * 64 * 2);
+  ok = ok && alloc_act(c, "feat", static_cast<size_t>(mb) * S * S * 64 * 2);
+  c->pool_blocks = std::max(1, std::min(4 * c->num_sms / std::max(1, mb) + 1, (R0 * R0 + 63) / 64));
+  ok = ok && alloc_act(c, "pool", static_cast<size_t>(mb) * c->pool_blocks * 256 * 4);
+  if (!ok) return false;
+
+  float* x = aptr<float>(c, "x");
+  bf16* xn = aptr<bf16>(c, "xn");
+  bf16* actx = aptr<bf16>(c, "ctx");
+  bf16* hmid = aptr<bf16>(c, "hmid");
+  const int sms = c->num_sms;
+
+  // ---- encoder ---------------------------------------------------------------------------------------------------
+  {
+    EpiPatch::Params e{x, wptr<float>(c, "patch.b"), P, ntok, D};
+    if (!add_linear<256, EpiPatch, 8>(c, "patch_embed", aptr<bf16>(c, "patches"), static_cast<uint64_t>(c->max_batch) * P, P, 768,
+                                      wptr<bf16>(c, "patch.w"), D, e, /*a_is_batch_window=*/true))
+      return false;
+    const float* prefix = wptr<float>(c, "prefix");
+    c->plan.emplace_back("prefix_tokens", [=](int nb, int, float*, float*, cudaStream_t st) {
+      return launch_fill_prefix(x, prefix, ntok, D, nb, st);
+    });
+  }
+  AttnParams ap{};
+  {
+    const uint64_t BH = static_cast<uint64_t>(mb) * H;
+    const uint64_t dq[3] = {64, (uint64_t)ntok, BH};
+    const uint64_t sq[2] = {128, (uint64_t)ntok * 128};
+    const uint32_t bq[3] = {64, 128, 1};
+    if (!make_tmap(&ap.tma_q, aptr<bf16>(c, "q"), 3, dq, sq, bq)) return false;
+    if (!make_tmap(&ap.tma_k, aptr<bf16>(c, "k"), 3, dq, sq, bq)) return false;
+    const uint64_t dv[3] = {(uint64_t)ntok, 64, BH};
+    const uint64_t sv[2] = {(uint64_t)c->vt_pitch * 2, (uint64_t)c->vt_pitch * 2 * 64};
+    const uint32_t bv[3] = {64, 64, 1};
+    if (!make_tmap(&ap.tma_vt, aptr<bf16>(c, "vt"), 3, dv, sv, bv)) return false;
+    ap.out = actx;
+    ap.ntok = ntok;
+    ap.heads = H;
+    ap.kv_tiles = (ntok + 127) / 128;
+  }
+  for (int l = 0; l < c->L; ++l) {
+    const std::string pre = "enc." + std::to_string(l) + ".";
+    const float *ln1w = wptr<float>(c, pre + "ln1.w"), *ln1b = wptr<float>(c, pre + "ln1.b");
+    const float *ln2w = wptr<float>(c, pre + "ln2.w"), *ln2b = wptr<float>(c, pre + "ln2.b");
+    c->plan.emplace_back(pre + "ln1", [=](int nb, int, float*, float*, cudaStream_t st) {
+      return launch_layernorm(x, ln1w, ln1b, xn, nb * ntok, D, 1e-5f, st);
+    });
+    {
+      EpiQKV::Params e{};
+      e.q = aptr<bf16>(c, "q"); e.k = aptr<bf16>(c, "k"); e.vt = aptr<bf16>(c, "vt");
+      e.bias = wptr<float>(c, pre + "qkv.b");
+      e.rope_cos = wptr<float>(c, "rope.cos"); e.rope_sin = wptr<float>(c, "rope.sin");
+      e.ntok = ntok; e.heads = H; e.D = D; e.vt_pitch = c->vt_pitch;
+      e.qscale = 0.125f * 1.4426950408889634f;
+      if (!add_linear<256, EpiQKV, 8>(c, pre + "qkv", xn, MT, ntok, D, wptr<bf16>(c, pre + "qkv.w"), 3 * D, e)) return false;
+    }
+    c->plan.emplace_back(pre + "attention", [=](int nb, int, float*, float*, cudaStream_t st) {
+      return launch_attention(ap, (ntok + 127) / 128, nb * H, st);
+    });
+    {
+      EpiResidual::Params e{x, wptr<float>(c, pre + "o.b"), wptr<float>(c, pre + "ls1"), nullptr, ntok, P, D};
+      if (!add_linear<256, EpiResidual, 8>(c, pre + "o_proj", actx, MT, ntok, D, wptr<bf16>(c, pre + "o.w"), D, e)) return false;
+    }
+    c->plan.emplace_back(pre + "ln2", [=](int nb, int, float*, float*, cudaStream_t st) {
+      return launch_layernorm(x, ln2w, ln2b, xn, nb * ntok, D, 1e-5f, st);
+    });
+    {
+      EpiGelu::Params e{hmid, wptr<float>(c, pre + "up.b"), I};
+      if (!add_linear<256, EpiGelu, 8>(c, pre + "up_proj", xn, MT, ntok, D, wptr<bf16>(c, pre + "up.w"), I, e)) return false;
+    }
+    {
+      bf16* tap = nullptr;
+      for (int j = 0; j < 4; ++j)
+        if (c->taps[j] == l + 1) tap = aptr<bf16>(c, "tap" + std::to_string(j));
+      EpiResidual::Params e{x, wptr<float>(c, pre + "down.b"), wptr<float>(c, pre + "ls2"), tap, ntok, P, D};
+      if (!add_linear<256, EpiResidual, 8>(c, pre + "down_proj", hmid, MT, ntok, I, wptr<bf16>(c, pre + "down.w"), D, e)) return false;
+    }
+  }
+
+  // ---- DPT head: projects + resize layers (model.py:193-211) --------------------------------------------------------
+  const uint64_t MP = static_cast<uint64_t>(mb) * P;
+  for (int j = 0; j < 4; ++j) {
+    const std::string sj = std::to_string(j);
+    EpiConv::Params e = conv_epi(aptr<bf16>(c, "f" + sj), nullptr, wptr<float>(c, "head.proj" + sj + ".b"), nullptr, nullptr, 0,
+                                 c->oc[j], g, g);
+    e.linear = 1; e.hin = g; e.win = g;
+    if (!add_linear<256, EpiConv, 8>(c, "head.proj" + sj, aptr<bf16>(c, "tap" + sj), MP, P, D, wptr<bf16>(c, "head.proj" + sj + ".w"),
+                                     c->oc[j], e))
+      return false;
+  }
+  {  // ConvTranspose k4 s4 (256 -> 256): one GEMM, N = 16 phases x 256, depth-to-space in the epilogue
+    EpiConv::Params e = conv_epi(aptr<bf16>(c, "r0"), nullptr, wptr<float>(c, "head.rs0.b"), nullptr, nullptr, 0, c->oc[0], R[1], R[1]);
+    e.linear = 1; e.hin = g; e.win = g; e.up = 4;
+    if (!add_linear<256, EpiConv, 8>(c, "head.rs0", aptr<bf16>(c, "f0"), MP, P, c->oc[0], wptr<bf16>(c, "head.rs0.w"), 16 * c->oc[0], e))
+      return false;
+  }
+  {  // ConvTranspose k2 s2 (512 -> 512)
+    EpiConv::Params e = conv_epi(aptr<bf16>(c, "r1"), nullptr, wptr<float>(c, "head.rs1.b"), nullptr, nullptr, 0, c->oc[1], R[2], R[2]);
+    e.linear = 1; e.hin = g; e.win = g; e.up = 2;
+    if (!add_linear<256, EpiConv, 8>(c, "head.rs1", aptr<bf16>(c, "f1"), MP, P, c->oc[1], wptr<bf16>(c, "head.rs1.w"), 4 * c->oc[1], e))
+      return false;
+  }
+  {  // Conv 3x3 stride 2 (1024 -> 1024) on f3
+    CUtensorMap ta;
+    if (!tmap_nhwc_s2(&ta, aptr<bf16>(c, "f3"), mb, g, g, c->oc[3])) return false;
+    EpiConv::Params e = conv_epi(aptr<bf16>(c, "r3"), nullptr, wptr<float>(c, "head.rs3.b"), nullptr, nullptr, 0, c->oc[3], R[4], R[4]);
+    if (!add_conv<256, EpiConv, 8>(c, "head.rs3", ta, geom_3x3_s2(R[4], R[4], c->oc[3]), wptr<bf16>(c, "head.rs3.w"), c->oc[3], 0,
+                                   9 * c->oc[3], c->oc[3], e))
+      return false;
+  }
+  // layer{k}_rn: 3x3, no bias, -> 256; the relu'd copy feeds the first conv of the residual unit that consumes it
+  const char* rn_in[5] = {"", "r0", "r1", "f2", "r3"};
+  for (int k = 1; k <= 4; ++k) {
+    const std::string sk = std::to_string(k);
+    EpiConv::Params e = conv_epi(aptr<bf16>(c, "l" + sk), aptr<bf16>(c, "l" + sk + "r"), nullptr, nullptr, nullptr, 0, 256, R[k], R[k]);
+    if (!add_conv3x3<256, 8>(c, "head.rn" + sk, aptr<bf16>(c, rn_in[k]), R[k], R[k], c->oc[k - 1], "head.rn" + sk + ".w", 256, e))
+      return false;
+  }
+  // ---- fusion blocks (model.py:383-405), BN folded into the conv weights (eval mode) -------------------------------
+  bf16 *tA = aptr<bf16>(c, "tA"), *tB = aptr<bf16>(c, "tB"), *tC = aptr<bf16>(c, "tC"), *tD = aptr<bf16>(c, "tD");
+  const char* pname[5] = {"p1", "p1", "p2", "p3", "p4"};    // output of refinenet k is p_k (index by k)
+  for (int k = 4; k >= 1; --k) {
+    const std::string rk = "head.ref" + std::to_string(k) + ".";
+    const int Rk = R[k];
+    bf16* lk = aptr<bf16>(c, "l" + std::to_string(k));
+    bf16* lkr = aptr<bf16>(c, "l" + std::to_string(k) + "r");
+    const bf16* sum_in;       // input of resConfUnit2 and its relu'd copy
+    const bf16* sum_in_relu;
+    if (k == 4) {             // refinenet4 is called with one input: resConfUnit1 unused
+      sum_in = lk;
+      sum_in_relu = lkr;
+    } else {
+      // output = p_{k+1} + resConfUnit1(l_k):   a = relu(bn1(conv1(relu(l_k))));  s = bn2(conv2(a)) + l_k + p_{k+1}
+      if (!add_conv3x3<256, 8>(c, rk + "rcu1.c1", lkr, Rk, Rk, 256, rk + "rcu1.c1.w", 256,
+                               conv_epi(tA, nullptr, wptr<float>(c, rk + "rcu1.c1.b"), nullptr, nullptr, 1, 256, Rk, Rk)))
+        return false;
+      if (!add_conv3x3<256, 8>(c, rk + "rcu1.c2", tA, Rk, Rk, 256, rk + "rcu1.c2.w", 256,
+                               conv_epi(tB, tC, wptr<float>(c, rk + "rcu1.c2.b"), lk, aptr<bf16>(c, pname[k + 1]), 0, 256, Rk, Rk)))
+        return false;
+      sum_in = tB;
+      sum_in_relu = tC;
+    }
+    // resConfUnit2
+    if (!add_conv3x3<256, 8>(c, rk + "rcu2.c1", sum_in_relu, Rk, Rk, 256, rk + "rcu2.c1.w", 256,
+                             conv_epi(tA, nullptr, wptr<float>(c, rk + "rcu2.c1.b"), nullptr, nullptr, 1, 256, Rk, Rk)))
+      return false;
+    if (!add_conv3x3<256, 8>(c, rk + "rcu2.c2", tA, Rk, Rk, 256, rk + "rcu2.c2.w", 256,
+                             conv_epi(tD, nullptr, wptr<float>(c, rk + "rcu2.c2.b"), sum_in, nullptr, 0, 256, Rk, Rk)))
+      return false;
+    // out_conv (1x1) at low resolution, then 2x bilinear up-sampling
+    {
+      EpiConv::Params e = conv_epi(tA, nullptr, wptr<float>(c, rk + "out.b"), nullptr, nullptr, 0, 256, Rk, Rk);
+      e.linear = 1; e.hin = Rk; e.win = Rk;
+      if (!add_linear<256, EpiConv, 8>(c, rk + "out_conv", tD, static_cast<uint64_t>(mb) * Rk * Rk, Rk * Rk, 256,
+                                       wptr<bf16>(c, rk + "out.w"), 256, e))
+        return false;
+    }
+    {
+      bf16* pk = aptr<bf16>(c, pname[k]);
+      float* pool = (k == 1) ? aptr<float>(c, "pool") : nullptr;
+      const int pb = c->pool_blocks;
+      c->plan.emplace_back(rk + "upsample", [=](int nb, int, float*, float*, cudaStream_t st) {
+        return launch_upsample2x(tA, pk, pool, pb, nb, Rk, Rk, sms, st);
+      });
+    }
+  }
+  // ---- IoU head (model.py:185-191)
+  {
+    const float* pool = aptr<float>(c, "pool");
+    const int pb = c->pool_blocks;
+    const float inv = 1.0f / (static_cast<float>(R0) * R0);
+    const float *w1 = wptr<float>(c, "head.cls.w1"), *b1 = wptr<float>(c, "head.cls.b1");
+    const float *w2 = wptr<float>(c, "head.cls.w2"), *b2 = wptr<float>(c, "head.cls.b2");
+    c->plan.emplace_back("head.iou", [=](int nb, int b0, float*, float* io, cudaStream_t st) {
+      return launch_iou_head(pool, pb, inv, w1, b1, w2, b2, io + static_cast<size_t>(b0) * K, K, nb, st);
+    });
+  }
+  // ---- mask head (model.py:455-467)
+  bf16 *p1 = aptr<bf16>(c, "p1"), *mh1 = aptr<bf16>(c, "mh1"), *feat0 = aptr<bf16>(c, "feat0"), *feat = aptr<bf16>(c, "feat");
+  if (!add_conv3x3<128, 8>(c, "head.mh.c1", p1, R0, R0, 256, "head.mh.c1.w", 128,
+                           conv_epi(mh1, nullptr, wptr<float>(c, "head.mh.c1.b"), nullptr, nullptr, 0, 128, R0, R0)))
+    return false;
+  {
+    CUtensorMap ta;
+    if (!tmap_nhwc(&ta, mh1, mb, R0, R0, 128)) return false;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        EpiConv::Params e = conv_epi(feat0, nullptr, wptr<float>(c, "head.mh.up.b"), nullptr, nullptr, 1, 64, S, S);
+        e.up = 2; e.ph_h = a; e.ph_w = b;
+        if (!add_conv<64, EpiConv, 4>(c, "head.mh.up." + std::to_string(a) + std::to_string(b), ta, geom_convt_phase(R0, R0, 128, a, b),
+                                      wptr<bf16>(c, "head.mh.up.w"), 4 * 64, (a * 2 + b) * 64, 4 * 128, 64, e))
+          return false;
+      }
+  }
+  {
+    CUtensorMap ta;
+    if (!tmap_nhwc(&ta, feat0, mb, S, S, 64)) return false;
+    if (!add_conv<64, EpiConv, 4>(c, "head.mh.c2", ta, geom_3x3(S, S, 64), wptr<bf16>(c, "head.mh.c2.w"), 64, 0, 9 * 64, 64,
+                                  conv_epi(feat, nullptr, wptr<float>(c, "head.mh.c2.b"), nullptr, nullptr, 1, 64, S, S)))
+      return false;
+  }
+  {
+    CUtensorMap ta;
+    if (!tmap_nhwc(&ta, feat, mb, S, S, 64)) return false;
+    EpiMask::Params e{nullptr, wptr<float>(c, "head.mh.heads.b"), wptr<float>(c, "head.mh.heads.w2"), wptr<float>(c, "head.mh.heads.b2"), S, K};
+    auto patch = [S, K](EpiMask::Params& q, int, int b0, float* mo, float*) { q.out = mo + static_cast<size_t>(b0) * K * S * S; };
+    bool r;
+    if (K == 3)
+      r = add_conv<96, EpiMask, 4>(c, "head.mh.heads", ta, geom_3x3(S, S, 64), wptr<bf16>(c, "head.mh.heads.w"), 96, 0, 9 * 64, 96, e, patch);
+    else
+      r = add_conv<32, EpiMask, 4>(c, "head.mh.heads", ta, geom_3x3(S, S, 64), wptr<bf16>(c, "head.mh.heads.w"), 32, 0, 9 * 64, 32, e, patch);
+    if (!r) return false;
+  }
+  return true;
+}
+
+std::vector<std::string> required_tensors(const s3od_ctx* c) {
+  std::vector<std::string> r = {"patch.w", "patch.b", "prefix", "rope.cos", "rope.sin", "pre.lut"};
+  for (int l = 0; l < c->L; ++l) {
+    const std::string p = "enc." + std::to_string(l) + ".";
+    for (const char* s : {"ln1.w", "ln1.b", "qkv.w", "qkv.b", "o.w", "o.b", "ls1", "ln2.w", "ln2.b", "up.w", "up.b", "down.w", "down.b", "ls2"})
+      r.push_back(p + s);
+  }
+  for (int j = 0; j < 4; ++j) {
+    r.push_back("head.proj" + std::to_string(j) + ".w");
+    r.push_back("head.proj" + std::to_string(j) + ".b");
+    r.push_back("head.rn" + std::to_string(j + 1) + ".w");
+  }
+  for (const char* s : {"head.rs0.w", "head.rs0.b", "head.rs1.w", "head.rs1.b", "head.rs3.w", "head.rs3.b", "head.mh.c1.w", "head.mh.c1.b",
+                        "head.mh.up.w", "head.mh.up.b", "head.mh.c2.w", "head.mh.c2.b", "head.mh.heads.w", "head.mh.heads.b",
+                        "head.mh.heads.w2", "head.mh.heads.b2", "head.cls.w1", "head.cls.b1", "head.cls.w2", "head.cls.b2"})
+    r.push_back(s);
+  for (int k = 1; k <= 4; ++k) {
+    const std::string p = "head.ref" + std::to_string(k) + ".";
+    r.push_back(p + "out.w");
+    r.push_back(p + "out.b");
+    for (int u = (k == 4 ? 2 : 1); u <= 2; ++u)
+      for (int cc = 1; cc <= 2; ++cc) {
+        r.push_back(p + "rcu" + std::to_string(u) + ".c" + std::to_string(cc) + ".w");
+        r.push_back(p + "rcu" + std::to_string(u) + ".c" + std::to_string(cc) + ".b");
+      }
+  }
+  return r;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* s3od_last_error(void) { return g_err.c_str(); }
+const char* s3od_version(void) { return "s3od_b200 0.1 (sm_100a)"; }
+
+int s3od_create(s3od_ctx** out, int device, int arch, int num_outputs, int image_size, int max_batch, int micro_batch) {
+  if (out == nullptr) return fail(S3OD_ERR_ARG, "ctx out pointer is null");
+  if (arch != S3OD_ARCH_VITB && arch != S3OD_ARCH_VITL) return fail(S3OD_ERR_ARG, "unknown arch");
+  if (num_outputs != 1 && num_outputs != 3) return fail(S3OD_ERR_ARG, "num_outputs must be 1 or 3");
+  if (image_size < 32 || image_size % 32 != 0) return fail(S3OD_ERR_ARG, "image_size must be a positive multiple of 32");
+  if (max_batch < 1 || micro_batch < 1) return fail(S3OD_ERR_ARG, "batch sizes must be >= 1");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(S3OD_ERR_STATE, std::string("s3od_b200 needs an sm_100 GPU, found ") + prop.name);
+  s3od_ctx* c = new s3od_ctx();
+  c->device = device; c->arch = arch; c->K = num_outputs; c->S = image_size;
+  c->max_batch = max_batch; c->mb = micro_batch < max_batch ? micro_batch : max_batch;
+  c->g = image_size / 16; c->P = c->g * c->g; c->ntok = c->P + 5;
+  c->vt_pitch = (c->ntok + 7) & ~7;
+  if (arch == S3OD_ARCH_VITB) {
+    c->D = 768; c->H = 12; c->I = 3072; c->L = 11;
+    const int t[4] = {2, 5, 8, 11};
+    memcpy(c->taps, t, sizeof(t));
+  } else {
+    c->D = 1024; c->H = 16; c->I = 4096; c->L = 23;
+    const int t[4] = {4, 11, 17, 23};
+    memcpy(c->taps, t, sizeof(t));
+  }
+  c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  return S3OD_OK;
+}
+
+int s3od_set_tensor(s3od_ctx* c, const char* name, const void* host_data, size_t bytes) {
+  if (c == nullptr || name == nullptr || host_data == nullptr || bytes == 0) return fail(S3OD_ERR_ARG, "bad argument to s3od_set_tensor");
+  if (c->finalized) return fail(S3OD_ERR_STATE, "context already finalized");
+  CK(cudaSetDevice(c->device));
+  void* p = nullptr;
+  CK(cudaMalloc(&p, (bytes + 255) & ~size_t(255)));
+  CK(cudaMemcpy(p, host_data, bytes, cudaMemcpyHostToDevice));
+  auto it = c->w.find(name);
+  if (it != c->w.end()) cudaFree(it->second.p);
+  c->w[name] = DevBuf{p, bytes};
+  return S3OD_OK;
+}
+
+int s3od_finalize(s3od_ctx* c) {
+  if (c == nullptr) return fail(S3OD_ERR_ARG, "null ctx");
+  if (c->finalized) return S3OD_OK;
+  CK(cudaSetDevice(c->device));
+  for (const std::string& n : required_tensors(c))
+    if (c->w.find(n) == c->w.end()) return fail(S3OD_ERR_MISSING, "missing tensor: " + n);
+  CK(cudaMalloc(reinterpret_cast<void**>(&c->d_img), sizeof(ImageDesc) * c->max_batch));
+  CK(cudaMalloc(reinterpret_cast<void**>(&c->d_post), sizeof(PostDesc) * c->max_batch));
+  if (!build_plan(c)) return S3OD_ERR_CUDA;
+  c->finalized = true;
+  return S3OD_OK;
+}
+
+static_assert(sizeof(s3od_image) == sizeof(ImageDesc), "s3od_image must mirror ImageDesc");
+static_assert(sizeof(s3od_post) == sizeof(PostDesc), "s3od_post must mirror PostDesc");
+
+int s3od_preprocess_u8(s3od_ctx* c, const s3od_image* images, int batch, s3od_stream stream) {
+  if (c == nullptr || !c->finalized) return fail(S3OD_ERR_STATE, "context not finalized");
+  if (images == nullptr || batch < 1 || batch > c->max_batch) return fail(S3OD_ERR_ARG, "bad batch for s3od_preprocess_u8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaMemcpyAsync(c->d_img, images, sizeof(ImageDesc) * batch, cudaMemcpyHostToDevice, st));
+  CK(launch_preprocess(c->d_img, wptr<bf16>(c, "pre.lut"), aptr<bf16>(c, "patches"), c->S, batch, st));
+  c->launches += 1;
+  return S3OD_OK;
+}
+
+int s3od_pack_input_f32(s3od_ctx* c, const float* d_x, int batch, s3od_stream stream) {
+  if (c == nullptr || !c->finalized) return fail(S3OD_ERR_STATE, "context not finalized");
+  if (d_x == nullptr || batch < 1 || batch > c->max_batch) return fail(S3OD_ERR_ARG, "bad batch for s3od_pack_input_f32");
+  CK(launch_pack_input(d_x, aptr<bf16>(c, "patches"), c->S, batch, static_cast<cudaStream_t>(stream)));
+  c->launches += 1;
+  return S3OD_OK;
+}
+
+int s3od_forward(s3od_ctx* c, int batch, float* d_mask_logits, float* d_iou_logits, s3od_stream stream) {
+  if (c == nullptr || !c->finalized) return fail(S3OD_ERR_STATE, "context not finalized");
+  if (batch < 1 || batch > c->max_batch || d_mask_logits == nullptr || d_iou_logits == nullptr)
+    return fail(S3OD_ERR_ARG, "bad argument to s3od_forward");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int b0 = 0; b0 < batch; b0 += c->mb) {
+    const int nb = std::min(c->mb, batch - b0);
+    for (auto& op : c->plan) {
+      cudaError_t e = op.second(nb, b0, d_mask_logits, d_iou_logits, st);
+      if (e != cudaSuccess) return fail(S3OD_ERR_CUDA, "launch of '" + op.first + "' failed: " + cudaGetErrorString(e));
+      c->launches += 1;
+    }
+    c->last_nb = nb;
+  }
+  return S3OD_OK;
+}
+
+int s3od_postprocess(s3od_ctx* c, const float* d_mask_logits, const float* d_iou_logits, const s3od_post* images, int batch,
+                     float* d_ious, int32_t* d_best_idx, s3od_stream stream) {
+  if (c == nullptr || !c->finalized) return fail(S3OD_ERR_STATE, "context not finalized");
+  if (images == nullptr || batch < 1 || batch > c->max_batch || d_mask_logits == nullptr || d_iou_logits == nullptr ||
+      d_ious == nullptr || d_best_idx == nullptr)
+    return fail(S3OD_ERR_ARG, "bad argument to s3od_postprocess");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int maxH = 0, maxW = 0;
+  for (int i = 0; i < batch; ++i) {
+    maxH = std::max(maxH, images[i].H);
+    maxW = std::max(maxW, images[i].W);
+  }
+  CK(cudaMemcpyAsync(c->d_post, images, sizeof(PostDesc) * batch, cudaMemcpyHostToDevice, st));
+  CK(launch_postprocess(c->d_post, d_mask_logits, d_iou_logits, d_ious, d_best_idx, c->S, c->K, batch, maxH, maxW, st));
+  c->launches += 1;
+  return S3OD_OK;
+}
+
+int s3od_get_stage(s3od_ctx* c, const char* name, void** d_ptr, size_t* bytes) {
+  if (c == nullptr || name == nullptr || d_ptr == nullptr || bytes == nullptr) return fail(S3OD_ERR_ARG, "bad argument to s3od_get_stage");
+  auto it = c->act.find(name);
+  if (it == c->act.end()) return fail(S3OD_ERR_MISSING, std::string("unknown stage: ") + name);
+  *d_ptr = it->second.p;
+  *bytes = it->second.bytes;
+  return S3OD_OK;
+}
+
+int s3od_read_stage(s3od_ctx* c, const char* name, void* d_dst, size_t bytes, s3od_stream stream) {
+  if (c == nullptr || name == nullptr || d_dst == nullptr) return fail(S3OD_ERR_ARG, "bad argument to s3od_read_stage");
+  auto it = c->act.find(name);
+  if (it == c->act.end()) return fail(S3OD_ERR_MISSING, std::string("unknown stage: ") + name);
+  if (bytes > it->second.bytes) return fail(S3OD_ERR_ARG, std::string("stage ") + name + " is smaller than the requested size");
+  CK(cudaMemcpyAsync(d_dst, it->second.p, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
+long long s3od_launch_count(s3od_ctx* c) { return c == nullptr ? 0 : c->launches; }
+
+void s3od_destroy(s3od_ctx* c) {
+  if (c == nullptr) return;
+  cudaSetDevice(c->device);
+  for (auto& kv : c->w) cudaFree(kv.second.p);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->d_img) cudaFree(c->d_img);
+  if (c->d_post) cudaFree(c->d_post);
+  delete c;
+}
+
+// ------------------------------------------------------------------------------------------ kernel-level entry points
+int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream) {
+  if (N % 128 != 0 || K % 64 != 0 || M < 1) return fail(S3OD_ERR_ARG, "s3od_op_gemm_f32 needs N % 128 == 0 and K % 64 == 0");
+  GemmParams<EpiStoreF32> p{};
+  if (!tmap_matrix(&p.tma_a, d_a, M, K, kBM)) return S3OD_ERR_CUDA;
+  if (!tmap_matrix(&p.tma_b, d_b, N, K, 128)) return S3OD_ERR_CUDA;
+  p.M = M; p.m_tiles = (M + kBM - 1) / kBM; p.n_tiles = N / 128; p.num_k_blocks = K / 64;
+  p.epi = EpiStoreF32::Params{d_c, N};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK((launch_gemm<128, A_LINEAR, EpiStoreF32, 8>(p, sms, static_cast<cudaStream_t>(stream))));
+  return S3OD_OK;
+}
+
+int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void* d_y, int M, int D, float eps, s3od_stream stream) {
+  CK(launch_layernorm(d_x, d_w, d_b, static_cast<bf16*>(d_y), M, D, eps, static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
+int s3od_op_attention(const void* d_q, const void* d_k, const void* d_vt, void* d_out, int batch, int heads, int ntok, int vt_pitch,
+                      s3od_stream stream) {
+  if (vt_pitch % 8 != 0 || vt_pitch < ntok) return fail(S3OD_ERR_ARG, "vt_pitch must be a multiple of 8 and >= ntok");
+  AttnParams ap{};
+  const uint64_t BH = static_cast<uint64_t>(batch) * heads;
+  const uint64_t dq[3] = {64, (uint64_t)ntok, BH};
+  const uint64_t sq[2] = {128, (uint64_t)ntok * 128};
+  const uint32_t bq[3] = {64, 128, 1};
+  if (!make_tmap(&ap.tma_q, d_q, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
+  if (!make_tmap(&ap.tma_k, d_k, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
+  const uint64_t dv[3] = {(uint64_t)ntok, 64, BH};
+  const uint64_t sv[2] = {(uint64_t)vt_pitch * 2, (uint64_t)vt_pitch * 2 * 64};
+  const uint32_t bv[3] = {64, 64, 1};
+  if (!make_tmap(&ap.tma_vt, d_vt, 3, dv, sv, bv)) return S3OD_ERR_CUDA;
+  ap.out = static_cast<bf16*>(d_out);
+  ap.ntok = ntok; ap.heads = heads; ap.kv_tiles = (ntok + 127) / 128;
+  CK(launch_attention(ap, (ntok + 127) / 128, static_cast<int>(BH), static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
+int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin, int cout,
+                    int relu, s3od_stream stream) {
+  if (cin % 64 != 0 || cout % 256 != 0) return fail(S3OD_ERR_ARG, "s3od_op_conv3x3 needs cin % 64 == 0 and cout % 256 == 0");
+  GemmParams<EpiConv> p{};
+  if (!tmap_nhwc(&p.tma_a, d_in, batch, h, w, cin)) return S3OD_ERR_CUDA;
+  if (!tmap_matrix(&p.tma_b, d_w, cout, 9 * cin, 256)) return S3OD_ERR_CUDA;
+  p.geom = geom_3x3(h, w, cin);
+  p.m_tiles = batch * p.geom.tiles_h * p.geom.tiles_w;
+  p.n_tiles = cout / 256;
+  p.num_k_blocks = 9 * cin / 64;
+  p.epi = conv_epi(static_cast<bf16*>(d_out), nullptr, d_bias, nullptr, nullptr, relu, cout, h, w);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK((launch_gemm<256, A_CONV, EpiConv, 8>(p, sms, static_cast<cudaStream_t>(stream))));
+  return S3OD_OK;
+}
+
+}  // extern "C"

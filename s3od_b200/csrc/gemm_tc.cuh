@@ -1,0 +1,558 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M, N] = A[M, K] * B[N, K]^T     bf16 operands, fp32 accumulation in TMEM, fused epilogue.
+//
+// One CTA per SM walks output tiles (128 x BN) round-robin.  Roles:
+//   warp 0 (one lane)  TMA producer : A and B k-blocks (64 bf16 = one 128B-swizzle row) into a STAGES-deep ring
+//   warp 1 (one lane)  MMA issuer   : tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM
+//   warp 2             TMEM allocator
+//   warps 4..          epilogue     : tcgen05.ld -> registers -> fused epilogue functor -> global
+// The A operand is either a plain row-major matrix (A_LINEAR: tokens x channels, NHWC pixels x channels) or an
+// implicit im2col view of an NHWC activation (A_CONV): every k-block is one filter tap x 64 input channels and
+// is fetched as a shifted 8 x 16 pixel box through a 5-D tensor map; out-of-bounds pixels are zero-filled by
+// the TMA unit, which is exactly the convolution's zero padding.
+#pragma once
+#include "common.cuh"
+
+namespace s3od {
+
+constexpr int kBM = 128;            // tile rows (UMMA M)
+constexpr int kBK = 64;             // k-block: 64 bf16 = 128 bytes = one swizzle row
+constexpr int kTileH = 8;           // conv M tile = 8 x 16 output pixels
+constexpr int kTileW = 16;
+constexpr int kMaxTaps = 9;
+
+enum AMode { A_LINEAR = 0, A_CONV = 1 };
+
+// Geometry of the implicit-GEMM A operand.  The activation is addressed through a 5-D tensor map
+// (dim0 = channels', dim1 = W', dim2 = P, dim3 = H', dim4 = batch); for a plain NHWC tensor P = 1.
+// The stride-2 3x3 convolution views the input as (2C, W/2, 2, H/2, B) so that tap offsets stay unit-stride.
+struct ConvGeom {
+  int H, W;                  // output grid walked by the M tiles (per image)
+  int tiles_h, tiles_w;      // ceil(H / 8), ceil(W / 16)
+  int cin_blocks;            // Cin / 64
+  int ntaps;
+  int dc[kMaxTaps];          // per-tap start in dim0 (channel offset)
+  int dw[kMaxTaps];          // per-tap offset in dim1
+  int dp[kMaxTaps];          // per-tap index  in dim2
+  int dh[kMaxTaps];          // per-tap offset in dim3
+};
+
+// Where an accumulator row lives in the problem.
+struct RowInfo {
+  int gm;        // A_LINEAR: global row index;  A_CONV: unused
+  int b, h, w;   // A_CONV: image, output row / col
+  bool valid;
+};
+
+template <class Epi>
+struct GemmParams {
+  CUtensorMap tma_a;
+  CUtensorMap tma_b;
+  int M;                 // A_LINEAR: valid rows
+  int m_tiles, n_tiles;  // tile grid
+  int num_k_blocks;      // K / 64   (A_CONV: ntaps * cin_blocks)
+  int b_row_offset;      // first row of B used by this launch (sub-pixel phases share one weight tensor)
+  int a_row_offset;      // A_LINEAR: first row of A used by this launch (micro-batch window into a larger buffer)
+  ConvGeom geom;
+  typename Epi::Params epi;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  // TMEM columns per accumulator stage (power of two so every stage starts on an aligned column)
+  static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr uint32_t kTmemCols = 2 * kAccStride < 32 ? 32 : 2 * kAccStride;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int AMODE, class Epi, int EPI_WARPS>
+__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
+  using Cfg = GemmCfg<BN>;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+  static_assert(Cfg::kBBytes % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                          // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + Cfg::kStages;          // [kStages]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;             // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 32 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.n_tiles;
+        const int n_blk = tile % p.n_tiles;
+        int cb = 0, h0 = 0, w0 = 0;
+        if (AMODE == A_CONV) {
+          const int per_img = p.geom.tiles_h * p.geom.tiles_w;
+          cb = m_blk / per_img;
+          const int r = m_blk % per_img;
+          h0 = (r / p.geom.tiles_w) * kTileH;
+          w0 = (r % p.geom.tiles_w) * kTileW;
+        }
+        int tap = 0, cblk = 0;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          if (AMODE == A_LINEAR) {
+            tma_load_2d(sA + stage * Cfg::kABytes, &p.tma_a, &full[stage], kb * kBK, p.a_row_offset + m_blk * kBM);
+          } else {
+            tma_load_5d(sA + stage * Cfg::kABytes, &p.tma_a, &full[stage], p.geom.dc[tap] + cblk * kBK,
+                        w0 + p.geom.dw[tap], p.geom.dp[tap], h0 + p.geom.dh[tap], cb);
+            if (++cblk == p.geom.cin_blocks) {
+              cblk = 0;
+              ++tap;
+            }
+          }
+          tma_load_2d(sB + stage * Cfg::kBBytes, &p.tma_b, &full[stage], kb * kBK, p.b_row_offset + n_blk * BN);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_sdesc_sw128(smem_u32(sA + stage * Cfg::kABytes));
+          const uint64_t b_desc = make_sdesc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes (2 x 16B units) per 16-element K step inside the 128B swizzle row
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == p.num_k_blocks - 1) umma_commit(&acc_full[acc]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;
+    const int quad = ew & 3;                               // TMEM lane quarter this warp may read (== warp % 4)
+    constexpr int kGroups = EPI_WARPS / 4;
+    constexpr int kColsPerGroup = BN / kGroups;
+    const int col_begin = (ew >> 2) * kColsPerGroup;
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.n_tiles;
+      const int n_blk = tile % p.n_tiles;
+      RowInfo ri;
+      if (AMODE == A_LINEAR) {
+        ri.gm = m_blk * kBM + row;
+        ri.b = ri.h = ri.w = 0;
+        ri.valid = ri.gm < p.M;
+      } else {
+        const int per_img = p.geom.tiles_h * p.geom.tiles_w;
+        ri.b = m_blk / per_img;
+        const int r = m_blk % per_img;
+        ri.h = (r / p.geom.tiles_w) * kTileH + row / kTileW;
+        ri.w = (r % p.geom.tiles_w) * kTileW + row % kTileW;
+        ri.gm = 0;
+        ri.valid = ri.h < p.geom.H && ri.w < p.geom.W;
+      }
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::kAccStride + col_begin;
+      Epi::template run<kColsPerGroup>(p.epi, ri, n_blk * BN + col_begin, taddr);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ================================================================================================
+// Epilogue functors.  run<NCOLS>(params, row, n0, taddr): this thread owns accumulator row `row`, columns
+// [n0, n0 + NCOLS) of the output, readable from TMEM at taddr (+column offset).
+// All tcgen05.ld are warp-collective, so every lane executes them even when its row is out of range.
+// ================================================================================================
+
+S3OD_DEVICE void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    d[i] = u;
+  }
+}
+S3OD_DEVICE void load_bf16x32(const __nv_bfloat16* src, float (&v)[32]) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = s[i];
+    v[8 * i + 0] = bf16_lo(u.x); v[8 * i + 1] = bf16_hi(u.x);
+    v[8 * i + 2] = bf16_lo(u.y); v[8 * i + 3] = bf16_hi(u.y);
+    v[8 * i + 4] = bf16_lo(u.z); v[8 * i + 5] = bf16_hi(u.z);
+    v[8 * i + 6] = bf16_lo(u.w); v[8 * i + 7] = bf16_hi(u.w);
+  }
+}
+S3OD_DEVICE void add_vec32(const float* __restrict__ src, float (&v)[32]) {
+  const float4* s = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = __ldg(s + i);
+    v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+  }
+}
+
+// ---- patch embedding: x[b, 5 + p, :] = acc + bias   (HF:75-92; the 5 prefix rows are filled by fill_prefix_kernel)
+struct EpiPatch {
+  struct Params {
+    float* x;            // [B * ntok, D] fp32 residual stream
+    const float* bias;   // [D]
+    int npatch, ntok, D;
+  };
+  template <int NCOLS>
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+    const int b = ri.gm / e.npatch, pi = ri.gm % e.npatch;
+    float* dst = e.x + (static_cast<size_t>(b) * e.ntok + 5 + pi) * e.D + n0;
+#pragma unroll 1
+    for (int c = 0; c < NCOLS; c += 32) {
+      float v[32];
+      tmem_ld_f32x32(taddr + c, v);
+      if (ri.valid) {
+        add_vec32(e.bias + n0 + c, v);
+        float4* d4 = reinterpret_cast<float4*>(dst + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  }
+};
+
+// ---- fused q/k/v projection: + bias, RoPE on the patch rows of q and k (HF:238-268), softmax scale folded into q,
+//      head-major stores: Q,K [B*H, ntok, 64], V transposed [B*H, 64, vt_pitch] (K-major B operand of P.V)
+struct EpiQKV {
+  struct Params {
+    __nv_bfloat16* q;
+    __nv_bfloat16* k;
+    __nv_bfloat16* vt;
+    const float* bias;      // [3D], k part zero (config.json: key_bias=false)
+    const float* rope_cos;  // [npatch, 32]
+    const float* rope_sin;  // [npatch, 32]
+    int ntok, heads, D, vt_pitch;
+    float qscale;           // head_dim^-0.5 * log2(e)
+  };
+  template <int NCOLS>
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+    static_assert(NCOLS % 64 == 0, "a thread must own whole heads for RoPE");
+    const int b = ri.gm / e.ntok, t = ri.gm % e.ntok;
+#pragma unroll 1
+    for (int c = 0; c < NCOLS; c += 64) {
+      float lo[32], hi[32];
+      tmem_ld_f32x32(taddr + c, lo);
+      tmem_ld_f32x32(taddr + c + 32, hi);
+      if (ri.valid) {
+        const int n = n0 + c;
+        const int which = n / e.D;
+        const int head = (n % e.D) >> 6;
+        add_vec32(e.bias + n, lo);
+        add_vec32(e.bias + n + 32, hi);
+        const size_t bh = static_cast<size_t>(b) * e.heads + head;
+        if (which == 2) {
+          __nv_bfloat16* dst = e.vt + bh * 64 * e.vt_pitch + t;
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            dst[static_cast<size_t>(i) * e.vt_pitch] = __float2bfloat16_rn(lo[i]);
+            dst[static_cast<size_t>(i + 32) * e.vt_pitch] = __float2bfloat16_rn(hi[i]);
+          }
+        } else {
+          if (t >= 5) {
+            const float4* cs = reinterpret_cast<const float4*>(e.rope_cos + static_cast<size_t>(t - 5) * 32);
+            const float4* sn = reinterpret_cast<const float4*>(e.rope_sin + static_cast<size_t>(t - 5) * 32);
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 c4 = __ldg(cs + i), s4 = __ldg(sn + i);
+              const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float a = lo[4 * i + j], bb = hi[4 * i + j];
+                lo[4 * i + j] = a * cc[j] - bb * ss[j];     // x*cos + (-x2)*sin
+                hi[4 * i + j] = bb * cc[j] + a * ss[j];     // x*cos + ( x1)*sin
+              }
+            }
+          }
+          if (which == 0) {
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) { lo[i] *= e.qscale; hi[i] *= e.qscale; }
+          }
+          __nv_bfloat16* dst = (which == 0 ? e.q : e.k) + (bh * e.ntok + t) * 64;
+          store_bf16x32(dst, lo);
+          store_bf16x32(dst + 32, hi);
+        }
+      }
+    }
+  }
+};
+
+// ---- o_proj / down_proj: x += lambda * (acc + bias)  (LayerScale + residual, HF:440-441, 447-448);
+//      optionally also emits the bf16 tap (patch rows only) that the DPT head reads (model.py:72-84)
+struct EpiResidual {
+  struct Params {
+    float* x;             // [M, D] fp32, read-modify-write
+    const float* bias;    // [D]
+    const float* lambda;  // [D]
+    __nv_bfloat16* tap;   // [B * npatch, D] or nullptr
+    int ntok, npatch, D;
+  };
+  template <int NCOLS>
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+    float* xr = e.x + static_cast<size_t>(ri.gm) * e.D + n0;
+    const int b = ri.gm / e.ntok, t = ri.gm % e.ntok;
+#pragma unroll 1
+    for (int c = 0; c < NCOLS; c += 32) {
+      float v[32];
+      tmem_ld_f32x32(taddr + c, v);
+      if (ri.valid) {
+        add_vec32(e.bias + n0 + c, v);
+        const float4* l4 = reinterpret_cast<const float4*>(e.lambda + n0 + c);
+        float4* x4 = reinterpret_cast<float4*>(xr + c);
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 l = __ldg(l4 + i);
+          float4 xv = x4[i];
+          xv.x = fmaf(v[4 * i + 0], l.x, xv.x);
+          xv.y = fmaf(v[4 * i + 1], l.y, xv.y);
+          xv.z = fmaf(v[4 * i + 2], l.z, xv.z);
+          xv.w = fmaf(v[4 * i + 3], l.w, xv.w);
+          x4[i] = xv;
+          v[4 * i + 0] = xv.x; v[4 * i + 1] = xv.y; v[4 * i + 2] = xv.z; v[4 * i + 3] = xv.w;
+        }
+        if (e.tap != nullptr && t >= 5) {
+          store_bf16x32(e.tap + (static_cast<size_t>(b) * e.npatch + (t - 5)) * e.D + n0 + c, v);
+        }
+      }
+    }
+  }
+};
+
+// ---- up_proj: out = gelu_erf(acc + bias) in bf16  (HF:385-386, hidden_act "gelu" = exact erf form)
+struct EpiGelu {
+  struct Params {
+    __nv_bfloat16* out;   // [M, ld]
+    const float* bias;
+    int ld;
+  };
+  template <int NCOLS>
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+    __nv_bfloat16* dst = e.out + static_cast<size_t>(ri.gm) * e.ld + n0;
+#pragma unroll 1
+    for (int c = 0; c < NCOLS; c += 32) {
+      float v[32];
+      tmem_ld_f32x32(taddr + c, v);
+      if (ri.valid) {
+        add_vec32(e.bias + n0 + c, v);
+  #pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        store_bf16x32(dst + c, v);
+      }
+    }
+  }
+};
+
+// ---- convolution / 1x1 / transposed-conv epilogue, NHWC bf16 output:
+//      out = [relu](acc + bias + res1 + res2); optional second tensor with relu(out) (input of the next RCU conv).
+//      `up` > 1 scatters sub-pixel phases of a transposed convolution (depth-to-space):
+//        A_LINEAR (k == stride ConvT as one GEMM): phase = n / cout, (a, b) = divmod(phase, up)
+//        A_CONV   (k4 s2 p1 ConvT, one launch per phase): (a, b) = (ph_h, ph_w)
+struct EpiConv {
+  struct Params {
+    __nv_bfloat16* out;
+    __nv_bfloat16* out_relu;      // nullable
+    const float* bias;            // nullable, [cout]
+    const __nv_bfloat16* res1;    // nullable, same layout as out
+    const __nv_bfloat16* res2;    // nullable
+    int relu;
+    int linear;                   // 1: rows are pixels of a (B, hin, win) grid
+    int hin, win;
+    int up, ph_h, ph_w;
+    int cout, oh, ow;             // output tensor (B, oh, ow, cout)
+  };
+  template <int NCOLS>
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+    int b, h, w, a = e.ph_h, bb = e.ph_w, ch = n0;
+    if (e.linear) {
+      const int per = e.hin * e.win;
+      b = ri.gm / per;
+      const int r = ri.gm % per;
+      h = r / e.win;
+      w = r % e.win;
+      if (e.up > 1) {
+        const int phase = n0 / e.cout;
+        ch = n0 % e.cout;
+        a = phase / e.up;
+        bb = phase % e.up;
+      }
+    } else {
+      b = ri.b; h = ri.h; w = ri.w;
+    }
+    const size_t pix = (static_cast<size_t>(b) * e.oh + (h * e.up + a)) * e.ow + (w * e.up + bb);
+    const size_t off = pix * e.cout + ch;
+#pragma unroll 1
+    for (int c = 0; c < NCOLS; c += 32) {
+      float v[32];
+      tmem_ld_f32x32(taddr + c, v);
+      if (ri.valid) {
+        if (e.bias != nullptr) add_vec32(e.bias + ch + c, v);
+        if (e.res1 != nullptr) {
+          float r[32];
+          load_bf16x32(e.res1 + off + c, r);
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += r[i];
+        }
+        if (e.res2 != nullptr) {
+          float r[32];
+          load_bf16x32(e.res2 + off + c, r);
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += r[i];
+        }
+        if (e.relu) {
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        store_bf16x32(e.out + off + c, v);
+        if (e.out_relu != nullptr) {
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          store_bf16x32(e.out_relu + off + c, v);
+        }
+      }
+    }
+  }
+};
+
+// ---- merged mask heads (model.py:438-453, 462-467): the K 3x3 convs (64->32) run as one N = 32K conv;
+//      here: ReLU, then each head's 1x1 (32 -> 1) as an in-register dot product; planar fp32 logits (B, K, S, S).
+struct EpiMask {
+  struct Params {
+    float* out;          // [B, K, S, S]
+    const float* bias;   // [32K]
+    const float* w2;     // [K, 32]
+    const float* b2;     // [K]
+    int S, K;
+  };
+  template <int NCOLS>
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+    (void)n0;
+#pragma unroll 1
+    for (int k = 0; k < NCOLS / 32; ++k) {
+      float v[32];
+      tmem_ld_f32x32(taddr + 32 * k, v);
+      if (ri.valid) {
+        add_vec32(e.bias + 32 * k, v);
+        float acc = __ldg(e.b2 + k);
+        const float4* w4 = reinterpret_cast<const float4*>(e.w2 + 32 * k);
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 wv = __ldg(w4 + i);
+          acc = fmaf(fmaxf(v[4 * i + 0], 0.0f), wv.x, acc);
+          acc = fmaf(fmaxf(v[4 * i + 1], 0.0f), wv.y, acc);
+          acc = fmaf(fmaxf(v[4 * i + 2], 0.0f), wv.z, acc);
+          acc = fmaf(fmaxf(v[4 * i + 3], 0.0f), wv.w, acc);
+        }
+        e.out[((static_cast<size_t>(ri.b) * e.K + k) * e.S + ri.h) * e.S + ri.w] = acc;
+      }
+    }
+  }
+};
+
+// ---- plain fp32 store (unit tests and the tiny classifier-free paths)
+struct EpiStoreF32 {
+  struct Params {
+    float* out;
+    int ld;
+  };
+  template <int NCOLS>
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+    float* dst = e.out + static_cast<size_t>(ri.gm) * e.ld + n0;
+#pragma unroll 1
+    for (int c = 0; c < NCOLS; c += 32) {
+      float v[32];
+      tmem_ld_f32x32(taddr + c, v);
+      if (ri.valid) {
+        float4* d4 = reinterpret_cast<float4*>(dst + c);
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  }
+};
+
+}  // namespace s3od

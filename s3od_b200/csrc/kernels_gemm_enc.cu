@@ -1,0 +1,9 @@
+// tcgen05 GEMM instantiations of the ViT encoder.
+#include "kernels_gemm_impl.cuh"
+namespace s3od {
+S3OD_INSTANTIATE_GEMM(256, A_LINEAR, EpiPatch, 8)
+S3OD_INSTANTIATE_GEMM(256, A_LINEAR, EpiQKV, 8)
+S3OD_INSTANTIATE_GEMM(256, A_LINEAR, EpiResidual, 8)
+S3OD_INSTANTIATE_GEMM(256, A_LINEAR, EpiGelu, 8)
+S3OD_INSTANTIATE_GEMM(128, A_LINEAR, EpiStoreF32, 8)
+}  // namespace s3od

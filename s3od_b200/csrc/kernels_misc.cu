@@ -1,0 +1,85 @@
+// Attention and bandwidth-bound kernel launchers.
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "launch.h"
+
+namespace s3od {
+
+cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  attention_kernel<<<dim3(q_tiles, bh), kAttnThreads, kAttnSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* y, int M, int D, float eps,
+                             cudaStream_t stream) {
+  const int rows_per_block = 8;
+  const int grid = (M + rows_per_block - 1) / rows_per_block;
+  if (D == 768)
+    layernorm_kernel<768><<<grid, 256, 0, stream>>>(x, w, b, y, M, eps);
+  else if (D == 1024)
+    layernorm_kernel<1024><<<grid, 256, 0, stream>>>(x, w, b, y, M, eps);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, __nv_bfloat16* patches, int S, int B,
+                              cudaStream_t stream) {
+  const int n = S * (S / 8);
+  preprocess_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(descs, lut, patches, S);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_input(const float* x, __nv_bfloat16* patches, int S, int B, cudaStream_t stream) {
+  const int n = 3 * S * (S / 8);
+  pack_input_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(x, patches, S);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_prefix(float* x, const float* prefix, int ntok, int D, int B, cudaStream_t stream) {
+  const int n = B * 5 * D;
+  fill_prefix_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x, prefix, ntok, D, B);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float* pool, int pool_blocks, int B, int h, int w,
+                              int num_sms, cudaStream_t stream) {
+  const int npix = 4 * h * w;
+  int blocks;
+  if (pool != nullptr) {
+    blocks = pool_blocks;
+  } else {
+    blocks = (npix + 63) / 64;                                   // >= 8 pixel steps per block
+    const int cap = (8 * num_sms + B - 1) / B;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+  }
+  upsample2x_kernel<256><<<dim3(blocks, B), 256, 0, stream>>>(in, out, pool, h, w);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, const float* w1, const float* b1, const float* w2,
+                            const float* b2, float* iou_logits, int K, int B, cudaStream_t stream) {
+  iou_head_kernel<<<B, 256, 0, stream>>>(pool, nblocks, inv_npix, w1, b1, w2, b2, iou_logits, K);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
+                               int* best_idx, int S, int K, int B, int maxH, int maxW, cudaStream_t stream) {
+  dim3 grid((maxW + 127) / 128, maxH, B);
+  if (K == 3)
+    postprocess_kernel<3><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+  else if (K == 1)
+    postprocess_kernel<1><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+}  // namespace s3od

@@ -1,0 +1,25 @@
+// Host-side launch declarations; kernels are instantiated in kernels_gemm_*.cu / kernels_misc.cu.
+#pragma once
+#include "gemm_tc.cuh"
+#include "types.h"
+
+namespace s3od {
+
+template <int BN, int AMODE, class Epi, int EPI_WARPS>
+cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stream);
+
+cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream);
+cudaError_t launch_layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* y, int M, int D, float eps,
+                             cudaStream_t stream);
+cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, __nv_bfloat16* patches, int S, int B,
+                              cudaStream_t stream);
+cudaError_t launch_pack_input(const float* x, __nv_bfloat16* patches, int S, int B, cudaStream_t stream);
+cudaError_t launch_fill_prefix(float* x, const float* prefix, int ntok, int D, int B, cudaStream_t stream);
+cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float* pool, int pool_blocks, int B, int h, int w,
+                              int num_sms, cudaStream_t stream);
+cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, const float* w1, const float* b1, const float* w2,
+                            const float* b2, float* iou_logits, int K, int B, cudaStream_t stream);
+cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
+                               int* best_idx, int S, int K, int B, int maxH, int maxW, cudaStream_t stream);
+
+}  // namespace s3od

@@ -1,0 +1,40 @@
+// Plain parameter structs shared by host launch code and kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace s3od {
+
+struct ImageDesc {             // one source image on the device
+  const uint8_t* src;          // (h, w, 3) uint8, RGB interleaved
+  int h, w;                    // source size
+  int new_h, new_w;            // size after the aspect-preserving resize (utils.py:6-29)
+  int pad_h, pad_w;            // top / left padding on the S x S canvas
+  int mode;                    // 0 = copy, 1 = exact 2x box filter, 2 = cv2 INTER_LINEAR fixed point
+  const int* xtab;             // mode 2: [x0 | x1 | a0 | a1] x new_w
+  const int* ytab;             // mode 2: [y0 | y1 | b0 | b1] x new_h
+};
+
+struct PostDesc {              // one output image of the post-process
+  const uint8_t* src;          // (H, W, 3) source RGB
+  float* all_masks;            // (K, H, W) fp32 out
+  uint8_t* rgba;               // (H, W, 4) out
+  int H, W;                    // source size
+  int pad_h, pad_w;            // crop offset on the S x S mask
+  int ky, kx;                  // taps per output row / column
+  const int* ystart;           // [H]  first source row of each output row (inside the cropped region)
+  const float* yw;             // [H, ky]
+  const int* xstart;           // [W]
+  const float* xw;             // [W, kx]
+};
+
+struct AttnParams {
+  CUtensorMap tma_q;    // (64 d, ntok, B*H)  box (64, 128, 1)
+  CUtensorMap tma_k;    // (64 d, ntok, B*H)  box (64, 128, 1)
+  CUtensorMap tma_vt;   // (ntok, 64 d, B*H)  box (64, 64, 1)
+  __nv_bfloat16* out;   // [B * ntok, heads * 64]
+  int ntok, heads, kv_tiles;
+};
+
+}  // namespace s3od

@@ -1,0 +1,245 @@
+"""ctypes binding of libs3od_b200.so and the device-side model object.
+
+`B200DPTSegmentation` plays the role of the reference's `DPTSegmentation` nn.Module behind
+`BackgroundRemoval.model` (/root/reference/src/s3od/model.py:89-106): `model(x)` takes a float (B,3,S,S) tensor and
+returns `{'pred_masks', 'pred_iou'}`.  PyTorch is used only for device memory and streams; every kernel is in the
+CUDA library.  There is no CPU or eager fallback: if the library cannot be loaded, or no sm_100 GPU is present, this
+module raises.
+"""
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import geometry
+from .arch import ARCHS, ArchSpec
+from .utils import check_padding, get_pad_info
+from .weights import pack_weights
+
+_LIB = None
+
+
+class S3odImage(ctypes.Structure):
+    _fields_ = [("d_src", ctypes.c_void_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("new_h", ctypes.c_int32),
+                ("new_w", ctypes.c_int32), ("pad_h", ctypes.c_int32), ("pad_w", ctypes.c_int32), ("mode", ctypes.c_int32),
+                ("d_xtab", ctypes.c_void_p), ("d_ytab", ctypes.c_void_p)]
+
+
+class S3odPost(ctypes.Structure):
+    _fields_ = [("d_src", ctypes.c_void_p), ("d_all_masks", ctypes.c_void_p), ("d_rgba", ctypes.c_void_p),
+                ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("pad_h", ctypes.c_int32), ("pad_w", ctypes.c_int32),
+                ("ky", ctypes.c_int32), ("kx", ctypes.c_int32), ("d_ystart", ctypes.c_void_p), ("d_yw", ctypes.c_void_p),
+                ("d_xstart", ctypes.c_void_p), ("d_xw", ctypes.c_void_p)]
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libs3od_b200.so")
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the C-ABI library; raises (no fallback) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m s3od_b200.build` (there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.s3od_last_error.restype = ctypes.c_char_p
+    lib.s3od_version.restype = ctypes.c_char_p
+    lib.s3od_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ci]
+    lib.s3od_set_tensor.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t]
+    lib.s3od_finalize.argtypes = [vp]
+    lib.s3od_preprocess_u8.argtypes = [vp, ctypes.POINTER(S3odImage), ci, vp]
+    lib.s3od_pack_input_f32.argtypes = [vp, vp, ci, vp]
+    lib.s3od_forward.argtypes = [vp, ci, vp, vp, vp]
+    lib.s3od_postprocess.argtypes = [vp, vp, vp, ctypes.POINTER(S3odPost), ci, vp, vp, vp]
+    lib.s3od_get_stage.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    lib.s3od_read_stage.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, vp]
+    lib.s3od_launch_count.argtypes = [vp]
+    lib.s3od_launch_count.restype = ctypes.c_longlong
+    lib.s3od_destroy.argtypes = [vp]
+    lib.s3od_destroy.restype = None
+    lib.s3od_op_gemm_f32.argtypes = [vp, vp, vp, ci, ci, ci, vp]
+    lib.s3od_op_layernorm.argtypes = [vp, vp, vp, vp, ci, ci, cf, vp]
+    lib.s3od_op_attention.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
+    lib.s3od_op_conv3x3.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    _LIB = lib
+    return lib
+
+
+def _check(lib, rc: int, what: str):
+    if rc != 0:
+        msg = lib.s3od_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class B200DPTSegmentation:
+    """Device model: packed weights + launch plan inside the CUDA library."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int = 1024, device: str = "cuda:0",
+                 max_batch: int = 1, micro_batch: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("s3od_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.arch = arch
+        self.image_size = int(image_size)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("s3od_b200 runs on CUDA devices only")
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.dev_index)
+        self.max_batch = int(max_batch)
+        self.micro_batch = int(micro_batch or min(self.max_batch, 8))
+        self.K = arch.num_outputs
+        self._ctx = ctypes.c_void_p()
+        arch_id = 0 if arch.hidden == 768 else 1
+        with torch.cuda.device(self.dev_index):
+            _check(self.lib, self.lib.s3od_create(ctypes.byref(self._ctx), self.dev_index, arch_id, self.K, self.image_size,
+                                                  self.max_batch, self.micro_batch), "s3od_create")
+            for name, t in pack_weights(state_dict, arch, self.image_size).items():
+                t = t.contiguous()
+                _check(self.lib, self.lib.s3od_set_tensor(self._ctx, name.encode(), t.data_ptr(), t.numel() * t.element_size()),
+                       f"s3od_set_tensor({name})")
+            _check(self.lib, self.lib.s3od_finalize(self._ctx), "s3od_finalize")
+        self._tab_cache: Dict[Tuple, Tuple] = {}
+
+    # -- nn.Module-ish surface used by BackgroundRemoval ----------------------------------------------------------
+    def to(self, device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("s3od_b200 model cannot be moved off the GPU (no CPU fallback)")
+        return self
+
+    def eval(self):
+        return self
+
+    def __call__(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return self.forward(x)
+
+    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """The reference's inner seam: x float (B,3,S,S) on this device -> logits (model.py:99-106)."""
+        S = self.image_size
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != S or x.shape[3] != S:
+            raise ValueError(f"expected input of shape (B,3,{S},{S}), got {tuple(x.shape)}")
+        x = x.to(self.device, torch.float32).contiguous()
+        B = x.shape[0]
+        with torch.cuda.device(self.dev_index):
+            st = _stream_ptr(self.device)
+            _check(self.lib, self.lib.s3od_pack_input_f32(self._ctx, x.data_ptr(), B, st), "s3od_pack_input_f32")
+            return self._forward_staged(B)
+
+    def _forward_staged(self, B: int) -> Dict[str, torch.Tensor]:
+        S, K = self.image_size, self.K
+        masks = torch.empty((B, K, S, S), dtype=torch.float32, device=self.device)
+        ious = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        _check(self.lib, self.lib.s3od_forward(self._ctx, B, masks.data_ptr(), ious.data_ptr(), _stream_ptr(self.device)),
+               "s3od_forward")
+        return {"pred_masks": masks, "pred_iou": ious}
+
+    # -- fused uint8 path -----------------------------------------------------------------------------------------
+    def _tables(self, key, builder):
+        t = self._tab_cache.get(key)
+        if t is None:
+            t = builder()
+            self._tab_cache[key] = t
+        return t
+
+    def geometry(self, h: int, w: int):
+        """pad_info + preprocess mode / tables for a source of size (h, w)."""
+        S = self.image_size
+        pad = get_pad_info(np.empty((h, w, 0), np.uint8), S)
+        check_padding(pad, S)
+        return pad
+
+    def preprocess(self, d_images: Sequence[torch.Tensor]) -> List[dict]:
+        """_preprocess (predictor.py:79-94) for uint8 (H,W,3) tensors already on the device; stages the model input."""
+        B = len(d_images)
+        descs = (S3odImage * B)()
+        pads = []
+        for i, img in enumerate(d_images):
+            h, w = int(img.shape[0]), int(img.shape[1])
+            pad = self.geometry(h, w)
+            new_h, new_w = pad["resized_size"]
+            mode = geometry.resize_mode(h, w, new_h, new_w)
+            xt = yt = None
+            if mode == 2:
+                xt, yt = self._tables(("lin", h, w, new_h, new_w), lambda: (
+                    torch.from_numpy(geometry.linear_tables(new_w, w, False)).to(self.device),
+                    torch.from_numpy(geometry.linear_tables(new_h, h, True)).to(self.device)))
+            descs[i] = S3odImage(img.data_ptr(), h, w, new_h, new_w, pad["height_pad"], pad["width_pad"], mode,
+                                 xt.data_ptr() if xt is not None else None, yt.data_ptr() if yt is not None else None)
+            pads.append(pad)
+        with torch.cuda.device(self.dev_index):
+            _check(self.lib, self.lib.s3od_preprocess_u8(self._ctx, descs, B, _stream_ptr(self.device)), "s3od_preprocess_u8")
+        return pads
+
+    def postprocess(self, masks: torch.Tensor, iou_logits: torch.Tensor, d_images: Sequence[torch.Tensor], pads: List[dict]):
+        """Tail of remove_background (predictor.py:113-132) on the device.  Returns per-image (all_masks, rgba) device
+        tensors plus (B,K) ious and (B,) best indices."""
+        B = len(d_images)
+        S, K = self.image_size, self.K
+        descs = (S3odPost * B)()
+        outs = []
+        for i, (img, pad) in enumerate(zip(d_images, pads)):
+            H, W = pad["original_size"]
+            hp, wp = pad["height_pad"], pad["width_pad"]
+            ch, cw = S - 2 * hp, S - 2 * wp
+            ys, yw, xs, xw = self._tables(("aa", ch, cw, H, W), lambda: tuple(
+                torch.from_numpy(a).to(self.device) for a in (geometry.aa_tables(ch, H) + geometry.aa_tables(cw, W))))
+            all_masks = torch.empty((K, H, W), dtype=torch.float32, device=self.device)
+            rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=self.device)
+            descs[i] = S3odPost(img.data_ptr(), all_masks.data_ptr(), rgba.data_ptr(), H, W, hp, wp, yw.shape[1], xw.shape[1],
+                                ys.data_ptr(), yw.data_ptr(), xs.data_ptr(), xw.data_ptr())
+            outs.append((all_masks, rgba))
+        ious = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        best = torch.empty((B,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.dev_index):
+            _check(self.lib, self.lib.s3od_postprocess(self._ctx, masks.data_ptr(), iou_logits.data_ptr(), descs, B,
+                                                       ious.data_ptr(), best.data_ptr(), _stream_ptr(self.device)),
+                   "s3od_postprocess")
+        return outs, ious, best
+
+    def run_u8(self, d_images: Sequence[torch.Tensor]):
+        """preprocess -> forward -> postprocess for device-resident uint8 images (the device-timed hot path)."""
+        pads = self.preprocess(d_images)
+        with torch.cuda.device(self.dev_index):
+            out = self._forward_staged(len(d_images))
+        outs, ious, best = self.postprocess(out["pred_masks"], out["pred_iou"], d_images, pads)
+        return out, outs, ious, best
+
+    def stage(self, name: str, dtype: torch.dtype, shape: Tuple[int, ...]) -> torch.Tensor:
+        """Copy of an internal activation of the last micro-batch (stage-wise parity tests)."""
+        out = torch.empty(shape, dtype=dtype, device=self.device)
+        with torch.cuda.device(self.dev_index):
+            _check(self.lib, self.lib.s3od_read_stage(self._ctx, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
+                                                      _stream_ptr(self.device)), "s3od_read_stage")
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.s3od_launch_count(self._ctx))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.s3od_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+def arch_from_name(name: str) -> ArchSpec:
+    if name not in ARCHS:
+        raise ValueError(f"unknown encoder {name!r}; known: {sorted(ARCHS)}")
+    return ARCHS[name]

@@ -1,0 +1,105 @@
+"""Drop-in for `s3od.BackgroundRemoval` (/root/reference/src/s3od/predictor.py:16-139) on the B200-native path.
+
+Same constructor, class attributes, `from_pretrained`, `remove_background` signature and `RemovalResult` fields as the
+reference; errors are the same types under the same conditions (ValueError for an unloadable model id, ValueError for
+the odd-padding inputs the reference cannot paste).  Additive surface: `remove_background_batch`, and
+`encoder_name` / `num_outputs` / `max_batch` / `micro_batch` keyword arguments.
+
+Everything between the uint8 source image and the result arrays runs in the CUDA library: letterbox resize + normalise,
+the DINOv3 ViT + DPT head forward, sigmoid / crop / antialiased resize / argmax / RGBA composite.
+"""
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+from PIL import Image
+
+from .arch import ARCHS
+from .engine import B200DPTSegmentation
+
+
+@dataclass
+class RemovalResult:
+    predicted_mask: np.ndarray
+    all_masks: np.ndarray
+    all_ious: np.ndarray
+    rgba_image: Image.Image
+
+
+class BackgroundRemoval:
+    DEFAULT_MODEL_ID = "okupyn/s3od"
+    DEFAULT_CHECKPOINT_NAME = "s3od.pt"
+
+    def __init__(self, model_id: Optional[str] = None, image_size: int = 1024, device: Optional[str] = None,
+                 encoder_name: str = "dinov3_base", num_outputs: int = 3, max_batch: int = 1,
+                 micro_batch: Optional[int] = None):
+        self.image_size = image_size
+        self.device = device or "cuda"
+        if not str(self.device).startswith("cuda"):
+            raise RuntimeError("s3od_b200.BackgroundRemoval runs on CUDA (sm_100a) devices only; there is no CPU fallback")
+        self._arch = ARCHS[encoder_name]
+        if num_outputs != self._arch.num_outputs:
+            from dataclasses import replace
+            self._arch = replace(self._arch, num_outputs=num_outputs)
+        self._max_batch = max_batch
+        self._micro_batch = micro_batch
+        model_id = model_id or self.DEFAULT_MODEL_ID
+        self.model = self._load_model(model_id)
+        self.model.to(self.device)
+        self.model.eval()
+        self.mean = np.array([0.485, 0.456, 0.406])
+        self.std = np.array([0.229, 0.224, 0.225])
+
+    @classmethod
+    def from_pretrained(cls, model_id: str, **kwargs):
+        return cls(model_id=model_id, **kwargs)
+
+    def _load_model(self, model_id: str) -> B200DPTSegmentation:
+        """predictor.py:49-77: hub download, else a local path, else ValueError; strict state_dict ingest."""
+        try:
+            from huggingface_hub import hf_hub_download
+            checkpoint_path = hf_hub_download(repo_id=model_id, filename=self.DEFAULT_CHECKPOINT_NAME)
+        except Exception as e:  # noqa: BLE001 - the reference catches everything here
+            if Path(model_id).exists():
+                checkpoint_path = model_id
+            else:
+                raise ValueError(f"Could not load model from {model_id}. "
+                                 f"Ensure model exists on HuggingFace or provide valid local path. Error: {e}")
+        checkpoint = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        return B200DPTSegmentation(checkpoint["state_dict"], self._arch, self.image_size, self.device,
+                                   max_batch=self._max_batch, micro_batch=self._micro_batch)
+
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _to_uint8(image: Union[np.ndarray, Image.Image]) -> np.ndarray:
+        if isinstance(image, Image.Image):
+            return np.array(image.convert("RGB"))
+        Image.fromarray(image)          # the reference builds a PIL image here: same dtype / shape errors
+        return image
+
+    @torch.no_grad()
+    def remove_background(self, image: Union[np.ndarray, Image.Image], threshold: float = 0.5) -> RemovalResult:
+        """predictor.py:96-139.  `threshold` is accepted and unused, as in the reference."""
+        return self.remove_background_batch([image])[0]
+
+    @torch.no_grad()
+    def remove_background_batch(self, images: Sequence[Union[np.ndarray, Image.Image]]) -> List[RemovalResult]:
+        """Batched form of remove_background: host uint8 images in, host results out."""
+        arrays = [np.ascontiguousarray(self._to_uint8(im)) for im in images]
+        results: List[RemovalResult] = []
+        dev = self.model.device
+        for s in range(0, len(arrays), self.model.max_batch):
+            chunk = arrays[s:s + self.model.max_batch]
+            for a in chunk:                                     # raise before touching the GPU, like the reference's paste
+                self.model.geometry(a.shape[0], a.shape[1])
+            d_imgs = [torch.from_numpy(a).to(dev, non_blocking=True) for a in chunk]
+            _, outs, ious, best = self.model.run_u8(d_imgs)
+            ious_h = ious.cpu().numpy()
+            best_h = best.cpu().numpy()
+            for i, (all_masks, rgba) in enumerate(outs):
+                am = all_masks.cpu().numpy()
+                results.append(RemovalResult(predicted_mask=am[int(best_h[i])], all_masks=am, all_ious=ious_h[i].copy(),
+                                             rgba_image=Image.fromarray(rgba.cpu().numpy(), mode="RGBA")))
+        return results

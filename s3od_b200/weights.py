@@ -1,0 +1,150 @@
+"""Checkpoint ingest: reference `state_dict` -> packed tensors for the CUDA library.
+
+Input is the reference checkpoint format (`{'state_dict': ...}`, /root/reference/src/s3od/predictor.py:65,76;
+key list in SURVEY 8b).  Both `encoder.model.layer.N.*` (transformers 5.x) and `encoder.layer.N.*` prefixes are
+accepted.  Output: dict name -> contiguous CPU tensor (bf16 for GEMM operands, fp32 for vectors):
+
+  * every GEMM B operand is K-major `[N, K]` bf16 (what TMA + tcgen05 read);
+  * q/k/v projections are fused into one `[3D, D]` matrix (k bias = 0, config.json key_bias=false);
+  * convolution weights are tap-major `[Cout, (ky*3+kx)*Cin + ci]` to match NHWC implicit GEMM;
+  * eval-mode BatchNorm of the residual units is folded into the preceding conv (model.py:334-345);
+  * the k == stride transposed convs become one `[k*k*Cout, Cin]` GEMM (depth-to-space in the epilogue);
+  * the k4 s2 p1 transposed conv is split into its four 2x2 sub-pixel phases;
+  * the `num_outputs` mask heads are merged into one `[32*K, 9*64]` conv + a `[K, 32]` block of 1x1 weights;
+  * RoPE cos/sin tables (HF:168-200) and the preprocess normalisation LUT (predictor.py:91) are precomputed.
+"""
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+
+from .arch import ArchSpec
+
+
+def _enc_prefix(sd) -> str:
+    return "encoder.model.layer." if any(k.startswith("encoder.model.layer.") for k in sd) else "encoder.layer."
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+def conv_to_gemm(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, kh, kw) -> [Cout, (ky*kw + kx)*Cin + ci]  (tap-major, channels fastest: NHWC implicit GEMM)."""
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+
+
+def fold_bn(w, b, gamma, beta, mean, var, eps):
+    """conv followed by eval BatchNorm == conv with scaled weights: y = (conv(x)+b - mean) * gamma/sqrt(var+eps) + beta."""
+    s = gamma / torch.sqrt(var + eps)
+    return w * s[:, None, None, None], (b - mean) * s + beta
+
+
+def rope_tables(gh: int, gw: int, head_dim: int = 64, theta: float = 100.0):
+    """cos/sin (P, head_dim/2) fp32: eval path of DINOv3ViTRopePositionEmbedding (HF:168-200); the reference tiles the
+    32 angles twice, so only the first half is stored."""
+    inv_freq = 1.0 / theta ** torch.arange(0, 1, 4 / head_dim, dtype=torch.float32)
+    ch = torch.arange(0.5, gh, dtype=torch.float32) / gh
+    cw = torch.arange(0.5, gw, dtype=torch.float32) / gw
+    coords = torch.stack(torch.meshgrid(ch, cw, indexing="ij"), dim=-1).flatten(0, 1)
+    coords = 2.0 * coords - 1.0
+    angles = (2 * math.pi * coords[:, :, None] * inv_freq[None, None, :]).flatten(1, 2)
+    return torch.cos(angles).contiguous(), torch.sin(angles).contiguous()
+
+
+def normalisation_lut() -> torch.Tensor:
+    """bf16[3*256]: (v/255 - mean)/std computed like predictor.py:91 (float32 /255, float64 mean/std, cast to fp32)."""
+    mean = np.array([0.485, 0.456, 0.406])
+    std = np.array([0.229, 0.224, 0.225])
+    v = np.arange(256, dtype=np.uint8).astype(np.float32) / 255.0
+    lut = ((v[None, :] - mean[:, None]) / std[:, None]).astype(np.float32)
+    return torch.from_numpy(lut).reshape(-1).to(torch.bfloat16).contiguous()
+
+
+# ConvTranspose2d(k4, s2, p1): output row 2i+a gets input rows / kernel rows  a=0: (i, kh=1), (i-1, kh=3);
+# a=1: (i+1, kh=0), (i, kh=2).  engine.cu::geom_convt_phase uses the same (offset, tap) order.
+_CT_K = {0: (1, 3), 1: (0, 2)}
+
+
+def pack_weights(sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int) -> Dict[str, torch.Tensor]:
+    D, I, K = arch.hidden, arch.mlp, arch.num_outputs
+    out: Dict[str, torch.Tensor] = {}
+    e = "encoder.embeddings."
+    out["patch.w"] = _bf16(sd[e + "patch_embeddings.weight"].reshape(D, -1))          # k = c*256 + ky*16 + kx
+    out["patch.b"] = _f32(sd[e + "patch_embeddings.bias"])
+    out["prefix"] = _f32(torch.cat([sd[e + "cls_token"].reshape(1, D), sd[e + "register_tokens"].reshape(-1, D)], 0))
+    g = image_size // arch.patch
+    out["rope.cos"], out["rope.sin"] = rope_tables(g, g, arch.head_dim, arch.rope_theta)
+    out["pre.lut"] = normalisation_lut()
+
+    pre = _enc_prefix(sd)
+    for l in range(arch.layers_needed):                                               # layer 12 / final norm are dead (F3)
+        p, o = f"{pre}{l}.", f"enc.{l}."
+        out[o + "ln1.w"], out[o + "ln1.b"] = _f32(sd[p + "norm1.weight"]), _f32(sd[p + "norm1.bias"])
+        out[o + "ln2.w"], out[o + "ln2.b"] = _f32(sd[p + "norm2.weight"]), _f32(sd[p + "norm2.bias"])
+        a = p + "attention."
+        kb = sd.get(a + "k_proj.bias", torch.zeros(D))
+        out[o + "qkv.w"] = _bf16(torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0))
+        out[o + "qkv.b"] = _f32(torch.cat([sd[a + "q_proj.bias"], kb, sd[a + "v_proj.bias"]], 0))
+        out[o + "o.w"], out[o + "o.b"] = _bf16(sd[a + "o_proj.weight"]), _f32(sd[a + "o_proj.bias"])
+        out[o + "ls1"], out[o + "ls2"] = _f32(sd[p + "layer_scale1.lambda1"]), _f32(sd[p + "layer_scale2.lambda1"])
+        out[o + "up.w"], out[o + "up.b"] = _bf16(sd[p + "mlp.up_proj.weight"]), _f32(sd[p + "mlp.up_proj.bias"])
+        out[o + "down.w"], out[o + "down.b"] = _bf16(sd[p + "mlp.down_proj.weight"]), _f32(sd[p + "mlp.down_proj.bias"])
+
+    h = "seg_head."
+    for j in range(4):
+        w = sd[h + f"projects.{j}.weight"]
+        out[f"head.proj{j}.w"] = _bf16(w.reshape(w.shape[0], -1))
+        out[f"head.proj{j}.b"] = _f32(sd[h + f"projects.{j}.bias"])
+    for j, k in ((0, 4), (1, 2)):
+        w = sd[h + f"resize_layers.{j}.weight"]                                       # (Cin, Cout, k, k)
+        ci, co = w.shape[0], w.shape[1]
+        out[f"head.rs{j}.w"] = _bf16(w.permute(2, 3, 1, 0).reshape(k * k * co, ci))   # row = (a*k + b)*Cout + co
+        out[f"head.rs{j}.b"] = _f32(sd[h + f"resize_layers.{j}.bias"])
+    out["head.rs3.w"] = _bf16(conv_to_gemm(sd[h + "resize_layers.3.weight"]))
+    out["head.rs3.b"] = _f32(sd[h + "resize_layers.3.bias"])
+    s = h + "scratch."
+    for j in range(1, 5):
+        out[f"head.rn{j}.w"] = _bf16(conv_to_gemm(sd[s + f"layer{j}_rn.weight"]))
+    for r in range(1, 5):
+        p = s + f"refinenet{r}."
+        w = sd[p + "out_conv.weight"]
+        out[f"head.ref{r}.out.w"] = _bf16(w.reshape(w.shape[0], -1))
+        out[f"head.ref{r}.out.b"] = _f32(sd[p + "out_conv.bias"])
+        for u in ((2,) if r == 4 else (1, 2)):                                        # refinenet4.resConfUnit1 is unused (F8)
+            q = p + f"resConfUnit{u}."
+            for cidx in (1, 2):
+                bn = q + f"bn{cidx}."
+                w, b = sd[q + f"conv{cidx}.weight"], sd[q + f"conv{cidx}.bias"]
+                if bn + "weight" in sd:
+                    w, b = fold_bn(w, b, sd[bn + "weight"], sd[bn + "bias"], sd[bn + "running_mean"], sd[bn + "running_var"],
+                                   arch.bn_eps)
+                out[f"head.ref{r}.rcu{u}.c{cidx}.w"] = _bf16(conv_to_gemm(w))
+                out[f"head.ref{r}.rcu{u}.c{cidx}.b"] = _f32(b)
+    m = h + "mask_head."
+    out["head.mh.c1.w"] = _bf16(conv_to_gemm(sd[m + "output_conv1.weight"]))
+    out["head.mh.c1.b"] = _f32(sd[m + "output_conv1.bias"])
+    wt = sd[m + "upsample_2x.0.weight"]                                               # (Cin=128, Cout=64, 4, 4)
+    phases = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = [wt[:, :, kh, kw].t() for kh in _CT_K[a] for kw in _CT_K[b]]       # each (Cout, Cin); tap = r*2 + c
+            phases.append(torch.cat(taps, dim=1))                                     # (Cout, 4*Cin)
+    out["head.mh.up.w"] = _bf16(torch.cat(phases, dim=0))                             # row = (a*2+b)*Cout + co
+    out["head.mh.up.b"] = _f32(sd[m + "upsample_2x.0.bias"])
+    out["head.mh.c2.w"] = _bf16(conv_to_gemm(sd[m + "upsample_2x.2.weight"]))
+    out["head.mh.c2.b"] = _f32(sd[m + "upsample_2x.2.bias"])
+    out["head.mh.heads.w"] = _bf16(torch.cat([conv_to_gemm(sd[m + f"mask_heads.{k}.0.weight"]) for k in range(K)], 0))
+    out["head.mh.heads.b"] = _f32(torch.cat([sd[m + f"mask_heads.{k}.0.bias"] for k in range(K)], 0))
+    out["head.mh.heads.w2"] = _f32(torch.cat([sd[m + f"mask_heads.{k}.2.weight"].reshape(1, -1) for k in range(K)], 0))
+    out["head.mh.heads.b2"] = _f32(torch.cat([sd[m + f"mask_heads.{k}.2.bias"].reshape(1) for k in range(K)], 0))
+    c = h + "classifier_head."
+    out["head.cls.w1"], out["head.cls.b1"] = _f32(sd[c + "2.weight"]), _f32(sd[c + "2.bias"])
+    out["head.cls.w2"], out["head.cls.b2"] = _f32(sd[c + "4.weight"]), _f32(sd[c + "4.bias"])
+    return out
