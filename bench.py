@@ -1,0 +1,293 @@
+"""Benchmark of the S3OD `remove_background` hot path (dinob) - see the contract in DESIGN.md section "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--source 1024|2048]
+
+A step = one pass of the hot path over one batch of synthetic uint8 images per GPU:
+preprocess kernel -> ViT-B + DPT head forward -> postprocess kernel, all inputs resident in HBM (`value`), and the
+same through the public API with host buffers (`e2e`).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from s3od_b200 import sharder                       # noqa: E402
+from s3od_b200.arch import VITB                     # noqa: E402
+from s3od_b200.synth import save_checkpoint, synth_noise_image, synth_state_dict   # noqa: E402
+
+METRIC = "images/sec (dinob, device-timed)"
+UNIT = "images/s"
+GFLOP_PER_IMAGE = 2276.8            # algorithmic FLOPs of the needed layers, dinob @ 1024^2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def kernel_family(label: str) -> str:
+    if label.endswith("attention"):
+        return "attention"
+    if label.endswith((".ln1", ".ln2")):
+        return "layernorm"
+    if label.startswith("enc.") or label == "patch_embed":
+        return "encoder_gemm"
+    if label.endswith("upsample") or label in ("prefix_tokens", "head.iou"):
+        return "head_bandwidth"
+    if label in ("head.mh.c2", "head.mh.heads") or label.startswith("head.mh.up"):
+        return "head_conv_smallN"
+    return "head_conv"
+
+
+# algorithmic GFLOP per image of each family (SURVEY 8(d) breakdown, dinob @ 1024^2)
+FAMILY_GFLOP = {
+    "attention": 11 * 51.67,
+    "encoder_gemm": 4.83 + 11 * (19.35 + 38.70),
+    "head_conv": 17.7 + 36.5 + 140.1 + 2.95 + 21.47 + 85.90 + 343.60 + 154.62,
+    "head_conv_smallN": 68.72 + 77.31 + 116.17,
+}
+
+
+def run_b200(args, rank, local_rank, world):
+    from s3od_b200 import BackgroundRemoval
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B, S, src = args.batch, args.image_size, args.source
+    ckpt = os.path.join("/tmp", f"s3od_synth_vitb_seed0_{os.getpid()}.pt")
+    save_checkpoint(ckpt, VITB, 0)
+    br = BackgroundRemoval(model_id=ckpt, image_size=S, device=f"cuda:{local_rank}", max_batch=B, micro_batch=args.micro_batch)
+    os.remove(ckpt)
+    model = br.model
+    # seeded synthetic uint8 images (reference fixture style), distinct per rank / slot; resident in HBM for `value`
+    b0, _ = sharder.shard_range(B * world, rank, world)
+    host_imgs = []
+    for i in range(B):
+        t = torch.empty((src, src, 3), dtype=torch.uint8, pin_memory=True)
+        t.numpy()[...] = synth_noise_image(src, src, seed=b0 + i)
+        host_imgs.append(t)
+    d_imgs = [t.to(dev) for t in host_imgs]
+    np_imgs = [t.numpy() for t in host_imgs]          # numpy views of pinned memory for the public API
+
+    def step_device():
+        return model.run_u8(d_imgs)
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize(dev)
+    model.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    sharder.barrier()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        sampler.start()
+    launches0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sharder.barrier()
+    ms_local = e0.elapsed_time(e1)
+    launches = model.launch_count() - launches0
+    prof = model.profile_read()
+    model.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sharder.max_over_ranks(ms_local, device=dev)
+    del out
+
+    # ---- end to end through the public API: pinned host uint8 in, host results out (H2D + D2H inside the timed region)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(2, args.warmup)):
+        br.remove_background_batch(np_imgs)
+    sharder.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = br.remove_background_batch(np_imgs)
+        loss_like = float(res[0].all_ious.sum())       # host read of the step's result
+    torch.cuda.synchronize(dev)
+    t_e2e_local = time.perf_counter() - t0
+    t_e2e = sharder.max_over_ranks(t_e2e_local, device=dev)
+    h2d = B * src * src * 3
+    d2h = B * (3 * src * src * 4 + src * src * 4 + 3 * 4 + 4)
+    del res
+
+    if rank != 0:
+        return None
+    peaks = load_peaks()
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+    # ---- per-family device time (CUDA events on the launch stream, recorded inside the timed region)
+    fam_ms, fam_n = {}, {}
+    for label, n, imgs, ms in prof:
+        f = kernel_family(label)
+        fam_ms[f] = fam_ms.get(f, 0.0) + ms
+        fam_n[f] = fam_n.get(f, 0) + n
+    total_ms = sum(fam_ms.values())
+    images = B * args.steps
+    families = {}
+    for f, ms in sorted(fam_ms.items(), key=lambda kv: -kv[1]):
+        ent = {"share": round(ms / total_ms, 4), "ms_per_image": round(ms / images, 5), "launches": fam_n[f]}
+        if f in FAMILY_GFLOP and S == 1024:
+            ent["tflops"] = round(FAMILY_GFLOP[f] * images / ms, 1)
+        families[f] = ent
+    dom = max((f for f in fam_ms if f in FAMILY_GFLOP), key=lambda f: fam_ms[f])
+    achieved = FAMILY_GFLOP[dom] * images / fam_ms[dom] if S == 1024 else None
+    roofline = {"kernel": dom, "bound": "tensor", "achieved": round(achieved, 1) if achieved else None,
+                "peak": peaks["tflops_sustained"], "peak_source": peaks["source"] + " (sustained: timed inside a long step)",
+                "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4) if achieved else None,
+                "traffic": None, "avg_launch_ms": round(fam_ms[dom] / fam_n[dom], 4),
+                "whole_step_tflops": round(GFLOP_PER_IMAGE * value / world / 1e3, 1) if S == 1024 else None,
+                "whole_step_frac": round(GFLOP_PER_IMAGE * value / world / 1e3 / peaks["tflops_sustained"], 4) if S == 1024 else None}
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"dinob inference bf16, batch {B} synthetic {src}x{src} uint8 images per GPU, image_size {S} "
+                               "(preprocess + backbone + mask decoder + IoU head + postprocess), seeded random weights",
+                   "batch_per_gpu": B, "image_size": S, "source": src, "micro_batch": model.micro_batch,
+                   "cache": "inputs + activations per step exceed the 126 MB L2 by >10x (no flush needed)"},
+        "clocks": clocks,
+        "e2e": {"value": round(world * B * e2e_steps / t_e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "BackgroundRemoval.remove_background_batch (pinned host uint8 in, host results out)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": families,
+    }
+    return line
+
+
+def cpu_baseline(sample_images: int, S: int, src: int):
+    """The CPU oracle (port of the reference path) on the host cores: full remove_background per image."""
+    from oracle.pipeline import remove_background
+    sd = synth_state_dict(VITB, 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    remove_background(sd, synth_noise_image(64, 64, seed=0), VITB, 64)          # thread-pool / allocator warm-up, tiny
+    t0 = time.perf_counter()
+    for i in range(sample_images):
+        remove_background(sd, synth_noise_image(src, src, seed=i), VITB, S)
+    dt = time.perf_counter() - t0
+    return {"value": round(sample_images / dt, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_images} image(s) {src}x{src}, image_size {S}, full remove_background on the CPU oracle "
+                      f"(torch {torch.__version__} fp32), {dt:.1f} s"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference path's CPU implementation (oracle port; /root/reference cannot travel)."""
+    if rank != 0:
+        return None
+    from oracle.pipeline import remove_background
+    sd = synth_state_dict(VITB, 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    S, src = args.image_size, args.source
+    imgs = [synth_noise_image(src, src, seed=i) for i in range(2)]
+    for _ in range(min(args.warmup, 1)):
+        remove_background(sd, imgs[0], VITB, S)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        remove_background(sd, imgs[i % 2], VITB, S)       # one step = a 1-image sample of the batch
+    dt = time.perf_counter() - t0
+    v = round(args.steps / dt, 4)
+    sample = f"1 image {src}x{src} per step (bounded sample of the batch-{args.batch} workload), oracle port of the reference CPU path"
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"dinob inference, batch {args.batch} synthetic {src}x{src} uint8 images per GPU, image_size {S}",
+                       "batch_per_gpu": args.batch, "image_size": S, "source": src},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE.json configs[1])")
+    ap.add_argument("--image-size", type=int, default=1024)
+    ap.add_argument("--source", type=int, default=1024, help="source image side (2048 = configs[2] shape)")
+    ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=2, help="images timed on the CPU oracle (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    rank, local_rank, world = sharder.init_from_env("nccl")
+    line = run_b200(args, rank, local_rank, world)
+    if rank == 0:
+        if world == 1 and args.cpu_sample > 0:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_sample, args.image_size, args.source)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

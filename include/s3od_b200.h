@@ -84,6 +84,11 @@ int s3od_get_stage(s3od_ctx* ctx, const char* name, void** d_ptr, size_t* bytes)
 /* Copy the first `bytes` of an internal activation into a caller buffer (device to device, on `stream`). */
 int s3od_read_stage(s3od_ctx* ctx, const char* name, void* d_dst, size_t bytes, s3od_stream stream);
 
+/* Per-launch timing with CUDA events recorded on the forward stream around every kernel of the plan.
+ * s3od_profile_read writes one "label\tlaunches\timages\ttotal_ms" line per plan entry and resets the counters. */
+int s3od_profile_enable(s3od_ctx* ctx, int on);
+int s3od_profile_read(s3od_ctx* ctx, char* buf, size_t buf_bytes);
+
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 long long s3od_launch_count(s3od_ctx* ctx);
 

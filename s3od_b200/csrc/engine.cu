@@ -178,6 +178,11 @@ struct s3od_ctx {
   ImageDesc* d_img = nullptr;
   PostDesc* d_post = nullptr;
   int last_nb = 0;
+  // optional per-op timing with CUDA events on the launch stream (bench.py roofline numbers)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<std::pair<int, int>> ev_ops;        // (op index, nb) for every recorded event pair
   // launch plan: every op takes (nb images, first image index b0, mask-logit out, iou-logit out, stream)
   using Op = std::function<cudaError_t(int, int, float*, float*, cudaStream_t)>;
   std::vector<std::pair<std::string, Op>> plan;
@@ -653,9 +658,23 @@ int s3od_forward(s3od_ctx* c, int batch, float* d_mask_logits, float* d_iou_logi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int b0 = 0; b0 < batch; b0 += c->mb) {
     const int nb = std::min(c->mb, batch - b0);
-    for (auto& op : c->plan) {
+    for (size_t oi = 0; oi < c->plan.size(); ++oi) {
+      auto& op = c->plan[oi];
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (c->profile) {
+        while (c->ev_pool.size() < c->ev_used + 2) {
+          cudaEvent_t ev;
+          CK(cudaEventCreate(&ev));
+          c->ev_pool.push_back(ev);
+        }
+        e0 = c->ev_pool[c->ev_used++];
+        e1 = c->ev_pool[c->ev_used++];
+        c->ev_ops.emplace_back(static_cast<int>(oi), nb);
+        CK(cudaEventRecord(e0, st));
+      }
       cudaError_t e = op.second(nb, b0, d_mask_logits, d_iou_logits, st);
       if (e != cudaSuccess) return fail(S3OD_ERR_CUDA, "launch of '" + op.first + "' failed: " + cudaGetErrorString(e));
+      if (c->profile) CK(cudaEventRecord(e1, st));
       c->launches += 1;
     }
     c->last_nb = nb;
@@ -699,6 +718,40 @@ int s3od_read_stage(s3od_ctx* c, const char* name, void* d_dst, size_t bytes, s3
   return S3OD_OK;
 }
 
+int s3od_profile_enable(s3od_ctx* c, int on) {
+  if (c == nullptr) return fail(S3OD_ERR_ARG, "null ctx");
+  c->profile = on != 0;
+  c->ev_used = 0;
+  c->ev_ops.clear();
+  return S3OD_OK;
+}
+
+// Writes "label<TAB>launches<TAB>images<TAB>total_ms\n" per plan entry, for all forwards since the last enable/read.
+int s3od_profile_read(s3od_ctx* c, char* buf, size_t buf_bytes) {
+  if (c == nullptr || buf == nullptr || buf_bytes == 0) return fail(S3OD_ERR_ARG, "bad argument to s3od_profile_read");
+  std::vector<double> ms(c->plan.size(), 0.0);
+  std::vector<long long> cnt(c->plan.size(), 0), imgs(c->plan.size(), 0);
+  if (c->ev_used > 0) CK(cudaEventSynchronize(c->ev_pool[c->ev_used - 1]));
+  for (size_t i = 0; i < c->ev_ops.size(); ++i) {
+    float t = 0.0f;
+    CK(cudaEventElapsedTime(&t, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]));
+    ms[c->ev_ops[i].first] += t;
+    cnt[c->ev_ops[i].first] += 1;
+    imgs[c->ev_ops[i].first] += c->ev_ops[i].second;
+  }
+  std::string out;
+  for (size_t i = 0; i < c->plan.size(); ++i) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\t%lld\t%lld\t%.6f\n", c->plan[i].first.c_str(), cnt[i], imgs[i], ms[i]);
+    out += line;
+  }
+  c->ev_used = 0;
+  c->ev_ops.clear();
+  if (out.size() + 1 > buf_bytes) return fail(S3OD_ERR_ARG, "profile buffer too small: need " + std::to_string(out.size() + 1));
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return S3OD_OK;
+}
+
 long long s3od_launch_count(s3od_ctx* c) { return c == nullptr ? 0 : c->launches; }
 
 void s3od_destroy(s3od_ctx* c) {
@@ -708,6 +761,7 @@ void s3od_destroy(s3od_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->d_img) cudaFree(c->d_img);
   if (c->d_post) cudaFree(c->d_post);
+  for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
   delete c;
 }
 

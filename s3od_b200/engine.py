@@ -59,6 +59,8 @@ def load_library() -> ctypes.CDLL:
     lib.s3od_postprocess.argtypes = [vp, vp, vp, ctypes.POINTER(S3odPost), ci, vp, vp, vp]
     lib.s3od_get_stage.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     lib.s3od_read_stage.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, vp]
+    lib.s3od_profile_enable.argtypes = [vp, ci]
+    lib.s3od_profile_read.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
     lib.s3od_launch_count.argtypes = [vp]
     lib.s3od_launch_count.restype = ctypes.c_longlong
     lib.s3od_destroy.argtypes = [vp]
@@ -223,6 +225,19 @@ class B200DPTSegmentation:
             _check(self.lib, self.lib.s3od_read_stage(self._ctx, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
                                                       _stream_ptr(self.device)), "s3od_read_stage")
         return out
+
+    def profile_enable(self, on: bool = True):
+        _check(self.lib, self.lib.s3od_profile_enable(self._ctx, 1 if on else 0), "s3od_profile_enable")
+
+    def profile_read(self):
+        """[(label, launches, images, total_ms)] for every kernel of the launch plan since the last read."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        _check(self.lib, self.lib.s3od_profile_read(self._ctx, buf, len(buf)), "s3od_profile_read")
+        rows = []
+        for line in buf.value.decode().splitlines():
+            label, n, imgs, ms = line.split("\t")
+            rows.append((label, int(n), int(imgs), float(ms)))
+        return rows
 
     def launch_count(self) -> int:
         return int(self.lib.s3od_launch_count(self._ctx))

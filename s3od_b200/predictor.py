@@ -86,20 +86,45 @@ class BackgroundRemoval:
 
     @torch.no_grad()
     def remove_background_batch(self, images: Sequence[Union[np.ndarray, Image.Image]]) -> List[RemovalResult]:
-        """Batched form of remove_background: host uint8 images in, host results out."""
+        """Batched form of remove_background: host uint8 images in, host results out.
+
+        Images go through the device in chunks of the model's micro-batch; the device-to-host copies of a chunk's
+        results run on a side stream into pinned memory while the next chunk computes."""
         arrays = [np.ascontiguousarray(self._to_uint8(im)) for im in images]
-        results: List[RemovalResult] = []
-        dev = self.model.device
-        for s in range(0, len(arrays), self.model.max_batch):
-            chunk = arrays[s:s + self.model.max_batch]
-            for a in chunk:                                     # raise before touching the GPU, like the reference's paste
-                self.model.geometry(a.shape[0], a.shape[1])
+        model = self.model
+        dev = model.device
+        for a in arrays:                                        # raise before touching the GPU, like the reference's paste
+            model.geometry(a.shape[0], a.shape[1])
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        side = self._copy_stream
+        pending = []
+        step = max(1, min(model.max_batch, model.micro_batch))
+        for s0 in range(0, len(arrays), step):
+            chunk = arrays[s0:s0 + step]
             d_imgs = [torch.from_numpy(a).to(dev, non_blocking=True) for a in chunk]
-            _, outs, ious, best = self.model.run_u8(d_imgs)
-            ious_h = ious.cpu().numpy()
-            best_h = best.cpu().numpy()
-            for i, (all_masks, rgba) in enumerate(outs):
-                am = all_masks.cpu().numpy()
-                results.append(RemovalResult(predicted_mask=am[int(best_h[i])], all_masks=am, all_ious=ious_h[i].copy(),
-                                             rgba_image=Image.fromarray(rgba.cpu().numpy(), mode="RGBA")))
+            _, outs, ious, best = model.run_u8(d_imgs)
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                h_ious = torch.empty(ious.shape, dtype=ious.dtype, pin_memory=True).copy_(ious, non_blocking=True)
+                h_best = torch.empty(best.shape, dtype=best.dtype, pin_memory=True).copy_(best, non_blocking=True)
+                host = []
+                for all_masks, rgba in outs:
+                    hm = torch.empty(all_masks.shape, dtype=all_masks.dtype, pin_memory=True).copy_(all_masks, non_blocking=True)
+                    hr = torch.empty(rgba.shape, dtype=rgba.dtype, pin_memory=True).copy_(rgba, non_blocking=True)
+                    host.append((hm, hr))
+                for t in [ious, best] + [x for pair in outs for x in pair] + d_imgs:
+                    t.record_stream(side)
+            pending.append((host, h_ious, h_best))
+        side.synchronize()
+        results: List[RemovalResult] = []
+        for host, h_ious, h_best in pending:
+            ious_np, best_np = h_ious.numpy(), h_best.numpy()
+            for i, (hm, hr) in enumerate(host):
+                am = hm.numpy()
+                results.append(RemovalResult(predicted_mask=am[int(best_np[i])], all_masks=am, all_ious=ious_np[i].copy(),
+                                             rgba_image=Image.fromarray(hr.numpy(), mode="RGBA")))
         return results
