@@ -102,10 +102,9 @@ int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N,
 /* y bf16 = LayerNorm(x fp32) */
 int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void* d_y, int M, int D, float eps,
                       s3od_stream stream);
-/* out[B*ntok, heads*64] bf16 = softmax(Q K^T) V ; q,k [B*heads, ntok, 64] bf16 (q pre-scaled by log2e/8),
- * vt [B*heads, 64, vt_pitch] bf16 */
-int s3od_op_attention(const void* d_q, const void* d_k, const void* d_vt, void* d_out, int batch, int heads, int ntok,
-                      int vt_pitch, s3od_stream stream);
+/* out[B*ntok, heads*64] bf16 = softmax(Q K^T) V ; q, k, v [B*heads, ntok, 64] bf16 (q pre-scaled by log2e/8) */
+int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d_out, int batch, int heads, int ntok,
+                      s3od_stream stream);
 /* NHWC bf16 3x3 / stride 1 / pad 1 convolution, weights [cout, 9*cin] bf16 (tap-major), fp32 bias or NULL */
 int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin,
                     int cout, int relu, s3od_stream stream);

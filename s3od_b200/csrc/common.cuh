@@ -137,15 +137,94 @@ S3OD_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+S3OD_DEVICE void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// registers -> TMEM, same lane / column mapping as tmem_ld_32x32
+S3OD_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+S3OD_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 S3OD_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but the loaded registers are in/out operands so that no use of them can be scheduled above the wait.
+S3OD_DEVICE void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+S3OD_DEVICE void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // Load 32 fp32 accumulator columns of this thread's TMEM lane.
 S3OD_DEVICE void tmem_ld_f32x32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   tmem_ld_32x32(taddr, r);
-  tmem_ld_wait();
+  tmem_ld_wait(r);
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+S3OD_DEVICE void tmem_ld_f32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld_32x16(taddr, r);
+  tmem_ld_wait(r);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Same descriptor for an MN-major operand (e.g. V[kv, d] used as B[N = d, K = kv]): every smem row is one K index
+// holding 64 contiguous N elements (128 B, swizzled); 8 K-rows form a 1024 B group (SBO); a 16-deep K step spans
+// two groups, so the start address advances by 2048 B per MMA.  The instruction descriptor must set b_major = MN.
+S3OD_DEVICE uint64_t make_sdesc_sw128_mn(uint32_t saddr) { return make_sdesc_sw128(saddr); }
+
+// Per-warp shared-memory staging used by the GEMM epilogues to turn "one thread = one accumulator row" into
+// "four lanes = one 64-byte row segment": 32 rows x 16 words, rows padded to 20 words (both phases bank-conflict free).
+struct WarpStage {
+  uint32_t* base;
+  int lane;
+  static constexpr int kWordsPerRow = 20;
+  static constexpr int kBytes = 32 * kWordsPerRow * 4;
+  S3OD_DEVICE void write(const uint32_t (&w)[16]) const {
+    uint4* d = reinterpret_cast<uint4*>(base + lane * kWordsPerRow);
+    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    d[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    d[3] = make_uint4(w[12], w[13], w[14], w[15]);
+  }
+  // iteration it (0..3): this lane gets row it*8 + lane/4, 16-byte segment lane%4
+  S3OD_DEVICE int row(int it) const { return it * 8 + (lane >> 2); }
+  S3OD_DEVICE int seg() const { return lane & 3; }
+  S3OD_DEVICE uint4 read(int it) const {
+    return *reinterpret_cast<const uint4*>(base + row(it) * kWordsPerRow + seg() * 4);
+  }
+};
+
+S3OD_DEVICE float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // ---------------------------------------------------------------- small math / packing
@@ -166,7 +245,7 @@ S3OD_DEVICE float warp_sum(float v) {
 // q = erfc(|x|/sqrt2) is used directly on the negative side so large negative inputs do not cancel.
 S3OD_DEVICE float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);

@@ -3,7 +3,7 @@
 // Data layout in HBM (nb = images of the current micro-batch, g = S/16, P = g*g patches, ntok = P + 5):
 //   patches  bf16 [B*P, 768]            im2col of the letterboxed, normalised input (whole batch)
 //   x        fp32 [nb*ntok, D]          residual stream          xn / ctx bf16 [nb*ntok, D]   LN output / attention output
-//   q, k     bf16 [nb*H, ntok, 64]      vt bf16 [nb*H, 64, vt_pitch]                          hmid bf16 [nb*ntok, I]
+//   q, k, v  bf16 [nb*H, ntok, 64]      (head-major; V is read as an MN-major MMA operand)     hmid bf16 [nb*ntok, I]
 //   taps     bf16 [nb*P, D] x 4         == NHWC (nb, g, g, D): token-major IS channels-last, no permute (model.py:206)
 //   head     bf16 NHWC everywhere; mask logits fp32 planar (B, K, S, S) straight into the caller's buffer.
 #include <cuda.h>
@@ -219,7 +219,7 @@ using bf16 = __nv_bfloat16;
 // ---- plan builders -----------------------------------------------------------------------------------------------
 template <int BN, class Epi, int EW>
 bool add_linear(s3od_ctx* c, const std::string& label, const void* a, uint64_t a_rows_total, int rows_per_image, int Kdim,
-                const void* bw, int N, typename Epi::Params ep, bool a_is_batch_window = false,
+                const void* bw, int N, typename Epi::Params ep, bool a_is_batch_window = false, bool per_image_tiles = false,
                 std::function<void(typename Epi::Params&, int, int, float*, float*)> patch = nullptr) {
   if (N % BN != 0 || Kdim % 64 != 0) {
     g_err = "bad GEMM shape for " + label;
@@ -238,6 +238,11 @@ bool add_linear(s3od_ctx* c, const std::string& label, const void* a, uint64_t a
     GemmParams<Epi> q = p;
     q.M = nb * rows_per_image;
     q.m_tiles = (q.M + kBM - 1) / kBM;
+    if (per_image_tiles) {                      // token GEMMs: tiles never straddle two images
+      q.rows_per_image = rows_per_image;
+      q.tiles_per_image = (rows_per_image + kBM - 1) / kBM;
+      q.m_tiles = nb * q.tiles_per_image;
+    }
     q.a_row_offset = a_is_batch_window ? b0 * rows_per_image : 0;
     if (patch) patch(q.epi, nb, b0, mo, io);
     return launch_gemm<BN, A_LINEAR, Epi, EW>(q, sms, st);
@@ -301,7 +306,7 @@ bool build_plan(s3od_ctx* c) {
   ok = ok && alloc_act(c, "ctx", MT * D * 2);
   ok = ok && alloc_act(c, "q", MT * D * 2);
   ok = ok && alloc_act(c, "k", MT * D * 2);
-  ok = ok && alloc_act(c, "vt", static_cast<size_t>(mb) * H * 64 * c->vt_pitch * 2);
+  ok = ok && alloc_act(c, "v", MT * D * 2);
   ok = ok && alloc_act(c, "hmid", MT * I * 2);
   for (int j = 0; j < 4; ++j) ok = ok && alloc_act(c, "tap" + std::to_string(j), static_cast<size_t>(mb) * P * D * 2);
   const int R[5] = {0, 4 * g, 2 * g, g, g / 2};     // resolution of layer_k_rn, k = 1..4
@@ -338,7 +343,7 @@ bool build_plan(s3od_ctx* c) {
   {
     EpiPatch::Params e{x, wptr<float>(c, "patch.b"), P, ntok, D};
     if (!add_linear<256, EpiPatch, 8>(c, "patch_embed", aptr<bf16>(c, "patches"), static_cast<uint64_t>(c->max_batch) * P, P, 768,
-                                      wptr<bf16>(c, "patch.w"), D, e, /*a_is_batch_window=*/true))
+                                      wptr<bf16>(c, "patch.w"), D, e, /*a_is_batch_window=*/true, /*per_image_tiles=*/true))
       return false;
     const float* prefix = wptr<float>(c, "prefix");
     c->plan.emplace_back("prefix_tokens", [=](int nb, int, float*, float*, cudaStream_t st) {
@@ -353,10 +358,7 @@ bool build_plan(s3od_ctx* c) {
     const uint32_t bq[3] = {64, 128, 1};
     if (!make_tmap(&ap.tma_q, aptr<bf16>(c, "q"), 3, dq, sq, bq)) return false;
     if (!make_tmap(&ap.tma_k, aptr<bf16>(c, "k"), 3, dq, sq, bq)) return false;
-    const uint64_t dv[3] = {(uint64_t)ntok, 64, BH};
-    const uint64_t sv[2] = {(uint64_t)c->vt_pitch * 2, (uint64_t)c->vt_pitch * 2 * 64};
-    const uint32_t bv[3] = {64, 64, 1};
-    if (!make_tmap(&ap.tma_vt, aptr<bf16>(c, "vt"), 3, dv, sv, bv)) return false;
+    if (!make_tmap(&ap.tma_v, aptr<bf16>(c, "v"), 3, dq, sq, bq)) return false;
     ap.out = actx;
     ap.ntok = ntok;
     ap.heads = H;
@@ -371,33 +373,33 @@ bool build_plan(s3od_ctx* c) {
     });
     {
       EpiQKV::Params e{};
-      e.q = aptr<bf16>(c, "q"); e.k = aptr<bf16>(c, "k"); e.vt = aptr<bf16>(c, "vt");
+      e.q = aptr<bf16>(c, "q"); e.k = aptr<bf16>(c, "k"); e.v = aptr<bf16>(c, "v");
       e.bias = wptr<float>(c, pre + "qkv.b");
       e.rope_cos = wptr<float>(c, "rope.cos"); e.rope_sin = wptr<float>(c, "rope.sin");
-      e.ntok = ntok; e.heads = H; e.D = D; e.vt_pitch = c->vt_pitch;
+      e.ntok = ntok; e.heads = H; e.D = D;
       e.qscale = 0.125f * 1.4426950408889634f;
-      if (!add_linear<256, EpiQKV, 8>(c, pre + "qkv", xn, MT, ntok, D, wptr<bf16>(c, pre + "qkv.w"), 3 * D, e)) return false;
+      if (!add_linear<256, EpiQKV, 8>(c, pre + "qkv", xn, MT, ntok, D, wptr<bf16>(c, pre + "qkv.w"), 3 * D, e, false, true)) return false;
     }
     c->plan.emplace_back(pre + "attention", [=](int nb, int, float*, float*, cudaStream_t st) {
       return launch_attention(ap, (ntok + 127) / 128, nb * H, st);
     });
     {
       EpiResidual::Params e{x, wptr<float>(c, pre + "o.b"), wptr<float>(c, pre + "ls1"), nullptr, ntok, P, D};
-      if (!add_linear<256, EpiResidual, 8>(c, pre + "o_proj", actx, MT, ntok, D, wptr<bf16>(c, pre + "o.w"), D, e)) return false;
+      if (!add_linear<256, EpiResidual, 8>(c, pre + "o_proj", actx, MT, ntok, D, wptr<bf16>(c, pre + "o.w"), D, e, false, true)) return false;
     }
     c->plan.emplace_back(pre + "ln2", [=](int nb, int, float*, float*, cudaStream_t st) {
       return launch_layernorm(x, ln2w, ln2b, xn, nb * ntok, D, 1e-5f, st);
     });
     {
-      EpiGelu::Params e{hmid, wptr<float>(c, pre + "up.b"), I};
-      if (!add_linear<256, EpiGelu, 8>(c, pre + "up_proj", xn, MT, ntok, D, wptr<bf16>(c, pre + "up.w"), I, e)) return false;
+      EpiGelu::Params e{hmid, wptr<float>(c, pre + "up.b"), I, ntok};
+      if (!add_linear<256, EpiGelu, 8>(c, pre + "up_proj", xn, MT, ntok, D, wptr<bf16>(c, pre + "up.w"), I, e, false, true)) return false;
     }
     {
       bf16* tap = nullptr;
       for (int j = 0; j < 4; ++j)
         if (c->taps[j] == l + 1) tap = aptr<bf16>(c, "tap" + std::to_string(j));
       EpiResidual::Params e{x, wptr<float>(c, pre + "down.b"), wptr<float>(c, pre + "ls2"), tap, ntok, P, D};
-      if (!add_linear<256, EpiResidual, 8>(c, pre + "down_proj", hmid, MT, ntok, I, wptr<bf16>(c, pre + "down.w"), D, e)) return false;
+      if (!add_linear<256, EpiResidual, 8>(c, pre + "down_proj", hmid, MT, ntok, I, wptr<bf16>(c, pre + "down.w"), D, e, false, true)) return false;
     }
   }
 
@@ -785,9 +787,9 @@ int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void
   return S3OD_OK;
 }
 
-int s3od_op_attention(const void* d_q, const void* d_k, const void* d_vt, void* d_out, int batch, int heads, int ntok, int vt_pitch,
+int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d_out, int batch, int heads, int ntok,
                       s3od_stream stream) {
-  if (vt_pitch % 8 != 0 || vt_pitch < ntok) return fail(S3OD_ERR_ARG, "vt_pitch must be a multiple of 8 and >= ntok");
+  if (batch < 1 || heads < 1 || ntok < 1) return fail(S3OD_ERR_ARG, "bad shape for s3od_op_attention");
   AttnParams ap{};
   const uint64_t BH = static_cast<uint64_t>(batch) * heads;
   const uint64_t dq[3] = {64, (uint64_t)ntok, BH};
@@ -795,10 +797,7 @@ int s3od_op_attention(const void* d_q, const void* d_k, const void* d_vt, void* 
   const uint32_t bq[3] = {64, 128, 1};
   if (!make_tmap(&ap.tma_q, d_q, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
   if (!make_tmap(&ap.tma_k, d_k, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
-  const uint64_t dv[3] = {(uint64_t)ntok, 64, BH};
-  const uint64_t sv[2] = {(uint64_t)vt_pitch * 2, (uint64_t)vt_pitch * 2 * 64};
-  const uint32_t bv[3] = {64, 64, 1};
-  if (!make_tmap(&ap.tma_vt, d_vt, 3, dv, sv, bv)) return S3OD_ERR_CUDA;
+  if (!make_tmap(&ap.tma_v, d_v, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
   ap.out = static_cast<bf16*>(d_out);
   ap.ntok = ntok; ap.heads = heads; ap.kv_tiles = (ntok + 127) / 128;
   CK(launch_attention(ap, (ntok + 127) / 128, static_cast<int>(BH), static_cast<cudaStream_t>(stream)));

@@ -41,7 +41,8 @@ struct ConvGeom {
 // Where an accumulator row lives in the problem.
 struct RowInfo {
   int gm;        // A_LINEAR: global row index;  A_CONV: unused
-  int b, h, w;   // A_CONV: image, output row / col
+  int b, h, w;   // A_CONV: image, output row / col.  A_LINEAR with per-image tiling: b = image
+  int t;         // A_LINEAR with per-image tiling: row inside the image (token index)
   bool valid;
 };
 
@@ -54,33 +55,39 @@ struct GemmParams {
   int num_k_blocks;      // K / 64   (A_CONV: ntaps * cin_blocks)
   int b_row_offset;      // first row of B used by this launch (sub-pixel phases share one weight tensor)
   int a_row_offset;      // A_LINEAR: first row of A used by this launch (micro-batch window into a larger buffer)
+  int rows_per_image;    // A_LINEAR: > 0 tiles never straddle images: m_tiles = images * tiles_per_image (token GEMMs)
+  int tiles_per_image;
   ConvGeom geom;
   typename Epi::Params epi;
 };
 
-template <int BN>
+template <int BN, int EPI_WARPS = 8>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kStages = (196 * 1024 / kStageBytes) > 8 ? 8 : (196 * 1024 / kStageBytes);
   // TMEM columns per accumulator stage (power of two so every stage starts on an aligned column)
   static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr uint32_t kTmemCols = 2 * kAccStride < 32 ? 32 : 2 * kAccStride;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = EPI_WARPS * WarpStage::kBytes;   // epilogue transposition buffers
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 template <int BN, int AMODE, class Epi, int EPI_WARPS>
 __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI_WARPS>;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(Cfg::kBBytes % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by offsetting the shared array itself (a uintptr_t round trip would turn every access into a generic one)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint32_t* staging = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* full = bars;                          // [kStages]  TMA -> MMA
   uint64_t* empty = bars + Cfg::kStages;          // [kStages]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
@@ -129,12 +136,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
           h0 = (r / p.geom.tiles_w) * kTileH;
           w0 = (r % p.geom.tiles_w) * kTileW;
         }
+        int a_row0 = p.a_row_offset + m_blk * kBM;
+        if (AMODE == A_LINEAR && p.rows_per_image > 0)
+          a_row0 = p.a_row_offset + (m_blk / p.tiles_per_image) * p.rows_per_image + (m_blk % p.tiles_per_image) * kBM;
         int tap = 0, cblk = 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
           if (AMODE == A_LINEAR) {
-            tma_load_2d(sA + stage * Cfg::kABytes, &p.tma_a, &full[stage], kb * kBK, p.a_row_offset + m_blk * kBM);
+            tma_load_2d(sA + stage * Cfg::kABytes, &p.tma_a, &full[stage], kb * kBK, a_row0);
           } else {
             tma_load_5d(sA + stage * Cfg::kABytes, &p.tma_a, &full[stage], p.geom.dc[tap] + cblk * kBK,
                         w0 + p.geom.dw[tap], p.geom.dp[tap], h0 + p.geom.dh[tap], cb);
@@ -201,9 +211,18 @@ gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
       const int n_blk = tile % p.n_tiles;
       RowInfo ri;
       if (AMODE == A_LINEAR) {
-        ri.gm = m_blk * kBM + row;
-        ri.b = ri.h = ri.w = 0;
-        ri.valid = ri.gm < p.M;
+        ri.h = ri.w = 0;
+        if (p.rows_per_image > 0) {
+          ri.b = m_blk / p.tiles_per_image;
+          ri.t = (m_blk % p.tiles_per_image) * kBM + row;
+          ri.gm = ri.b * p.rows_per_image + ri.t;
+          ri.valid = ri.t < p.rows_per_image;
+        } else {
+          ri.gm = m_blk * kBM + row;
+          ri.b = 0;
+          ri.t = ri.gm;
+          ri.valid = ri.gm < p.M;
+        }
       } else {
         const int per_img = p.geom.tiles_h * p.geom.tiles_w;
         ri.b = m_blk / per_img;
@@ -211,12 +230,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
         ri.h = (r / p.geom.tiles_w) * kTileH + row / kTileW;
         ri.w = (r % p.geom.tiles_w) * kTileW + row % kTileW;
         ri.gm = 0;
+        ri.t = 0;
         ri.valid = ri.h < p.geom.H && ri.w < p.geom.W;
       }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::kAccStride + col_begin;
-      Epi::template run<kColsPerGroup>(p.epi, ri, n_blk * BN + col_begin, taddr);
+      const WarpStage stg{staging + ew * (WarpStage::kBytes / 4), lane};
+      Epi::template run<kColsPerGroup>(p.epi, ri, n_blk * BN + col_begin, taddr, stg);
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) {
@@ -280,7 +301,7 @@ struct EpiPatch {
     int npatch, ntok, D;
   };
   template <int NCOLS>
-  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
     const int b = ri.gm / e.npatch, pi = ri.gm % e.npatch;
     float* dst = e.x + (static_cast<size_t>(b) * e.ntok + 5 + pi) * e.D + n0;
 #pragma unroll 1
@@ -297,66 +318,79 @@ struct EpiPatch {
   }
 };
 
+// The three token-GEMM epilogues below run with per-image tiling (RowInfo.b / .t valid) and write through the per-warp
+// staging buffer: phase 1 is row-per-thread (TMEM layout), phase 2 is four lanes per 64-byte row segment, so every
+// global access is a full, contiguous segment instead of 16 bytes per lane scattered over 32 rows.
+
+S3OD_DEVICE void pack_bf16x32(const float (&v)[32], uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+}
+
 // ---- fused q/k/v projection: + bias, RoPE on the patch rows of q and k (HF:238-268), softmax scale folded into q,
-//      head-major stores: Q,K [B*H, ntok, 64], V transposed [B*H, 64, vt_pitch] (K-major B operand of P.V)
+//      head-major stores Q, K, V [B*H, ntok, 64] (V is consumed as an MN-major B operand by the attention kernel)
 struct EpiQKV {
   struct Params {
     __nv_bfloat16* q;
     __nv_bfloat16* k;
-    __nv_bfloat16* vt;
+    __nv_bfloat16* v;
     const float* bias;      // [3D], k part zero (config.json: key_bias=false)
     const float* rope_cos;  // [npatch, 32]
     const float* rope_sin;  // [npatch, 32]
-    int ntok, heads, D, vt_pitch;
+    int ntok, heads, D;
     float qscale;           // head_dim^-0.5 * log2(e)
   };
   template <int NCOLS>
-  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
     static_assert(NCOLS % 64 == 0, "a thread must own whole heads for RoPE");
-    const int b = ri.gm / e.ntok, t = ri.gm % e.ntok;
+    const int t = ri.t;
+    const int t0 = ri.t - stg.lane;                   // first row of this warp
 #pragma unroll 1
     for (int c = 0; c < NCOLS; c += 64) {
       float lo[32], hi[32];
       tmem_ld_f32x32(taddr + c, lo);
       tmem_ld_f32x32(taddr + c + 32, hi);
-      if (ri.valid) {
-        const int n = n0 + c;
-        const int which = n / e.D;
-        const int head = (n % e.D) >> 6;
-        add_vec32(e.bias + n, lo);
-        add_vec32(e.bias + n + 32, hi);
-        const size_t bh = static_cast<size_t>(b) * e.heads + head;
-        if (which == 2) {
-          __nv_bfloat16* dst = e.vt + bh * 64 * e.vt_pitch + t;
-  #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            dst[static_cast<size_t>(i) * e.vt_pitch] = __float2bfloat16_rn(lo[i]);
-            dst[static_cast<size_t>(i + 32) * e.vt_pitch] = __float2bfloat16_rn(hi[i]);
-          }
-        } else {
-          if (t >= 5) {
-            const float4* cs = reinterpret_cast<const float4*>(e.rope_cos + static_cast<size_t>(t - 5) * 32);
-            const float4* sn = reinterpret_cast<const float4*>(e.rope_sin + static_cast<size_t>(t - 5) * 32);
-  #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 c4 = __ldg(cs + i), s4 = __ldg(sn + i);
-              const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-  #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float a = lo[4 * i + j], bb = hi[4 * i + j];
-                lo[4 * i + j] = a * cc[j] - bb * ss[j];     // x*cos + (-x2)*sin
-                hi[4 * i + j] = bb * cc[j] + a * ss[j];     // x*cos + ( x1)*sin
-              }
+      const int n = n0 + c;
+      const int which = n / e.D;
+      const int head = (n % e.D) >> 6;
+      add_vec32(e.bias + n, lo);
+      add_vec32(e.bias + n + 32, hi);
+      if (which < 2) {
+        if (ri.valid && t >= 5) {
+          const float4* cs = reinterpret_cast<const float4*>(e.rope_cos + static_cast<size_t>(t - 5) * 32);
+          const float4* sn = reinterpret_cast<const float4*>(e.rope_sin + static_cast<size_t>(t - 5) * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 c4 = __ldg(cs + i), s4 = __ldg(sn + i);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a = lo[4 * i + j], bb = hi[4 * i + j];
+              lo[4 * i + j] = a * cc[j] - bb * ss[j];     // x*cos + (-x2)*sin
+              hi[4 * i + j] = bb * cc[j] + a * ss[j];     // x*cos + ( x1)*sin
             }
           }
-          if (which == 0) {
-  #pragma unroll
-            for (int i = 0; i < 32; ++i) { lo[i] *= e.qscale; hi[i] *= e.qscale; }
-          }
-          __nv_bfloat16* dst = (which == 0 ? e.q : e.k) + (bh * e.ntok + t) * 64;
-          store_bf16x32(dst, lo);
-          store_bf16x32(dst + 32, hi);
         }
+        if (which == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { lo[i] *= e.qscale; hi[i] *= e.qscale; }
+        }
+      }
+      __nv_bfloat16* base = (which == 0 ? e.q : which == 1 ? e.k : e.v) +
+                            (static_cast<size_t>(ri.b) * e.heads + head) * e.ntok * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t w[16];
+        if (half == 0) pack_bf16x32(lo, w); else pack_bf16x32(hi, w);
+        stg.write(w);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int tr = t0 + stg.row(it);
+          const uint4 d = stg.read(it);
+          if (tr < e.ntok) *reinterpret_cast<uint4*>(base + static_cast<size_t>(tr) * 64 + half * 32 + stg.seg() * 8) = d;
+        }
+        __syncwarp();
       }
     }
   }
@@ -366,39 +400,53 @@ struct EpiQKV {
 //      optionally also emits the bf16 tap (patch rows only) that the DPT head reads (model.py:72-84)
 struct EpiResidual {
   struct Params {
-    float* x;             // [M, D] fp32, read-modify-write
+    float* x;             // [B * ntok, D] fp32, read-modify-write
     const float* bias;    // [D]
     const float* lambda;  // [D]
     __nv_bfloat16* tap;   // [B * npatch, D] or nullptr
     int ntok, npatch, D;
   };
   template <int NCOLS>
-  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
-    float* xr = e.x + static_cast<size_t>(ri.gm) * e.D + n0;
-    const int b = ri.gm / e.ntok, t = ri.gm % e.ntok;
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
+    const int t0 = ri.t - stg.lane;
+    float* xb = e.x + static_cast<size_t>(ri.b) * e.ntok * e.D + n0 + stg.seg() * 4;
+    __nv_bfloat16* tb = e.tap == nullptr ? nullptr : e.tap + static_cast<size_t>(ri.b) * e.npatch * e.D + n0 + stg.seg() * 4;
 #pragma unroll 1
-    for (int c = 0; c < NCOLS; c += 32) {
-      float v[32];
-      tmem_ld_f32x32(taddr + c, v);
-      if (ri.valid) {
-        add_vec32(e.bias + n0 + c, v);
-        const float4* l4 = reinterpret_cast<const float4*>(e.lambda + n0 + c);
-        float4* x4 = reinterpret_cast<float4*>(xr + c);
-  #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 l = __ldg(l4 + i);
-          float4 xv = x4[i];
-          xv.x = fmaf(v[4 * i + 0], l.x, xv.x);
-          xv.y = fmaf(v[4 * i + 1], l.y, xv.y);
-          xv.z = fmaf(v[4 * i + 2], l.z, xv.z);
-          xv.w = fmaf(v[4 * i + 3], l.w, xv.w);
-          x4[i] = xv;
-          v[4 * i + 0] = xv.x; v[4 * i + 1] = xv.y; v[4 * i + 2] = xv.z; v[4 * i + 3] = xv.w;
-        }
-        if (e.tap != nullptr && t >= 5) {
-          store_bf16x32(e.tap + (static_cast<size_t>(b) * e.npatch + (t - 5)) * e.D + n0 + c, v);
+    for (int c = 0; c < NCOLS; c += 16) {
+      float v[16];
+      tmem_ld_f32x16(taddr + c, v);
+      uint32_t w[16];
+      const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0 + c);
+      const float4* l4 = reinterpret_cast<const float4*>(e.lambda + n0 + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bv = __ldg(b4 + i), lv = __ldg(l4 + i);
+        w[4 * i + 0] = __float_as_uint((v[4 * i + 0] + bv.x) * lv.x);
+        w[4 * i + 1] = __float_as_uint((v[4 * i + 1] + bv.y) * lv.y);
+        w[4 * i + 2] = __float_as_uint((v[4 * i + 2] + bv.z) * lv.z);
+        w[4 * i + 3] = __float_as_uint((v[4 * i + 3] + bv.w) * lv.w);
+      }
+      stg.write(w);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int tr = t0 + stg.row(it);
+        const uint4 d = stg.read(it);
+        if (tr < e.ntok) {
+          float4* xp = reinterpret_cast<float4*>(xb + static_cast<size_t>(tr) * e.D + c);
+          float4 xv = *xp;
+          xv.x += __uint_as_float(d.x); xv.y += __uint_as_float(d.y);
+          xv.z += __uint_as_float(d.z); xv.w += __uint_as_float(d.w);
+          *xp = xv;
+          if (tb != nullptr && tr >= 5) {
+            uint2 o;
+            o.x = pack_bf16x2(xv.x, xv.y);
+            o.y = pack_bf16x2(xv.z, xv.w);
+            *reinterpret_cast<uint2*>(tb + static_cast<size_t>(tr - 5) * e.D + c) = o;
+          }
         }
       }
+      __syncwarp();
     }
   }
 };
@@ -406,23 +454,32 @@ struct EpiResidual {
 // ---- up_proj: out = gelu_erf(acc + bias) in bf16  (HF:385-386, hidden_act "gelu" = exact erf form)
 struct EpiGelu {
   struct Params {
-    __nv_bfloat16* out;   // [M, ld]
+    __nv_bfloat16* out;   // [B * ntok, ld]
     const float* bias;
-    int ld;
+    int ld, ntok;
   };
   template <int NCOLS>
-  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
-    __nv_bfloat16* dst = e.out + static_cast<size_t>(ri.gm) * e.ld + n0;
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
+    const int t0 = ri.t - stg.lane;
+    __nv_bfloat16* ob = e.out + static_cast<size_t>(ri.b) * e.ntok * e.ld + n0 + stg.seg() * 8;
 #pragma unroll 1
     for (int c = 0; c < NCOLS; c += 32) {
       float v[32];
       tmem_ld_f32x32(taddr + c, v);
-      if (ri.valid) {
-        add_vec32(e.bias + n0 + c, v);
-  #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        store_bf16x32(dst + c, v);
+      add_vec32(e.bias + n0 + c, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      uint32_t w[16];
+      pack_bf16x32(v, w);
+      stg.write(w);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int tr = t0 + stg.row(it);
+        const uint4 d = stg.read(it);
+        if (tr < e.ntok) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(tr) * e.ld + c) = d;
       }
+      __syncwarp();
     }
   }
 };
@@ -446,7 +503,7 @@ struct EpiConv {
     int cout, oh, ow;             // output tensor (B, oh, ow, cout)
   };
   template <int NCOLS>
-  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
     int b, h, w, a = e.ph_h, bb = e.ph_w, ch = n0;
     if (e.linear) {
       const int per = e.hin * e.win;
@@ -509,7 +566,7 @@ struct EpiMask {
     int S, K;
   };
   template <int NCOLS>
-  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
     (void)n0;
 #pragma unroll 1
     for (int k = 0; k < NCOLS / 32; ++k) {
@@ -540,7 +597,7 @@ struct EpiStoreF32 {
     int ld;
   };
   template <int NCOLS>
-  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr) {
+  static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
     float* dst = e.out + static_cast<size_t>(ri.gm) * e.ld + n0;
 #pragma unroll 1
     for (int c = 0; c < NCOLS; c += 32) {

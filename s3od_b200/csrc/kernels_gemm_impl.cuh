@@ -6,7 +6,7 @@ namespace s3od {
 
 template <int BN, int AMODE, class Epi, int EPI_WARPS>
 cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI_WARPS>;
   auto kern = gemm_tc_kernel<BN, AMODE, Epi, EPI_WARPS>;
   static bool configured = false;
   if (!configured) {

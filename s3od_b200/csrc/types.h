@@ -32,7 +32,7 @@ struct PostDesc {              // one output image of the post-process
 struct AttnParams {
   CUtensorMap tma_q;    // (64 d, ntok, B*H)  box (64, 128, 1)
   CUtensorMap tma_k;    // (64 d, ntok, B*H)  box (64, 128, 1)
-  CUtensorMap tma_vt;   // (ntok, 64 d, B*H)  box (64, 64, 1)
+  CUtensorMap tma_v;    // (64 d, ntok, B*H)  box (64, 128, 1); consumed as an MN-major B operand
   __nv_bfloat16* out;   // [B * ntok, heads * 64]
   int ntok, heads, kv_tiles;
 };

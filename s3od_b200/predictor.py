@@ -101,10 +101,15 @@ class BackgroundRemoval:
         side = self._copy_stream
         pending = []
         step = max(1, min(model.max_batch, model.micro_batch))
-        for s0 in range(0, len(arrays), step):
+        if getattr(self, "_slot_free", None) is None:
+            self._slot_free = [None, None]                      # event: the slot's device buffers have been copied out
+        for ci, s0 in enumerate(range(0, len(arrays), step)):
             chunk = arrays[s0:s0 + step]
+            slot = ci & 1                                       # two sets of reusable device output buffers
+            if self._slot_free[slot] is not None:
+                main.wait_event(self._slot_free[slot])
             d_imgs = [torch.from_numpy(a).to(dev, non_blocking=True) for a in chunk]
-            _, outs, ious, best = model.run_u8(d_imgs)
+            _, outs, ious, best = model.run_u8(d_imgs, slot=slot)
             done = torch.cuda.Event()
             done.record(main)
             side.wait_event(done)
@@ -116,8 +121,9 @@ class BackgroundRemoval:
                     hm = torch.empty(all_masks.shape, dtype=all_masks.dtype, pin_memory=True).copy_(all_masks, non_blocking=True)
                     hr = torch.empty(rgba.shape, dtype=rgba.dtype, pin_memory=True).copy_(rgba, non_blocking=True)
                     host.append((hm, hr))
-                for t in [ious, best] + [x for pair in outs for x in pair] + d_imgs:
+                for t in d_imgs:
                     t.record_stream(side)
+                self._slot_free[slot] = side.record_event()
             pending.append((host, h_ious, h_best))
         side.synchronize()
         results: List[RemovalResult] = []

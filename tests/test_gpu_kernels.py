@@ -62,12 +62,9 @@ def test_attention(lib, B, H, ntok):
     q = (torch.randn(B * H, ntok, 64, device="cuda", generator=g) * 1.5).bfloat16()
     k = (torch.randn(B * H, ntok, 64, device="cuda", generator=g) * 1.5).bfloat16()
     v = torch.randn(B * H, ntok, 64, device="cuda", generator=g).bfloat16()
-    pitch = (ntok + 7) // 8 * 8
-    vt = torch.zeros(B * H, 64, pitch, device="cuda", dtype=torch.bfloat16)
-    vt[:, :, :ntok] = v.transpose(1, 2)
     qs = (q.float() * (0.125 * 1.4426950408889634)).bfloat16()
     out = torch.full((B * ntok, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
-    assert lib.s3od_op_attention(qs.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, ntok, pitch, _st()) == 0
+    assert lib.s3od_op_attention(qs.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, ntok, _st()) == 0
     torch.cuda.synchronize()
     s = (qs.float() @ k.float().transpose(1, 2)) * 0.6931471805599453
     ref = (torch.softmax(s, -1) @ v.float()).reshape(B, H, ntok, 64).permute(0, 2, 1, 3).reshape(B * ntok, H * 64)

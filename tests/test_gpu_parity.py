@@ -3,7 +3,10 @@
 Tolerances (bf16 operands, fp32 accumulation; BASELINE.json north_star "stated bf16 tolerance").  Rounding only the
 WEIGHTS to bf16 already moves sigmoid masks by up to 2e-2 on these seeded weights (tests/test_host_cpu.py), so:
     stage tensors     rel-L2 <= 2.5e-2
-    sigmoid masks     max-abs <= 4e-2, mean-abs <= 6e-3, IoU of masks thresholded at 0.5 >= 0.99
+    sigmoid masks     max-abs <= 4e-2, mean-abs <= 6e-3; masks thresholded at 0.5: IoU >= 0.985 and NOT ONE flipped pixel
+                      among those whose reference logit is further than 0.25 from the threshold.  (The seeded weights give
+                      soft masks - logit std ~3 - so ~1 % of all pixels sit within the ~1.3 % relative logit error of the
+                      threshold; that band alone costs up to 1.5 % IoU whatever the logit scale.)
     IoU logits        max-abs <= 3e-2;  sigmoid(IoU) max-abs <= 1e-2;  best-mask index exact
     preprocess        bit-exact (integer resize + LUT);  postprocess on given logits <= 2e-6;  alpha exact w.r.t. own mask
 """
@@ -24,6 +27,11 @@ pytestmark = pytest.mark.gpu
 CKPT = "/tmp/s3od_synth_vitb_seed0.pt"
 
 
+def synth_sd():
+    from s3od_b200.synth import synth_state_dict
+    return synth_state_dict(VITB, 0)
+
+
 def _rel(a, b):
     a, b = a.float(), b.float()
     return float((a - b).norm() / (b.norm() + 1e-12))
@@ -33,14 +41,17 @@ def _mask_metrics(logits, ref_logits):
     a, b = torch.sigmoid(logits.float()), torch.sigmoid(ref_logits.float())
     inter = float(((a > 0.5) & (b > 0.5)).sum())
     union = float(((a > 0.5) | (b > 0.5)).sum())
-    return float((a - b).abs().max()), float((a - b).abs().mean()), inter / max(union, 1.0)
+    confident = ref_logits.float().abs() > 0.25
+    flips = int((((a > 0.5) != (b > 0.5)) & confident).sum())
+    return float((a - b).abs().max()), float((a - b).abs().mean()), inter / max(union, 1.0), flips
 
 
 def _assert_masks(logits, ref_logits):
-    mx, mean, iou = _mask_metrics(logits, ref_logits)
+    mx, mean, iou, flips = _mask_metrics(logits, ref_logits)
     assert mx <= 4e-2, f"sigmoid max-abs {mx}"
     assert mean <= 6e-3, f"sigmoid mean-abs {mean}"
-    assert iou >= 0.99, f"thresholded IoU {iou}"
+    assert iou >= 0.985, f"thresholded IoU {iou}"
+    assert flips == 0, f"{flips} pixels flipped although their reference logit is > 0.25 away from the threshold"
 
 
 @pytest.fixture(scope="module")
@@ -188,7 +199,9 @@ def test_remove_background_matches_reference_golden(predictors, golden_dir, name
     d = np.abs(res.all_masks - g["all_masks"])
     assert d.max() <= 4e-2 and d.mean() <= 6e-3
     a, b = res.all_masks > 0.5, g["all_masks"] > 0.5
-    assert (a & b).sum() / max((a | b).sum(), 1) >= 0.99
+    assert (a & b).sum() / max((a | b).sum(), 1) >= 0.985
+    confident = np.abs(g["all_masks"] - 0.5) > 0.06                      # |logit| > 0.25
+    assert not ((a != b) & confident).any()
     assert np.abs(res.all_ious - g["all_ious"]).max() <= 1e-2
     assert int(res.all_ious.argmax()) == int(g["all_ious"].argmax())
     # reference contract tests (tests/test_fixture_inference.py:92-116, 73-89)
@@ -241,6 +254,9 @@ def test_full_size_against_reference_golden(predictors, golden_dir):
     res = br.remove_background(img)
     d = np.abs(res.all_masks[:, 5::16, 3::16] - g["all_masks_sub"])
     assert d.max() <= 4e-2 and d.mean() <= 6e-3
+    # every pixel, against the oracle run on the GPU box's CPU (the fixture only holds a 1/256 sub-sample)
+    ref = om.forward(synth_sd(), torch.from_numpy(x), VITB)
+    _assert_masks(out["pred_masks"].cpu(), ref["pred_masks"])
     assert int(res.all_ious.argmax()) == int(g["all_ious"].argmax())
     assert np.abs(res.all_ious - g["all_ious"]).max() <= 1e-2
     # size-independent properties at full size

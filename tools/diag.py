@@ -83,12 +83,9 @@ def diag_attn():
         q = (torch.randn(B * H, ntok, 64, device="cuda", generator=g) * 1.5).bfloat16()
         k = (torch.randn(B * H, ntok, 64, device="cuda", generator=g) * 1.5).bfloat16()
         v = torch.randn(B * H, ntok, 64, device="cuda", generator=g).bfloat16()
-        pitch = (ntok + 7) // 8 * 8
-        vt = torch.zeros(B * H, 64, pitch, device="cuda", dtype=torch.bfloat16)
-        vt[:, :, :ntok] = v.transpose(1, 2)
         qs = (q.float() * (0.125 * 1.4426950408889634)).bfloat16()
         out = torch.full((B * ntok, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
-        rc = lib.s3od_op_attention(qs.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, ntok, pitch, _st())
+        rc = lib.s3od_op_attention(qs.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, ntok, _st())
         torch.cuda.synchronize()
         s = (qs.float() @ k.float().transpose(1, 2)) * 0.6931471805599453
         ref = torch.softmax(s, -1) @ v.float()
@@ -98,14 +95,14 @@ def diag_attn():
     B, H, ntok = 8, 12, 4101
     q = torch.randn(B * H, ntok, 64, device="cuda").bfloat16()
     k = torch.randn(B * H, ntok, 64, device="cuda").bfloat16()
-    vt = torch.randn(B * H, 64, 4104, device="cuda").bfloat16()
+    v = torch.randn(B * H, ntok, 64, device="cuda").bfloat16()
     out = torch.empty(B * ntok, H * 64, device="cuda", dtype=torch.bfloat16)
     for _ in range(2):
-        lib.s3od_op_attention(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, ntok, 4104, _st())
+        lib.s3od_op_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, ntok, _st())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        lib.s3od_op_attention(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, ntok, 4104, _st())
+        lib.s3od_op_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, ntok, _st())
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
@@ -194,6 +191,68 @@ def diag_pipe():
 
 
 FAMILIES = {"gemm": diag_gemm, "ln": diag_ln, "attn": diag_attn, "conv": diag_conv, "model": diag_model, "pipe": diag_pipe}
+
+def diag_step():
+    """Time preprocess / forward / postprocess of one batch separately (CUDA events), with and without per-op events."""
+    from s3od_b200.synth import synth_state_dict, synth_noise_image
+    sd = synth_state_dict(VITB, 0)
+    B, S = 16, 1024
+    m = B200DPTSegmentation(sd, VITB, S, "cuda:0", max_batch=B, micro_batch=8)
+    imgs = [torch.from_numpy(synth_noise_image(S, S, seed=i)).cuda() for i in range(B)]
+    for prof in (False, True, False):
+        m.profile_enable(prof)
+        for it in range(3):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            t0 = time.perf_counter()
+            ev[0].record()
+            pads = m.preprocess(imgs)
+            ev[1].record()
+            out = m._forward_staged(B)
+            ev[2].record()
+            t1 = time.perf_counter()
+            res = m.postprocess(out["pred_masks"], out["pred_iou"], imgs, pads)
+            ev[3].record()
+            t2 = time.perf_counter()
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            print(f"profile={prof} it={it}: pre {ev[0].elapsed_time(ev[1]):.2f} ms, fwd {ev[1].elapsed_time(ev[2]):.2f} ms, "
+                  f"post {ev[2].elapsed_time(ev[3]):.2f} ms | host: launch fwd {1e3 * (t1 - t0):.2f} ms, post {1e3 * (t2 - t1):.2f} ms, "
+                  f"sync {1e3 * (t3 - t2):.2f} ms", flush=True)
+        if prof:
+            rows = m.profile_read()
+            print("   per-op sum", sum(r[3] for r in rows) / 3, "ms per iteration")
+    m.close()
+
+
+FAMILIES["step"] = diag_step
+
+
+def diag_stall():
+    """Find intermittent host stalls: time torch.empty and the library calls separately over many iterations."""
+    from s3od_b200.synth import synth_state_dict, synth_noise_image
+    from s3od_b200.engine import _check, _stream_ptr
+    sd = synth_state_dict(VITB, 0)
+    B, S = 16, 1024
+    m = B200DPTSegmentation(sd, VITB, S, "cuda:0", max_batch=B, micro_batch=8)
+    imgs = [torch.from_numpy(synth_noise_image(S, S, seed=i)).cuda() for i in range(B)]
+    pads = m.preprocess(imgs)
+    keep = None
+    for it in range(12):
+        t0 = time.perf_counter()
+        masks = torch.empty((B, 3, S, S), dtype=torch.float32, device="cuda")
+        ious = torch.empty((B, 3), dtype=torch.float32, device="cuda")
+        t1 = time.perf_counter()
+        _check(m.lib, m.lib.s3od_forward(m._ctx, B, masks.data_ptr(), ious.data_ptr(), _stream_ptr(m.device)), "fwd")
+        t2 = time.perf_counter()
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        keep = (masks, ious) if it % 2 == 0 else keep
+        print(f"it={it}: alloc {1e3 * (t1 - t0):.2f} ms, forward call {1e3 * (t2 - t1):.2f} ms, sync {1e3 * (t3 - t2):.2f} ms", flush=True)
+    m.close()
+
+
+FAMILIES["stall"] = diag_stall
+
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
