@@ -109,6 +109,9 @@ int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d
 int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin,
                     int cout, int relu, s3od_stream stream);
 
+/* debug aid: per-tile clock64() stamps of one attention CTA (only filled when S3OD_ATTN_TRACE=1 is set) */
+int s3od_debug_attn_trace(long long* host_out /* [64][8] */);
+
 #ifdef __cplusplus
 }
 #endif

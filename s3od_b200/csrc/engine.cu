@@ -804,6 +804,13 @@ int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d
   return S3OD_OK;
 }
 
+// debug: copies the 64 x 8 clock64() stamps written by the traced attention CTA (S3OD_ATTN_TRACE=1) to the host
+int s3od_debug_attn_trace(long long* host_out) {
+  if (g_attn_trace == nullptr || host_out == nullptr) return fail(S3OD_ERR_STATE, "attention tracing is off (set S3OD_ATTN_TRACE=1)");
+  CK(cudaMemcpy(host_out, g_attn_trace, 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return S3OD_OK;
+}
+
 int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin, int cout,
                     int relu, s3od_stream stream) {
   if (cin % 64 != 0 || cout % 256 != 0) return fail(S3OD_ERR_ARG, "s3od_op_conv3x3 needs cin % 64 == 0 and cout % 256 == 0");

@@ -3,7 +3,11 @@
 #include "elementwise.cuh"
 #include "launch.h"
 
+#include <cstdlib>
+
 namespace s3od {
+
+long long* g_attn_trace = nullptr;
 
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   static bool configured = false;
@@ -12,7 +16,16 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  attention_kernel<<<dim3(q_tiles, bh), kAttnThreads, kAttnSmemBytes, stream>>>(p);
+  AttnParams q = p;
+  static long long* trace_buf = nullptr;      // S3OD_ATTN_TRACE=1: clock64() stamps of one CTA, read back with s3od_debug_attn_trace
+  static const bool want_trace = getenv("S3OD_ATTN_TRACE") != nullptr;
+  if (want_trace && trace_buf == nullptr) {
+    cudaMalloc(&trace_buf, 64 * 8 * sizeof(long long));
+    cudaMemset(trace_buf, 0, 64 * 8 * sizeof(long long));
+  }
+  q.trace = trace_buf;
+  g_attn_trace = trace_buf;
+  attention_kernel<<<dim3(q_tiles, bh), kAttnThreads, kAttnSmemBytes, stream>>>(q);
   return cudaGetLastError();
 }
 

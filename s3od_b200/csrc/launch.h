@@ -8,6 +8,7 @@ namespace s3od {
 template <int BN, int AMODE, class Epi, int EPI_WARPS>
 cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stream);
 
+extern long long* g_attn_trace;
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream);
 cudaError_t launch_layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* y, int M, int D, float eps,
                              cudaStream_t stream);
