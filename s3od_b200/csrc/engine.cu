@@ -375,8 +375,8 @@ bool build_plan(s3od_ctx* c) {
       EpiQKV::Params e{};
       e.q = aptr<bf16>(c, "q"); e.k = aptr<bf16>(c, "k"); e.v = aptr<bf16>(c, "v");
       e.bias = wptr<float>(c, pre + "qkv.b");
-      e.rope_cos = wptr<float>(c, "rope.cos"); e.rope_sin = wptr<float>(c, "rope.sin");
       e.ntok = ntok; e.heads = H; e.D = D;
+      e.grid_w = g; e.inv_gh = 1.0f / g; e.inv_gw = 1.0f / g;
       e.qscale = 0.125f * 1.4426950408889634f;
       if (!add_linear<256, EpiQKV, 8>(c, pre + "qkv", xn, MT, ntok, D, wptr<bf16>(c, pre + "qkv.w"), 3 * D, e, false, true)) return false;
     }
@@ -541,7 +541,7 @@ bool build_plan(s3od_ctx* c) {
 }
 
 std::vector<std::string> required_tensors(const s3od_ctx* c) {
-  std::vector<std::string> r = {"patch.w", "patch.b", "prefix", "rope.cos", "rope.sin", "pre.lut"};
+  std::vector<std::string> r = {"patch.w", "patch.b", "prefix", "pre.lut"};
   for (int l = 0; l < c->L; ++l) {
     const std::string p = "enc." + std::to_string(l) + ".";
     for (const char* s : {"ln1.w", "ln1.b", "qkv.w", "qkv.b", "o.w", "o.b", "ls1", "ln2.w", "ln2.b", "up.w", "up.b", "down.w", "down.b", "ls2"})

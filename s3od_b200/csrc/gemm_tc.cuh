@@ -212,9 +212,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.n_tiles;
-      const int n_blk = tile % p.n_tiles;
+    auto row_info = [&](int m_blk) {
       RowInfo ri;
       if (AMODE == A_LINEAR) {
         ri.h = ri.w = 0;
@@ -238,6 +236,17 @@ gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
         ri.gm = 0;
         ri.t = 0;
         ri.valid = ri.h < p.geom.H && ri.w < p.geom.W;
+      }
+      return ri;
+    };
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const RowInfo ri = row_info(tile / p.n_tiles);
+      if constexpr (Epi::kPrefetch) {
+        // pull the residual rows this thread will read-modify-write into L2 one tile ahead of their use
+        if (tile == static_cast<int>(blockIdx.x)) Epi::prefetch(p.epi, ri, n_blk * BN + col_begin, kColsPerGroup);
+        const int nxt = tile + gridDim.x;
+        if (nxt < total_tiles) Epi::prefetch(p.epi, row_info(nxt / p.n_tiles), (nxt % p.n_tiles) * BN + col_begin, kColsPerGroup);
       }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
@@ -301,6 +310,7 @@ S3OD_DEVICE void add_vec32(const float* __restrict__ src, float (&v)[32]) {
 
 // ---- patch embedding: x[b, 5 + p, :] = acc + bias   (HF:75-92; the 5 prefix rows are filled by fill_prefix_kernel)
 struct EpiPatch {
+  static constexpr bool kPrefetch = false;
   struct Params {
     float* x;            // [B * ntok, D] fp32 residual stream
     const float* bias;   // [D]
@@ -336,14 +346,15 @@ S3OD_DEVICE void pack_bf16x32(const float (&v)[32], uint32_t (&w)[16]) {
 // ---- fused q/k/v projection: + bias, RoPE on the patch rows of q and k (HF:238-268), softmax scale folded into q,
 //      head-major stores Q, K, V [B*H, ntok, 64] (V is consumed as an MN-major B operand by the attention kernel)
 struct EpiQKV {
+  static constexpr bool kPrefetch = false;
   struct Params {
     __nv_bfloat16* q;
     __nv_bfloat16* k;
     __nv_bfloat16* v;
     const float* bias;      // [3D], k part zero (config.json: key_bias=false)
-    const float* rope_cos;  // [npatch, 32]
-    const float* rope_sin;  // [npatch, 32]
     int ntok, heads, D;
+    int grid_w;             // patches per image row: token t >= 5 sits at (y, x) = divmod(t - 5, grid_w)
+    float inv_gh, inv_gw;   // 1 / patch-grid height, width
     float qscale;           // head_dim^-0.5 * log2(e)
   };
   template <int NCOLS>
@@ -363,18 +374,23 @@ struct EpiQKV {
       add_vec32(e.bias + n + 32, hi);
       if (which < 2) {
         if (ri.valid && t >= 5) {
-          const float4* cs = reinterpret_cast<const float4*>(e.rope_cos + static_cast<size_t>(t - 5) * 32);
-          const float4* sn = reinterpret_cast<const float4*>(e.rope_sin + static_cast<size_t>(t - 5) * 32);
+          // RoPE angles recomputed in registers (DINOv3ViTRopePositionEmbedding, HF:168-200): patch-centre coordinates
+          // in [-1, 1], angle = 2 pi * coord * 100^(-i/16); dims 0..15 rotate with y, 16..31 with x, and dim d pairs
+          // with d + 32.  The SFU is idle in this kernel, whereas a (P, 64) table costs 16 scattered 16-byte loads per
+          // row and head, which is what the epilogue used to wait on.
+          const int pidx = t - 5;
+          const int py = pidx / e.grid_w, px = pidx - py * e.grid_w;
+          const float ay = 6.283185307179586f * (2.0f * ((py + 0.5f) * e.inv_gh) - 1.0f);
+          const float ax = 6.283185307179586f * (2.0f * ((px + 0.5f) * e.inv_gw) - 1.0f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 c4 = __ldg(cs + i), s4 = __ldg(sn + i);
-            const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float a = lo[4 * i + j], bb = hi[4 * i + j];
-              lo[4 * i + j] = a * cc[j] - bb * ss[j];     // x*cos + (-x2)*sin
-              hi[4 * i + j] = bb * cc[j] + a * ss[j];     // x*cos + ( x1)*sin
-            }
+          for (int i = 0; i < 32; ++i) {
+            // 100^(-(i % 16) / 16) = 2^(-(i % 16) * log2(100) / 16)
+            const float inv_freq = exp2f(-0.41524101186092029f * static_cast<float>(i & 15));
+            float sn, cs;
+            __sincosf((i < 16 ? ay : ax) * inv_freq, &sn, &cs);
+            const float a = lo[i], bb = hi[i];
+            lo[i] = a * cs - bb * sn;     // x*cos + (-x2)*sin
+            hi[i] = bb * cs + a * sn;     // x*cos + ( x1)*sin
           }
         }
         if (which == 0) {
@@ -405,6 +421,15 @@ struct EpiQKV {
 // ---- o_proj / down_proj: x += lambda * (acc + bias)  (LayerScale + residual, HF:440-441, 447-448);
 //      optionally also emits the bf16 tap (patch rows only) that the DPT head reads (model.py:72-84)
 struct EpiResidual {
+  static constexpr bool kPrefetch = true;
+  struct Params;
+  // the thread that owns accumulator row ri prefetches that row's ncols fp32 residual values (128-byte lines) into L2
+  template <class P>
+  static S3OD_DEVICE void prefetch(const P& e, const RowInfo& ri, int n0, int ncols) {
+    if (!ri.valid) return;
+    const float* xr = e.x + (static_cast<size_t>(ri.b) * e.ntok + ri.t) * e.D + n0;
+    for (int c = 0; c < ncols; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + c));
+  }
   struct Params {
     float* x;             // [B * ntok, D] fp32, read-modify-write
     const float* bias;    // [D]
@@ -459,6 +484,7 @@ struct EpiResidual {
 
 // ---- up_proj: out = gelu_erf(acc + bias) in bf16  (HF:385-386, hidden_act "gelu" = exact erf form)
 struct EpiGelu {
+  static constexpr bool kPrefetch = false;
   struct Params {
     __nv_bfloat16* out;   // [B * ntok, ld]
     const float* bias;
@@ -496,6 +522,7 @@ struct EpiGelu {
 //        A_LINEAR (k == stride ConvT as one GEMM): phase = n / cout, (a, b) = divmod(phase, up)
 //        A_CONV   (k4 s2 p1 ConvT, one launch per phase): (a, b) = (ph_h, ph_w)
 struct EpiConv {
+  static constexpr bool kPrefetch = false;
   struct Params {
     __nv_bfloat16* out;
     __nv_bfloat16* out_relu;      // nullable
@@ -564,6 +591,7 @@ struct EpiConv {
 // ---- merged mask heads (model.py:438-453, 462-467): the K 3x3 convs (64->32) run as one N = 32K conv;
 //      here: ReLU, then each head's 1x1 (32 -> 1) as an in-register dot product; planar fp32 logits (B, K, S, S).
 struct EpiMask {
+  static constexpr bool kPrefetch = false;
   struct Params {
     float* out;          // [B, K, S, S]
     const float* bias;   // [32K]
@@ -598,6 +626,7 @@ struct EpiMask {
 
 // ---- plain fp32 store (unit tests and the tiny classifier-free paths)
 struct EpiStoreF32 {
+  static constexpr bool kPrefetch = false;
   struct Params {
     float* out;
     int ld;

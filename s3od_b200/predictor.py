@@ -76,8 +76,10 @@ class BackgroundRemoval:
     def _to_uint8(image: Union[np.ndarray, Image.Image]) -> np.ndarray:
         if isinstance(image, Image.Image):
             return np.array(image.convert("RGB"))
-        Image.fromarray(image)          # the reference builds a PIL image here: same dtype / shape errors
-        return image
+        if isinstance(image, np.ndarray) and image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3:
+            return image                # the only layout the reference path handles end to end (predictor.py:106,131)
+        Image.fromarray(image)          # anything else: let PIL raise what it raises in the reference (predictor.py:106)
+        raise ValueError(f"expected an RGB uint8 array of shape (H, W, 3), got {getattr(image, 'shape', None)}")
 
     @torch.no_grad()
     def remove_background(self, image: Union[np.ndarray, Image.Image], threshold: float = 0.5) -> RemovalResult:
