@@ -85,7 +85,7 @@ class ClockSampler:
 def kernel_family(label: str) -> str:
     if label.endswith("attention"):
         return "attention"
-    if label.endswith((".ln1", ".ln2")):
+    if label.endswith((".ln1", ".ln2", "final_residual")):
         return "layernorm"
     if label.startswith("enc.") or label == "patch_embed":
         return "encoder_gemm"

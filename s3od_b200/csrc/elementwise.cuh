@@ -90,25 +90,47 @@ __global__ void fill_prefix_kernel(float* __restrict__ x, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// LayerNorm (eps 1e-5) over D of fp32 rows -> bf16 rows (the A operand of the following GEMM).  One warp per row,
-// the row lives in registers (two-pass mean / variance, fp32).  HF:411,416,433,445.
+// Residual add + LayerNorm (eps 1e-5), one warp per token row, the row lives in registers (fp32):
+//   if (dx)  x += dx            the LayerScale'd branch output the previous GEMM left in `dx` (HF:440-441, 447-448);
+//                               keeping the read-modify-write of the fp32 residual stream out of the GEMM epilogue makes
+//                               it a pure streaming pass with full memory-level parallelism
+//   if (tap) tap = bf16(x)      patch rows only: hidden_states[k][:, 5:] for the DPT head (model.py:72-84)
+//   if (y)   y = LN(x) in bf16  two-pass mean / variance (HF:411,416,433,445): the A operand of the next GEMM
 // ------------------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ b, __nv_bfloat16* __restrict__ y, int M,
-                                                        float eps) {
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const float* __restrict__ dx,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ tap, int M,
+                                                        int ntok, float eps) {
   constexpr int V = D / 128;      // float4 per lane
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
   float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = xr[lane + 32 * i];
+  if (dx != nullptr) {
+    const float4* dr = reinterpret_cast<const float4*>(dx + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 d = dr[lane + 32 * i];
+      v[i].x += d.x; v[i].y += d.y; v[i].z += d.z; v[i].w += d.w;
+      xr[lane + 32 * i] = v[i];
+    }
+  }
+  if (tap != nullptr) {
+    const int bimg = row / ntok, t = row - bimg * ntok;
+    if (t >= 5) {
+      uint2* tr = reinterpret_cast<uint2*>(tap + (static_cast<size_t>(bimg) * (ntok - 5) + (t - 5)) * D);
+#pragma unroll
+      for (int i = 0; i < V; ++i) tr[lane + 32 * i] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+    }
+  }
+  if (y == nullptr) return;
   float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
+  for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) * (1.0f / D);
   float q = 0.0f;
 #pragma unroll

@@ -302,6 +302,7 @@ bool build_plan(s3od_ctx* c) {
   bool ok = true;
   ok = ok && alloc_act(c, "patches", static_cast<size_t>(c->max_batch) * P * 768 * 2);
   ok = ok && alloc_act(c, "x", MT * D * 4);
+  ok = ok && alloc_act(c, "dx", MT * D * 4);
   ok = ok && alloc_act(c, "xn", MT * D * 2);
   ok = ok && alloc_act(c, "ctx", MT * D * 2);
   ok = ok && alloc_act(c, "q", MT * D * 2);
@@ -334,6 +335,7 @@ bool build_plan(s3od_ctx* c) {
   if (!ok) return false;
 
   float* x = aptr<float>(c, "x");
+  float* dx = aptr<float>(c, "dx");
   bf16* xn = aptr<bf16>(c, "xn");
   bf16* actx = aptr<bf16>(c, "ctx");
   bf16* hmid = aptr<bf16>(c, "hmid");
@@ -368,9 +370,16 @@ bool build_plan(s3od_ctx* c) {
     const std::string pre = "enc." + std::to_string(l) + ".";
     const float *ln1w = wptr<float>(c, pre + "ln1.w"), *ln1b = wptr<float>(c, pre + "ln1.b");
     const float *ln2w = wptr<float>(c, pre + "ln2.w"), *ln2b = wptr<float>(c, pre + "ln2.b");
-    c->plan.emplace_back(pre + "ln1", [=](int nb, int, float*, float*, cudaStream_t st) {
-      return launch_layernorm(x, ln1w, ln1b, xn, nb * ntok, D, 1e-5f, st);
-    });
+    {
+      // x += dx of the previous layer's MLP; hidden_states[l] is complete here, so this is where its tap is taken
+      bf16* tap = nullptr;
+      for (int j = 0; j < 4; ++j)
+        if (c->taps[j] == l) tap = aptr<bf16>(c, "tap" + std::to_string(j));
+      const float* dprev = l > 0 ? dx : nullptr;
+      c->plan.emplace_back(pre + "ln1", [=](int nb, int, float*, float*, cudaStream_t st) {
+        return launch_layernorm(x, dprev, ln1w, ln1b, xn, tap, nb * ntok, ntok, D, 1e-5f, st);
+      });
+    }
     {
       EpiQKV::Params e{};
       e.q = aptr<bf16>(c, "q"); e.k = aptr<bf16>(c, "k"); e.v = aptr<bf16>(c, "v");
@@ -384,23 +393,29 @@ bool build_plan(s3od_ctx* c) {
       return launch_attention(ap, (ntok + 127) / 128, nb * H, st);
     });
     {
-      EpiResidual::Params e{x, wptr<float>(c, pre + "o.b"), wptr<float>(c, pre + "ls1"), nullptr, ntok, P, D};
+      EpiResidual::Params e{dx, wptr<float>(c, pre + "o.b"), wptr<float>(c, pre + "ls1"), ntok, D};
       if (!add_linear<256, EpiResidual, 8>(c, pre + "o_proj", actx, MT, ntok, D, wptr<bf16>(c, pre + "o.w"), D, e, false, true)) return false;
     }
     c->plan.emplace_back(pre + "ln2", [=](int nb, int, float*, float*, cudaStream_t st) {
-      return launch_layernorm(x, ln2w, ln2b, xn, nb * ntok, D, 1e-5f, st);
+      return launch_layernorm(x, dx, ln2w, ln2b, xn, nullptr, nb * ntok, ntok, D, 1e-5f, st);
     });
     {
       EpiGelu::Params e{hmid, wptr<float>(c, pre + "up.b"), I, ntok};
       if (!add_linear<256, EpiGelu, 8>(c, pre + "up_proj", xn, MT, ntok, D, wptr<bf16>(c, pre + "up.w"), I, e, false, true)) return false;
     }
     {
-      bf16* tap = nullptr;
-      for (int j = 0; j < 4; ++j)
-        if (c->taps[j] == l + 1) tap = aptr<bf16>(c, "tap" + std::to_string(j));
-      EpiResidual::Params e{x, wptr<float>(c, pre + "down.b"), wptr<float>(c, pre + "ls2"), tap, ntok, P, D};
+      EpiResidual::Params e{dx, wptr<float>(c, pre + "down.b"), wptr<float>(c, pre + "ls2"), ntok, D};
       if (!add_linear<256, EpiResidual, 8>(c, pre + "down_proj", hmid, MT, ntok, I, wptr<bf16>(c, pre + "down.w"), D, e, false, true)) return false;
     }
+  }
+
+  {  // x += dx of the last needed layer; its output is the last tap (no LayerNorm: the final encoder.norm is dead code, F3)
+    bf16* tap = nullptr;
+    for (int j = 0; j < 4; ++j)
+      if (c->taps[j] == c->L) tap = aptr<bf16>(c, "tap" + std::to_string(j));
+    c->plan.emplace_back("enc.final_residual", [=](int nb, int, float*, float*, cudaStream_t st) {
+      return launch_layernorm(x, dx, nullptr, nullptr, nullptr, tap, nb * ntok, ntok, D, 1e-5f, st);
+    });
   }
 
   // ---- DPT head: projects + resize layers (model.py:193-211) --------------------------------------------------------
@@ -783,7 +798,8 @@ int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N,
 }
 
 int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void* d_y, int M, int D, float eps, s3od_stream stream) {
-  CK(launch_layernorm(d_x, d_w, d_b, static_cast<bf16*>(d_y), M, D, eps, static_cast<cudaStream_t>(stream)));
+  CK(launch_layernorm(const_cast<float*>(d_x), nullptr, d_w, d_b, static_cast<bf16*>(d_y), nullptr, M, M, D, eps,
+                      static_cast<cudaStream_t>(stream)));
   return S3OD_OK;
 }
 

@@ -418,30 +418,20 @@ struct EpiQKV {
   }
 };
 
-// ---- o_proj / down_proj: x += lambda * (acc + bias)  (LayerScale + residual, HF:440-441, 447-448);
-//      optionally also emits the bf16 tap (patch rows only) that the DPT head reads (model.py:72-84)
+// ---- o_proj / down_proj: dx = lambda * (acc + bias) in fp32 (LayerScale, HF:342-343).  The residual add x += dx is
+//      fused into the following layernorm_kernel, so this epilogue only streams stores.
 struct EpiResidual {
-  static constexpr bool kPrefetch = true;
-  struct Params;
-  // the thread that owns accumulator row ri prefetches that row's ncols fp32 residual values (128-byte lines) into L2
-  template <class P>
-  static S3OD_DEVICE void prefetch(const P& e, const RowInfo& ri, int n0, int ncols) {
-    if (!ri.valid) return;
-    const float* xr = e.x + (static_cast<size_t>(ri.b) * e.ntok + ri.t) * e.D + n0;
-    for (int c = 0; c < ncols; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + c));
-  }
+  static constexpr bool kPrefetch = false;
   struct Params {
-    float* x;             // [B * ntok, D] fp32, read-modify-write
+    float* dx;            // [B * ntok, D] fp32
     const float* bias;    // [D]
     const float* lambda;  // [D]
-    __nv_bfloat16* tap;   // [B * npatch, D] or nullptr
-    int ntok, npatch, D;
+    int ntok, D;
   };
   template <int NCOLS>
   static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
     const int t0 = ri.t - stg.lane;
-    float* xb = e.x + static_cast<size_t>(ri.b) * e.ntok * e.D + n0 + stg.seg() * 4;
-    __nv_bfloat16* tb = e.tap == nullptr ? nullptr : e.tap + static_cast<size_t>(ri.b) * e.npatch * e.D + n0 + stg.seg() * 4;
+    float* ob = e.dx + static_cast<size_t>(ri.b) * e.ntok * e.D + n0 + stg.seg() * 4;
 #pragma unroll 1
     for (int c = 0; c < NCOLS; c += 16) {
       float v[16];
@@ -463,19 +453,7 @@ struct EpiResidual {
       for (int it = 0; it < 4; ++it) {
         const int tr = t0 + stg.row(it);
         const uint4 d = stg.read(it);
-        if (tr < e.ntok) {
-          float4* xp = reinterpret_cast<float4*>(xb + static_cast<size_t>(tr) * e.D + c);
-          float4 xv = *xp;
-          xv.x += __uint_as_float(d.x); xv.y += __uint_as_float(d.y);
-          xv.z += __uint_as_float(d.z); xv.w += __uint_as_float(d.w);
-          *xp = xv;
-          if (tb != nullptr && tr >= 5) {
-            uint2 o;
-            o.x = pack_bf16x2(xv.x, xv.y);
-            o.y = pack_bf16x2(xv.z, xv.w);
-            *reinterpret_cast<uint2*>(tb + static_cast<size_t>(tr - 5) * e.D + c) = o;
-          }
-        }
+        if (tr < e.ntok) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(tr) * e.D + c) = d;
       }
       __syncwarp();
     }

@@ -29,14 +29,14 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
   return cudaGetLastError();
 }
 
-cudaError_t launch_layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* y, int M, int D, float eps,
-                             cudaStream_t stream) {
+cudaError_t launch_layernorm(float* x, const float* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,
+                             int ntok, int D, float eps, cudaStream_t stream) {
   const int rows_per_block = 8;
   const int grid = (M + rows_per_block - 1) / rows_per_block;
   if (D == 768)
-    layernorm_kernel<768><<<grid, 256, 0, stream>>>(x, w, b, y, M, eps);
+    layernorm_kernel<768><<<grid, 256, 0, stream>>>(x, dx, w, b, y, tap, M, ntok, eps);
   else if (D == 1024)
-    layernorm_kernel<1024><<<grid, 256, 0, stream>>>(x, w, b, y, M, eps);
+    layernorm_kernel<1024><<<grid, 256, 0, stream>>>(x, dx, w, b, y, tap, M, ntok, eps);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();
