@@ -47,17 +47,48 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const ImageDesc* __rest
   const int X = (idx % x8_per_row) << 3;
   const int ry = Y - d.pad_h;
   const bool row_in = ry >= 0 && ry < d.new_h;
+  const int rx0 = X - d.pad_w;
   const size_t prow = static_cast<size_t>(b) * g * g + (Y >> 4) * g + (X >> 4);
   __nv_bfloat16* dst = patches + prow * 768 + (Y & 15) * 16 + (X & 15);
+  uint8_t px[8][3];
+  // fast paths: all 8 pixels inside the resized image and the source row segment is 8- / 16-byte aligned
+  const bool inside = row_in && rx0 >= 0 && rx0 + 8 <= d.new_w;
+  if (inside && d.mode == 0 && ((d.w * 3) & 7) == 0 && (rx0 & 7) == 0) {
+    // 8 pixels = 24 contiguous bytes
+    const uint2* sp = reinterpret_cast<const uint2*>(d.src + (static_cast<size_t>(ry) * d.w + rx0) * 3);
+    uint2 v[3] = {__ldg(sp), __ldg(sp + 1), __ldg(sp + 2)};
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) px[i][c] = bytes[i * 3 + c];
+  } else if (inside && d.mode == 1 && ((d.w * 3) & 15) == 0 && (rx0 & 7) == 0) {
+    // exact 2x: (a + b + c + d + 2) >> 2 over 2 source rows x 16 source pixels = 2 x 48 contiguous bytes
+    const uint4* r0 = reinterpret_cast<const uint4*>(d.src + (static_cast<size_t>(2 * ry) * d.w + 2 * rx0) * 3);
+    const uint4* r1 = reinterpret_cast<const uint4*>(d.src + (static_cast<size_t>(2 * ry + 1) * d.w + 2 * rx0) * 3);
+    uint4 a[3] = {__ldg(r0), __ldg(r0 + 1), __ldg(r0 + 2)};
+    uint4 bq[3] = {__ldg(r1), __ldg(r1 + 1), __ldg(r1 + 2)};
+    const uint8_t* ba = reinterpret_cast<const uint8_t*>(a);
+    const uint8_t* bb = reinterpret_cast<const uint8_t*>(bq);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        px[i][c] = static_cast<uint8_t>((ba[i * 6 + c] + ba[i * 6 + 3 + c] + bb[i * 6 + c] + bb[i * 6 + 3 + c] + 2) >> 2);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rx = rx0 + i;
+      const bool in = row_in && rx >= 0 && rx < d.new_w;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) px[i][c] = in ? static_cast<uint8_t>(resized_px(d, ry, rx, c)) : 0;
+    }
+  }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rx = X + i - d.pad_w;
-      const int px = (row_in && rx >= 0 && rx < d.new_w) ? resized_px(d, ry, rx, c) : 0;
-      v[i] = s_lut[c * 256 + px];
-    }
+    for (int i = 0; i < 8; ++i) v[i] = s_lut[c * 256 + px[i][c]];
     *reinterpret_cast<uint4*>(dst + c * 256) = *reinterpret_cast<const uint4*>(v);
   }
 }
@@ -155,53 +186,66 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
 // ------------------------------------------------------------------------------------------------------------------
 // 2x bilinear up-sampling, align_corners=False, NHWC bf16 (FeatureFusionBlock, model.py:394-402; the following 1x1
 // out_conv has been applied at low resolution - it commutes with the interpolation because the weights sum to 1).
-// Thread = one output pixel x 8 channels.  With `pool` != nullptr each block also writes per-channel partial sums of
-// its outputs (deterministic two-stage average pool for the IoU head, model.py:185-191).
-// grid = (blocks_per_image, B), block = 256 threads = (C/8) channel groups x (256 / (C/8)) pixels per step.
+// Thread = one INPUT pixel x 8 channels -> the 2x2 output pixels it generates (9 taps read, 4 pixels written).  With
+// `pool` != nullptr each block also writes per-channel partial sums of its outputs (deterministic two-stage average
+// pool for the IoU head, model.py:185-191).
+// grid = (blocks_per_image, B), block = 256 threads = (C/8) channel groups x (256 / (C/8)) input pixels per step.
 // ------------------------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                          float* __restrict__ pool, int h, int w) {
   constexpr int CG = C / 8;                 // channel groups (threads along channels)
-  constexpr int PP = 256 / CG;              // pixels per block step
+  constexpr int PP = 256 / CG;              // input pixels per block step
   const int b = blockIdx.y;
   const int cg = threadIdx.x % CG;
   const int pl = threadIdx.x / CG;
-  const int OH = 2 * h, OW = 2 * w;
-  const int npix = OH * OW;
-  const int per_block = (npix + gridDim.x - 1) / gridDim.x;
-  const int p_begin = blockIdx.x * per_block;
-  const int p_end = min(npix, p_begin + per_block);
-  const __nv_bfloat16* ib = in + static_cast<size_t>(b) * h * w * C + cg * 8;
-  __nv_bfloat16* ob = out + static_cast<size_t>(b) * npix * C + cg * 8;
+  const int OW = 2 * w;
+  const int npix = h * w;
+  const __nv_bfloat16* ib = in + static_cast<size_t>(b) * npix * C + cg * 8;
+  __nv_bfloat16* ob = out + static_cast<size_t>(b) * 4 * npix * C + cg * 8;
   float psum[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) psum[i] = 0.0f;
-  for (int pix = p_begin + pl; pix < p_end; pix += PP) {
-    const int oy = pix / OW, ox = pix % OW;
-    // source coordinate (o + 0.5)/2 - 0.5, clamped at 0:  even o=2i -> taps (i-1: .25, i: .75), odd -> (i: .75, i+1: .25)
-    const int iy = oy >> 1, ix = ox >> 1;
-    const int y0 = (oy & 1) ? iy : max(iy - 1, 0), y1 = (oy & 1) ? min(iy + 1, h - 1) : iy;
-    const int x0 = (ox & 1) ? ix : max(ix - 1, 0), x1 = (ox & 1) ? min(ix + 1, w - 1) : ix;
-    const float wy0 = (oy & 1) ? 0.75f : (iy == 0 ? 0.0f : 0.25f), wy1 = 1.0f - wy0;
-    const float wx0 = (ox & 1) ? 0.75f : (ix == 0 ? 0.0f : 0.25f), wx1 = 1.0f - wx0;
-    const uint4 a = *reinterpret_cast<const uint4*>(ib + (static_cast<size_t>(y0) * w + x0) * C);
-    const uint4 bq = *reinterpret_cast<const uint4*>(ib + (static_cast<size_t>(y0) * w + x1) * C);
-    const uint4 c = *reinterpret_cast<const uint4*>(ib + (static_cast<size_t>(y1) * w + x0) * C);
-    const uint4 d = *reinterpret_cast<const uint4*>(ib + (static_cast<size_t>(y1) * w + x1) * C);
-    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {c.x, c.y, c.z, c.w},
-                   dv[4] = {d.x, d.y, d.z, d.w};
-    float r[8];
+  for (int ip = blockIdx.x * PP + pl; ip < npix; ip += gridDim.x * PP) {
+    const int iy = ip / w, ix = ip - iy * w;
+    const int ym = max(iy - 1, 0), yp = min(iy + 1, h - 1);
+    const int xm = max(ix - 1, 0), xp = min(ix + 1, w - 1);
+    // source coordinate (o + 0.5)/2 - 0.5 clamped at 0: output 2i uses taps (i-1: .25, i: .75) [(0, 1) at i = 0],
+    // output 2i+1 uses (i: .75, i+1: .25)
+    const float wl0 = ix == 0 ? 0.0f : 0.25f, wl1 = 1.0f - wl0;
+    const float wt0 = iy == 0 ? 0.0f : 0.25f, wt1 = 1.0f - wt0;
+    float L[3][8], R[3][8];                 // horizontally interpolated rows (ym, iy, yp) for output columns 2ix, 2ix+1
+    const int rows[3] = {ym, iy, yp};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      r[2 * i] = wy0 * (wx0 * bf16_lo(av[i]) + wx1 * bf16_lo(bv[i])) + wy1 * (wx0 * bf16_lo(cv[i]) + wx1 * bf16_lo(dv[i]));
-      r[2 * i + 1] = wy0 * (wx0 * bf16_hi(av[i]) + wx1 * bf16_hi(bv[i])) + wy1 * (wx0 * bf16_hi(cv[i]) + wx1 * bf16_hi(dv[i]));
+    for (int r = 0; r < 3; ++r) {
+      const __nv_bfloat16* rp = ib + static_cast<size_t>(rows[r]) * w * C;
+      const uint4 a = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(xm) * C);
+      const uint4 m = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(ix) * C);
+      const uint4 c = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(xp) * C);
+      const uint32_t av[4] = {a.x, a.y, a.z, a.w}, mv[4] = {m.x, m.y, m.z, m.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        L[r][2 * i] = wl0 * bf16_lo(av[i]) + wl1 * bf16_lo(mv[i]);
+        L[r][2 * i + 1] = wl0 * bf16_hi(av[i]) + wl1 * bf16_hi(mv[i]);
+        R[r][2 * i] = 0.75f * bf16_lo(mv[i]) + 0.25f * bf16_lo(cv[i]);
+        R[r][2 * i + 1] = 0.75f * bf16_hi(mv[i]) + 0.25f * bf16_hi(cv[i]);
+      }
     }
-    uint4 o;
-    o.x = pack_bf16x2(r[0], r[1]); o.y = pack_bf16x2(r[2], r[3]); o.z = pack_bf16x2(r[4], r[5]); o.w = pack_bf16x2(r[6], r[7]);
-    *reinterpret_cast<uint4*>(ob + static_cast<size_t>(pix) * C) = o;
+    float o00[8], o01[8], o10[8], o11[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) psum[i] += r[i];
+    for (int i = 0; i < 8; ++i) {
+      o00[i] = wt0 * L[0][i] + wt1 * L[1][i];
+      o01[i] = wt0 * R[0][i] + wt1 * R[1][i];
+      o10[i] = 0.75f * L[1][i] + 0.25f * L[2][i];
+      o11[i] = 0.75f * R[1][i] + 0.25f * R[2][i];
+      psum[i] += (o00[i] + o01[i]) + (o10[i] + o11[i]);
+    }
+    __nv_bfloat16* o0 = ob + (static_cast<size_t>(2 * iy) * OW + 2 * ix) * C;
+    __nv_bfloat16* o1 = o0 + static_cast<size_t>(OW) * C;
+    *reinterpret_cast<uint4*>(o0) = make_uint4(pack_bf16x2(o00[0], o00[1]), pack_bf16x2(o00[2], o00[3]), pack_bf16x2(o00[4], o00[5]), pack_bf16x2(o00[6], o00[7]));
+    *reinterpret_cast<uint4*>(o0 + C) = make_uint4(pack_bf16x2(o01[0], o01[1]), pack_bf16x2(o01[2], o01[3]), pack_bf16x2(o01[4], o01[5]), pack_bf16x2(o01[6], o01[7]));
+    *reinterpret_cast<uint4*>(o1) = make_uint4(pack_bf16x2(o10[0], o10[1]), pack_bf16x2(o10[2], o10[3]), pack_bf16x2(o10[4], o10[5]), pack_bf16x2(o10[6], o10[7]));
+    *reinterpret_cast<uint4*>(o1 + C) = make_uint4(pack_bf16x2(o11[0], o11[1]), pack_bf16x2(o11[2], o11[3]), pack_bf16x2(o11[4], o11[5]), pack_bf16x2(o11[6], o11[7]));
   }
   if (pool != nullptr) {
     __shared__ float red[PP][C + 1];
@@ -209,9 +253,9 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
     for (int i = 0; i < 8; ++i) red[pl][cg * 8 + i] = psum[i];
     __syncthreads();
     for (int ch = threadIdx.x; ch < C; ch += 256) {
-      float s = 0.0f;
-      for (int k = 0; k < PP; ++k) s += red[k][ch];
-      pool[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C + ch] = s;
+      float sacc = 0.0f;
+      for (int k = 0; k < PP; ++k) sacc += red[k][ch];
+      pool[(static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C + ch] = sacc;
     }
   }
 }
@@ -254,6 +298,79 @@ __global__ void __launch_bounds__(256) iou_head_kernel(const float* __restrict__
 // Thread = one output pixel; grid = (ceil(W/128), H, B)... x is the fastest dimension for coalesced stores.
 // ------------------------------------------------------------------------------------------------------------------
 S3OD_DEVICE float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+S3OD_DEVICE float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// Fast path (every image width a multiple of 4): one thread = 4 consecutive output pixels, 128-bit stores of the K mask
+// planes and of the RGBA pixels, 32-bit loads of the RGB source.
+template <int K>
+__global__ void __launch_bounds__(128) postprocess4_kernel(const PostDesc* __restrict__ descs, const float* __restrict__ mask_logits,
+                                                           const float* __restrict__ iou_logits, float* __restrict__ ious,
+                                                           int* __restrict__ best_idx, int S) {
+  const int b = blockIdx.z;
+  const PostDesc d = descs[b];
+  const int oy = blockIdx.y;
+  const int ox = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (oy >= d.H) return;
+  float sc[K];
+  int best = 0;
+  float bestv = -1.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    sc[k] = sigmoidf_acc(iou_logits[b * K + k]);
+    if (sc[k] > bestv) { bestv = sc[k]; best = k; }      // strict >: first maximum wins, like numpy argmax
+  }
+  if (blockIdx.x == 0 && oy == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) ious[b * K + k] = sc[k];
+    best_idx[b] = best;
+  }
+  if (ox >= d.W) return;
+  const int ys = d.ystart[oy] + d.pad_h;
+  const float* yw = d.yw + static_cast<size_t>(oy) * d.ky;
+  int xs[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xs[i] = d.xstart[ox + i] + d.pad_w;
+  float alpha[4];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float* plane = mask_logits + (static_cast<size_t>(b) * K + k) * S * S;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int ty = 0; ty < d.ky; ++ty) {
+      const float wy = yw[ty];
+      if (wy == 0.0f && ty > 0) continue;
+      const float* rowp = plane + static_cast<size_t>(min(ys + ty, S - 1)) * S;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* xw = d.xw + static_cast<size_t>(ox + i) * d.kx;
+        float hsum = 0.0f;
+        for (int tx = 0; tx < d.kx; ++tx) {
+          const float wx = xw[tx];
+          if (wx != 0.0f || tx == 0) {
+            const float pv = sigmoidf_fast(rowp[min(xs[i] + tx, S - 1)]);
+            hsum = (tx == 0) ? pv * wx : hsum + pv * wx;
+          }
+        }
+        acc[i] = (ty == 0) ? hsum * wy : acc[i] + hsum * wy;
+      }
+    }
+    *reinterpret_cast<float4*>(d.all_masks + (static_cast<size_t>(k) * d.H + oy) * d.W + ox) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (k == best) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) alpha[i] = acc[i];
+    }
+  }
+  const uint32_t* sp = reinterpret_cast<const uint32_t*>(d.src + (static_cast<size_t>(oy) * d.W + ox) * 3);
+  const uint32_t s0 = __ldg(sp), s1 = __ldg(sp + 1), s2 = __ldg(sp + 2);       // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+  uint32_t a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = static_cast<uint32_t>(static_cast<int>(alpha[i] * 255.0f)) << 24;   // truncation, predictor.py:130
+  uint4 o;
+  o.x = (s0 & 0x00FFFFFFu) | a[0];
+  o.y = (s0 >> 24) | ((s1 & 0x0000FFFFu) << 8) | a[1];
+  o.z = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | a[2];
+  o.w = (s2 >> 8) | a[3];
+  reinterpret_cast<uint4*>(d.rgba)[(static_cast<size_t>(oy) * d.W + ox) >> 2] = o;
+}
 
 template <int K>
 __global__ void __launch_bounds__(128) postprocess_kernel(const PostDesc* __restrict__ descs, const float* __restrict__ mask_logits,

@@ -707,12 +707,14 @@ int s3od_postprocess(s3od_ctx* c, const float* d_mask_logits, const float* d_iou
     return fail(S3OD_ERR_ARG, "bad argument to s3od_postprocess");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int maxH = 0, maxW = 0;
+  bool mult4 = true;
   for (int i = 0; i < batch; ++i) {
     maxH = std::max(maxH, images[i].H);
     maxW = std::max(maxW, images[i].W);
+    mult4 = mult4 && (images[i].W % 4 == 0);
   }
   CK(cudaMemcpyAsync(c->d_post, images, sizeof(PostDesc) * batch, cudaMemcpyHostToDevice, st));
-  CK(launch_postprocess(c->d_post, d_mask_logits, d_iou_logits, d_ious, d_best_idx, c->S, c->K, batch, maxH, maxW, st));
+  CK(launch_postprocess(c->d_post, d_mask_logits, d_iou_logits, d_ious, d_best_idx, c->S, c->K, batch, maxH, maxW, mult4, st));
   c->launches += 1;
   return S3OD_OK;
 }

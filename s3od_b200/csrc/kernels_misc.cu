@@ -63,12 +63,12 @@ cudaError_t launch_fill_prefix(float* x, const float* prefix, int ntok, int D, i
 
 cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float* pool, int pool_blocks, int B, int h, int w,
                               int num_sms, cudaStream_t stream) {
-  const int npix = 4 * h * w;
+  const int npix = h * w;                                        // input pixels; a block handles 8 per step
   int blocks;
   if (pool != nullptr) {
     blocks = pool_blocks;
   } else {
-    blocks = (npix + 63) / 64;                                   // >= 8 pixel steps per block
+    blocks = (npix + 31) / 32;                                   // >= 4 steps per block
     const int cap = (8 * num_sms + B - 1) / B;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -84,14 +84,21 @@ cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, cons
 }
 
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
-                               int* best_idx, int S, int K, int B, int maxH, int maxW, cudaStream_t stream) {
-  dim3 grid((maxW + 127) / 128, maxH, B);
-  if (K == 3)
-    postprocess_kernel<3><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
-  else if (K == 1)
-    postprocess_kernel<1><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
-  else
-    return cudaErrorInvalidValue;
+                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, cudaStream_t stream) {
+  if (K != 1 && K != 3) return cudaErrorInvalidValue;
+  if (all_w_mult4) {
+    dim3 grid((maxW / 4 + 127) / 128, maxH, B);
+    if (K == 3)
+      postprocess4_kernel<3><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+    else
+      postprocess4_kernel<1><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+  } else {
+    dim3 grid((maxW + 127) / 128, maxH, B);
+    if (K == 3)
+      postprocess_kernel<3><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+    else
+      postprocess_kernel<1><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+  }
   return cudaGetLastError();
 }
 

@@ -22,6 +22,6 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float
 cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, const float* w1, const float* b1, const float* w2,
                             const float* b2, float* iou_logits, int K, int B, cudaStream_t stream);
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
-                               int* best_idx, int S, int K, int B, int maxH, int maxW, cudaStream_t stream);
+                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, cudaStream_t stream);
 
 }  // namespace s3od

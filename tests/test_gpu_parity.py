@@ -8,7 +8,7 @@ WEIGHTS to bf16 already moves sigmoid masks by up to 2e-2 on these seeded weight
                       soft masks - logit std ~3 - so ~1 % of all pixels sit within the ~1.3 % relative logit error of the
                       threshold; that band alone costs up to 1.5 % IoU whatever the logit scale.)
     IoU logits        max-abs <= 3e-2;  sigmoid(IoU) max-abs <= 1e-2;  best-mask index exact
-    preprocess        bit-exact (integer resize + LUT);  postprocess on given logits <= 2e-6;  alpha exact w.r.t. own mask
+    preprocess        bit-exact (integer resize + LUT);  postprocess on given logits <= 5e-6;  alpha exact w.r.t. own mask
 """
 import os
 
@@ -181,7 +181,7 @@ def test_postprocess_matches_oracle_on_given_logits(models, H, W, S, hp, wp):
     d_img = torch.from_numpy(img).cuda()
     outs, ious, best = m.postprocess(torch.from_numpy(logits).cuda(), torch.from_numpy(ioul).cuda(), [d_img], [pad])
     am, rgba = outs[0][0].cpu().numpy(), outs[0][1].cpu().numpy()
-    np.testing.assert_allclose(am, ref["all_masks"], atol=2e-6)
+    np.testing.assert_allclose(am, ref["all_masks"], atol=5e-6)
     np.testing.assert_allclose(ious.cpu().numpy()[0], ref["all_ious"], atol=1e-6)
     assert int(best[0]) == ref["best_idx"]
     np.testing.assert_array_equal(rgba[..., :3], img)

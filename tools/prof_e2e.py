@@ -14,17 +14,20 @@ from s3od_b200.arch import VITB
 from s3od_b200.synth import save_checkpoint, synth_noise_image
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+MB = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 ck = "/tmp/prof_ck.pt"
 save_checkpoint(ck, VITB, 0)
-br = BackgroundRemoval(model_id=ck, image_size=1024, device="cuda:0", max_batch=B, micro_batch=8)
+br = BackgroundRemoval(model_id=ck, image_size=1024, device="cuda:0", max_batch=B, micro_batch=MB)
 imgs = []
 for i in range(B):
     t = torch.empty((1024, 1024, 3), dtype=torch.uint8, pin_memory=True)
     t.numpy()[...] = synth_noise_image(1024, 1024, seed=i)
     imgs.append(t.numpy())
-for _ in range(3):
+for i in range(8):
+    t1 = time.perf_counter()
     res = br.remove_background_batch(imgs)
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    print(f"call {i}: {1e3 * (time.perf_counter() - t1):.1f} ms")
 t0 = time.perf_counter()
 for _ in range(3):
     res = br.remove_background_batch(imgs)
