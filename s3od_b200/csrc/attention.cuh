@@ -43,6 +43,20 @@ S3OD_DEVICE float fast_exp2(float x) {
   return y;
 }
 
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 polynomial, relative error 1e-4 << the bf16 resolution of P):
+// the SFU does 16 exp2 per clock per SM, which at head_dim 64 (one exp2 per 256 tensor FLOP) is the attention kernel's
+// binding unit, so every kPolyEvery-th element is taken off it.
+S3OD_DEVICE float exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                    // 1.5 * 2^23: the mantissa now holds round(x)
+  const float f = x - (t - 12582912.0f);              // [-0.5, 0.5]
+  float p = fmaf(f, 0.05500962f, 0.24221106f);
+  p = fmaf(p, f, 0.69328284f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));      // * 2^round(x)
+}
+constexpr int kPolyEvery = 4;                         // 1 of every 4 exponentials goes to the FMA pipe
+
 // exp2 of 32 scores against the row reference -> 16 packed bf16 pairs; returns the fp32 row sum of the 32 values
 template <bool kMasked>
 S3OD_DEVICE float softmax_chunk(const uint32_t (&r)[32], float m_ref, int c, int nvalid, uint32_t (&w)[16]) {
@@ -50,7 +64,8 @@ S3OD_DEVICE float softmax_chunk(const uint32_t (&r)[32], float m_ref, int c, int
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float e0 = fast_exp2(__uint_as_float(r[2 * i]) - m_ref);
-    float e1 = fast_exp2(__uint_as_float(r[2 * i + 1]) - m_ref);
+    float e1 = ((2 * i + 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly(__uint_as_float(r[2 * i + 1]) - m_ref)
+                                                           : fast_exp2(__uint_as_float(r[2 * i + 1]) - m_ref);
     if (kMasked) {
       e0 = (c + 2 * i < nvalid) ? e0 : 0.0f;
       e1 = (c + 2 * i + 1 < nvalid) ? e1 : 0.0f;
@@ -99,7 +114,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
   const int q0 = blockIdx.x * kAttnTile;
   const int bh = blockIdx.y;
   const int T = p.kv_tiles;
-  long long* trace = (p.trace != nullptr && blockIdx.x == 5 && blockIdx.y == 0) ? p.trace : nullptr;
+  long long* trace = (p.trace != nullptr && blockIdx.x == 5 && blockIdx.y == p.trace_bh) ? p.trace : nullptr;
 #define S3OD_STAMP(slot) do { if (trace != nullptr && lane == 0) trace[j * 8 + (slot)] = clock64(); } while (0)
 
   if (warp == kWarpTma && lane == 0) {

@@ -24,6 +24,8 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
     cudaMemset(trace_buf, 0, 64 * 8 * sizeof(long long));
   }
   q.trace = trace_buf;
+  static const char* tb = getenv("S3OD_ATTN_TRACE_BH");
+  q.trace_bh = tb != nullptr ? atoi(tb) : 0;
   g_attn_trace = trace_buf;
   attention_kernel<<<dim3(q_tiles, bh), kAttnThreads, kAttnSmemBytes, stream>>>(q);
   return cudaGetLastError();
