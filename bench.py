@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from s3od_b200 import sharder                       # noqa: E402
-from s3od_b200.arch import VITB                     # noqa: E402
+from s3od_b200.arch import VITB, VITL               # noqa: E402
 from s3od_b200.synth import save_checkpoint, synth_noise_image, synth_state_dict   # noqa: E402
 
 METRIC = "images/sec (dinob, device-timed)"
@@ -110,9 +110,11 @@ def run_b200(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     B, S, src = args.batch, args.image_size, args.source
-    ckpt = os.path.join("/tmp", f"s3od_synth_vitb_seed0_{os.getpid()}.pt")
-    save_checkpoint(ckpt, VITB, 0)
-    br = BackgroundRemoval(model_id=ckpt, image_size=S, device=f"cuda:{local_rank}", max_batch=B, micro_batch=args.micro_batch)
+    arch = VITL if args.model == "dinol" else VITB
+    ckpt = os.path.join("/tmp", f"s3od_synth_{args.model}_seed0_{os.getpid()}.pt")
+    save_checkpoint(ckpt, arch, 0)
+    br = BackgroundRemoval(model_id=ckpt, image_size=S, device=f"cuda:{local_rank}", max_batch=B, micro_batch=args.micro_batch,
+                           encoder_name="dinov3_large" if args.model == "dinol" else "dinov3_base", num_outputs=arch.num_outputs)
     os.remove(ckpt)
     model = br.model
     # seeded synthetic uint8 images (reference fixture style), distinct per rank / slot; resident in HBM for `value`
@@ -168,7 +170,8 @@ def run_b200(args, rank, local_rank, world):
     t_e2e_local = time.perf_counter() - t0
     t_e2e = sharder.max_over_ranks(t_e2e_local, device=dev)
     h2d = B * src * src * 3
-    d2h = B * (3 * src * src * 4 + src * src * 4 + 3 * 4 + 4)
+    K = arch.num_outputs
+    d2h = B * (K * src * src * 4 + src * src * 4 + K * 4 + 4)
     del res
 
     if rank != 0:
@@ -192,22 +195,24 @@ def run_b200(args, rank, local_rank, world):
     families = {}
     for f, ms in sorted(fam_ms.items(), key=lambda kv: -kv[1]):
         ent = {"share": round(ms / total_ms, 4), "ms_per_image": round(ms / images, 5), "launches": fam_n[f]}
-        if f in FAMILY_GFLOP and S == 1024:
+        if f in FAMILY_GFLOP and S == 1024 and args.model == "dinob":
             ent["tflops"] = round(FAMILY_GFLOP[f] * images / ms, 1)
         families[f] = ent
     dom = max((f for f in fam_ms if f in FAMILY_GFLOP), key=lambda f: fam_ms[f])
-    achieved = FAMILY_GFLOP[dom] * images / fam_ms[dom] if S == 1024 else None
+    flops_known = S == 1024 and args.model == "dinob"
+    gflop_img = GFLOP_PER_IMAGE if args.model == "dinob" else 4958.1     # ViT-L, one mask
+    achieved = FAMILY_GFLOP[dom] * images / fam_ms[dom] if flops_known else None
     roofline = {"kernel": dom, "bound": "tensor", "achieved": round(achieved, 1) if achieved else None,
                 "peak": peaks["tflops_sustained"], "peak_source": peaks["source"] + " (sustained: timed inside a long step)",
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4) if achieved else None,
                 "traffic": None, "avg_launch_ms": round(fam_ms[dom] / fam_n[dom], 4),
-                "whole_step_tflops": round(GFLOP_PER_IMAGE * value / world / 1e3, 1) if S == 1024 else None,
-                "whole_step_frac": round(GFLOP_PER_IMAGE * value / world / 1e3 / peaks["tflops_sustained"], 4) if S == 1024 else None}
+                "whole_step_tflops": round(gflop_img * value / world / 1e3, 1) if S == 1024 else None,
+                "whole_step_frac": round(gflop_img * value / world / 1e3 / peaks["tflops_sustained"], 4) if S == 1024 else None}
     line = {
-        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC.replace("dinob", args.model), "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"dinob inference bf16, batch {B} synthetic {src}x{src} uint8 images per GPU, image_size {S} "
+        "config": {"workload": f"{args.model} inference bf16, batch {B} synthetic {src}x{src} uint8 images per GPU, image_size {S} "
                                "(preprocess + backbone + mask decoder + IoU head + postprocess), seeded random weights",
                    "batch_per_gpu": B, "image_size": S, "source": src, "micro_batch": model.micro_batch,
                    "cache": "inputs + activations per step exceed the 126 MB L2 by >10x (no flush needed)"},
@@ -273,6 +278,7 @@ def main():
     ap.add_argument("--source", type=int, default=1024, help="source image side (2048 = configs[2] shape)")
     ap.add_argument("--micro-batch", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--model", default="dinob", choices=["dinob", "dinol"], help="dinol = ViT-L backbone, one mask (BASELINE.json configs[4])")
     ap.add_argument("--dump-profile", default=None, help="write the per-kernel CUDA-event table (label, launches, images, ms) here")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images timed on the CPU oracle (0 = skip)")
     args = ap.parse_args()

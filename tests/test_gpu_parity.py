@@ -127,6 +127,25 @@ def test_model_matches_oracle_on_fresh_input(models, vitb_sd):
     assert float((out["pred_iou"].cpu() - ref["pred_iou"]).abs().max()) <= 3e-2
 
 
+def test_vitl_single_output_matches_oracle():
+    """BASELINE.json config 4 architecture: ViT-L/16 backbone (D=1024, 16 heads, 24 layers, taps 4/11/17/23), one mask."""
+    from s3od_b200.arch import VITL
+    from s3od_b200.engine import B200DPTSegmentation
+    from s3od_b200.synth import synth_state_dict
+    sd = synth_state_dict(VITL, 3)
+    S = 64
+    x = torch.from_numpy(np.concatenate([opp.preprocess(synth_image(S, S, seed=900 + i), S)[0] for i in range(2)], 0))
+    m = B200DPTSegmentation(sd, VITL, S, "cuda:0", max_batch=2)
+    try:
+        out = m(x.cuda())
+        ref = om.forward(sd, x, VITL)
+        assert out["pred_masks"].shape == (2, 1, S, S) and out["pred_iou"].shape == (2, 1)
+        _assert_masks(out["pred_masks"].cpu(), ref["pred_masks"], max_abs=5e-2)
+        assert float((out["pred_iou"].cpu() - ref["pred_iou"]).abs().max()) <= 5e-2
+    finally:
+        m.close()
+
+
 def test_micro_batching_is_deterministic(models):
     """B=3 pushed through micro-batches of 2 (+1 ragged) gives bit-identical logits to the same images run alone."""
     S = 64
