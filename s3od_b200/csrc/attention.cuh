@@ -1,40 +1,55 @@
 // Flash-style multi-head attention for sm_100a: softmax(Q K^T) V with head_dim 64, no mask, ragged sequence tail.
 // (DINOv3ViTAttention.forward HF:316-329; the 1/sqrt(64) scale and log2(e) are pre-folded into Q by the QKV epilogue.)
 //
-// One CTA = one 128-row query tile of one (image, head); it walks the key/value sequence in tiles of 128.
-//   warps 0..7         softmax      : two threads per query row (64 key columns each): row max (exchanged through smem),
-//                                     exp2, row sum; P written back to TENSOR MEMORY as packed bf16 (tcgen05.st)
-//   warp 8 (one lane)  MMA issuer   : S = Q K^T (128x128x64, operands in smem) into TMEM;
-//                                     O += P V (128x64x128): A = P read from TMEM, B = V read as an MN-major smem operand
-//                                     straight from its [kv, d] layout
-//   warp 9 (one lane)  TMA producer : Q once, then K and V tiles [128 kv x 64 d] through kStages-deep rings
-//   warp 10            TMEM allocator (256 columns: S 0..127, P 128..191 (bf16 pairs), O 192..255)
-// Keeping P in tensor memory takes 64 KB per tile (write + read) off the shared-memory port, which the MMA operand reads
-// and the TMA writes already load heavily, and needs no generic->async proxy fence.
+// One CTA per SM runs TWO streams = two adjacent 128-row query tiles of one (image, head); both walk the key/value
+// sequence in steps of 96 keys and share one K / V shared-memory ring (each tile is fetched once for 256 query rows).
+//   warps 0..7 / 8..15  softmax of stream 0 / 1.  Warps w and w + 4 of a stream share a TMEM lane quarter and take 16 rows
+//                       of it each (tcgen05.ld .16x256b): four threads share a row, so the row maximum is two shuffles and
+//                       nothing goes through shared memory.  The 96 scores of a step are read from tensor memory ONCE and
+//                       stay in registers (48 per thread): row max, exp2, row sum; the probabilities go back to TENSOR
+//                       MEMORY as packed bf16 (tcgen05.st .16x128b).  S is released to the MMA warp as soon as the loads
+//                       have landed, so Q K^T of the next step overlaps the whole exponential phase.
+//   warps 16, 17        MMA issuer of stream 0 / 1 (one elected lane): S = Q K^T (128x96x64, operands in smem) into TMEM;
+//                       O += P V (128x64x96): A = P read from TMEM, B = V read as an MN-major smem operand straight from
+//                       its [kv, d] layout.  Per stream 256 TMEM columns: S 0..95, P0 96..143, P1 144..191, O 192..255.
+//   warp 18 (one lane)  TMA producer: both Q tiles once, then K and V tiles [96 kv x 64 d] through kStages-deep rings
+// Why this shape (measured on B200 with tools/lab/attn_lab.cu, mma_rate.cu, pipe_rate.cu; clock64 stamps per step):
+//  * a max pass and an exp pass over tensor memory with the row split over two warps (smem exchange) left a serial chain
+//    tcgen05.ld -> max -> exchange -> tcgen05.ld -> exp per step; here S is read once and the row never leaves a warp;
+//  * with ONE P buffer the exponentials of step j+1 could not start before P V of step j had completed; 96-key steps leave
+//    room for TWO P buffers in 256 columns, so the softmax warps only ever wait for P V_{j-2} (and for P V_{j-1} in the
+//    rare step that rescales O);
+//  * one softmax warp per SM sub-partition gets 11 clk per MUFU.EX2, two or more get the pipe's 8 clk: 4 warps per
+//    sub-partition (16 softmax warps) are kept, which is why the row is spread over four threads instead of one;
+//  * ncu: the SFU (XU pipe) is 72 % busy and 63 % of the issue slots are used - the kernel is bound by the exponentials
+//    (one MUFU.EX2 per 256 tensor FLOP at head_dim 64).  Moving a share of them to an FMA-pipe polynomial
+//    (S3OD_ATTN_POLY_EVERY) buys nothing here because the extra ~7 issue slots per element land on the same saturated
+//    sub-partition; it is kept as a build option.
+// Keeping P in tensor memory takes the P write + read off the shared-memory port (a 128x96x16 MMA with both operands in
+// smem already needs 7 KB per 48 tensor cycles = more than the 128 B/clk the port delivers).
 // The running output stays in TMEM for the whole key/value walk.  The exponent reference m_ref of a row only moves when
-// the row maximum grows by more than 8 (in log2 units), in which case the two threads of the row rescale their halves
-// of O in TMEM (tcgen05.ld / mul / tcgen05.st); otherwise P = exp2(S - m_ref) is at most 2^8 and nothing is rescaled.
+// the row maximum grows by more than 8 (in log2 units), in which case the row of O is rescaled in TMEM
+// (tcgen05.ld / mul / tcgen05.st); otherwise P = exp2(S - m_ref) is at most 2^8 and nothing is rescaled.
 // The normaliser l follows the same reference, so the final O / l is the exact softmax average.
-// Two CTAs are resident per SM (TMEM 2 x 256 columns): while one CTA's softmax warps are in their exp2 phase the other
-// CTA's MMAs run.
 #pragma once
 #include "common.cuh"
 #include "types.h"
 
 namespace s3od {
 
-constexpr int kAttnThreads = 384;                 // 8 softmax warps + MMA, TMA, TMEM-alloc warps + 1 spare
-constexpr int kAttnTile = 128;
-constexpr int kAttnStages = 2;                    // K / V ring depth
+constexpr int kAttnThreads = 608;                 // 2 streams x 8 softmax warps, 2 MMA warps, TMA warp (104 registers each)
+// kAttnTile = 128 query rows per CTA; kAttnKvTile = 96 keys per step (types.h): S (96) + two P buffers (2 x 48) + O (64)
+// = the 256 TMEM columns a CTA may hold at 2 CTAs/SM.
+static_assert(kAttnKvTile == 96 && kAttnTile == 128, "attention kernel is written for 128 x 96 steps");
+constexpr int kAttnStages = 4;                    // K / V ring depth
 constexpr int kAttnQBytes = 128 * 128;            // 128 rows x 64 bf16
-constexpr int kAttnKBytes = 128 * 128;
-constexpr int kAttnVBytes = 128 * 128;            // 128 kv rows x 64 d
+constexpr int kAttnKBytes = kAttnKvTile * 128;
+constexpr int kAttnVBytes = kAttnKvTile * 128;    // 96 kv rows x 64 d
 constexpr int kAttnBarBytes = 256;                // mbarriers + the TMEM slot
-constexpr int kAttnXchgBytes = 2 * 128 * 4;       // per-row exchange between the two threads of a row (fp32)
 constexpr int kAttnSlack = 1024;                  // alignment slack for the dynamic smem base
 constexpr int kAttnSmemBytes =
-    kAttnQBytes + kAttnStages * (kAttnKBytes + kAttnVBytes) + kAttnBarBytes + kAttnXchgBytes + kAttnSlack;
-static_assert(2 * (kAttnSmemBytes + 1024) <= 228 * 1024, "attention kernel must stay 2 CTAs/SM");
+    2 * kAttnQBytes + kAttnStages * (kAttnKBytes + kAttnVBytes) + kAttnBarBytes + kAttnSlack;
+static_assert(kAttnSmemBytes + 1024 <= 227 * 1024, "attention kernel shared memory");
 constexpr float kAttnRescaleThreshold = 8.0f;
 
 S3OD_DEVICE float fast_exp2(float x) {
@@ -45,7 +60,7 @@ S3OD_DEVICE float fast_exp2(float x) {
 
 // exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 polynomial, relative error 1e-4 << the bf16 resolution of P):
 // the SFU does 16 exp2 per clock per SM, which at head_dim 64 (one exp2 per 256 tensor FLOP) is the attention kernel's
-// binding unit, so every kPolyEvery-th element is taken off it.
+// binding unit; every kPolyEvery-th element can be taken off it (off by default, see the header).
 S3OD_DEVICE float exp2_poly(float x) {
   x = fmaxf(x, -125.0f);
   const float t = x + 12582912.0f;                    // 1.5 * 2^23: the mantissa now holds round(x)
@@ -55,128 +70,250 @@ S3OD_DEVICE float exp2_poly(float x) {
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));      // * 2^round(x)
 }
-constexpr int kPolyEvery = 4;                         // 1 of every 4 exponentials goes to the FMA pipe
+#ifndef S3OD_ATTN_POLY_EVERY
+#define S3OD_ATTN_POLY_EVERY 0
+#endif
+#ifndef S3OD_ATTN_LAB
+#define S3OD_ATTN_LAB 0                               // tools/lab only: bit 0 = no max pass after tile 0, bit 1 = no exp2
+#endif
+constexpr int kPolyEvery = S3OD_ATTN_POLY_EVERY;      // 1 of every kPolyEvery exponentials goes to the FMA pipe (0 = none)
+S3OD_DEVICE float exp2_sel(float x, int e) {
+  if (S3OD_ATTN_LAB & 2) return x;
+  return (kPolyEvery > 0 && e % (kPolyEvery > 0 ? kPolyEvery : 1) == kPolyEvery - 1) ? exp2_poly(x) : fast_exp2(x);
+}
 
-// exp2 of 32 scores against the row reference -> 16 packed bf16 pairs; returns the fp32 row sum of the 32 values
+#ifndef S3OD_ATTN_PINGPONG
+#define S3OD_ATTN_PINGPONG 0                          // 1: the exponential phases of the two streams alternate (named barriers)
+#endif
+
+// tcgen05.ld / st in the 16-lane shapes (layout measured with tools/lab/tmem_layout.cu): for repetition i, thread t holds
+//   .16x256b : r[4i+0..1] = (lane t/4,     columns 8i + 2(t%4) + {0,1}),  r[4i+2..3] = (lane t/4 + 8, same columns)
+//   .16x128b : r[2i]      = (lane t/4,     column  4i + t%4),             r[2i+1]    = (lane t/4 + 8, same column)
+// so the four threads t%4 = 0..3 share a row (reductions are two shuffles) and a .16x256b pair of adjacent fp32 columns
+// packs into exactly the .16x128b bf16x2 column of the same thread.
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_ld_16x256_x8(uint32_t taddr, uint32_t (&r)[NR]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]),
+        "=r"(r[OFF + 6]), "=r"(r[OFF + 7]), "=r"(r[OFF + 8]), "=r"(r[OFF + 9]), "=r"(r[OFF + 10]), "=r"(r[OFF + 11]),
+        "=r"(r[OFF + 12]), "=r"(r[OFF + 13]), "=r"(r[OFF + 14]), "=r"(r[OFF + 15]), "=r"(r[OFF + 16]), "=r"(r[OFF + 17]),
+        "=r"(r[OFF + 18]), "=r"(r[OFF + 19]), "=r"(r[OFF + 20]), "=r"(r[OFF + 21]), "=r"(r[OFF + 22]), "=r"(r[OFF + 23]),
+        "=r"(r[OFF + 24]), "=r"(r[OFF + 25]), "=r"(r[OFF + 26]), "=r"(r[OFF + 27]), "=r"(r[OFF + 28]), "=r"(r[OFF + 29]),
+        "=r"(r[OFF + 30]), "=r"(r[OFF + 31])
+      : "r"(taddr));
+}
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_ld_16x256_x4(uint32_t taddr, uint32_t (&r)[NR]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]),
+        "=r"(r[OFF + 6]), "=r"(r[OFF + 7]), "=r"(r[OFF + 8]), "=r"(r[OFF + 9]), "=r"(r[OFF + 10]), "=r"(r[OFF + 11]),
+        "=r"(r[OFF + 12]), "=r"(r[OFF + 13]), "=r"(r[OFF + 14]), "=r"(r[OFF + 15])
+      : "r"(taddr));
+}
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_st_16x256_x4(uint32_t taddr, const uint32_t (&r)[NR]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[OFF + 0]), "r"(r[OFF + 1]), "r"(r[OFF + 2]), "r"(r[OFF + 3]), "r"(r[OFF + 4]), "r"(r[OFF + 5]), "r"(r[OFF + 6]),
+      "r"(r[OFF + 7]), "r"(r[OFF + 8]), "r"(r[OFF + 9]), "r"(r[OFF + 10]), "r"(r[OFF + 11]), "r"(r[OFF + 12]),
+      "r"(r[OFF + 13]), "r"(r[OFF + 14]), "r"(r[OFF + 15])
+      : "memory");
+}
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_st_16x128_x8(uint32_t taddr, const uint32_t (&r)[NR]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[OFF + 0]), "r"(r[OFF + 1]), "r"(r[OFF + 2]), "r"(r[OFF + 3]), "r"(r[OFF + 4]), "r"(r[OFF + 5]), "r"(r[OFF + 6]),
+      "r"(r[OFF + 7]), "r"(r[OFF + 8]), "r"(r[OFF + 9]), "r"(r[OFF + 10]), "r"(r[OFF + 11]), "r"(r[OFF + 12]),
+      "r"(r[OFF + 13]), "r"(r[OFF + 14]), "r"(r[OFF + 15])
+      : "memory");
+}
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_st_16x128_x4(uint32_t taddr, const uint32_t (&r)[NR]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[OFF + 0]), "r"(r[OFF + 1]), "r"(r[OFF + 2]), "r"(r[OFF + 3]), "r"(r[OFF + 4]), "r"(r[OFF + 5]), "r"(r[OFF + 6]),
+      "r"(r[OFF + 7])
+      : "memory");
+}
+// tcgen05.wait::ld with 16 of the loaded registers as in/out operands, so that no use of them is scheduled above it
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_ld_wait16(uint32_t (&r)[NR]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[OFF + 0]), "+r"(r[OFF + 1]), "+r"(r[OFF + 2]), "+r"(r[OFF + 3]), "+r"(r[OFF + 4]), "+r"(r[OFF + 5]),
+                 "+r"(r[OFF + 6]), "+r"(r[OFF + 7]), "+r"(r[OFF + 8]), "+r"(r[OFF + 9]), "+r"(r[OFF + 10]),
+                 "+r"(r[OFF + 11]), "+r"(r[OFF + 12]), "+r"(r[OFF + 13]), "+r"(r[OFF + 14]), "+r"(r[OFF + 15])
+               :
+               : "memory");
+}
+
+constexpr int kAttnRegs = kAttnKvTile / 2;           // scores per thread and step: 2 rows x 24 columns
+
+// maxima of this thread's 24 columns of its two rows; nvq = (valid columns of the step) - 2 * (lane % 4)
 template <bool kMasked>
-S3OD_DEVICE float softmax_chunk(const uint32_t (&r)[32], float m_ref, int c, int nvalid, uint32_t (&w)[16]) {
-  float sum = 0.0f;
+S3OD_DEVICE void row_max2(const uint32_t (&r)[kAttnRegs], int nvq, float& mxa, float& mxb) {
+  float a0 = -INFINITY, a1 = -INFINITY, b0 = -INFINITY, b1 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float e0 = fast_exp2(__uint_as_float(r[2 * i]) - m_ref);
-    float e1 = ((2 * i + 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly(__uint_as_float(r[2 * i + 1]) - m_ref)
-                                                           : fast_exp2(__uint_as_float(r[2 * i + 1]) - m_ref);
-    if (kMasked) {
-      e0 = (c + 2 * i < nvalid) ? e0 : 0.0f;
-      e1 = (c + 2 * i + 1 < nvalid) ? e1 : 0.0f;
+  for (int i = 0; i < kAttnRegs / 4; ++i) {
+    const bool v0 = !kMasked || 8 * i < nvq, v1 = !kMasked || 8 * i + 1 < nvq;
+    const float x0 = v0 ? __uint_as_float(r[4 * i + 0]) : -INFINITY, x1 = v1 ? __uint_as_float(r[4 * i + 1]) : -INFINITY;
+    const float y0 = v0 ? __uint_as_float(r[4 * i + 2]) : -INFINITY, y1 = v1 ? __uint_as_float(r[4 * i + 3]) : -INFINITY;
+    if (i & 1) {
+      a1 = fmaxf(fmaxf(a1, x0), x1);
+      b1 = fmaxf(fmaxf(b1, y0), y1);
+    } else {
+      a0 = fmaxf(fmaxf(a0, x0), x1);
+      b0 = fmaxf(fmaxf(b0, y0), y1);
     }
-    sum += e0 + e1;
-    w[i] = pack_bf16x2(e0, e1);
   }
-  return sum;
+  mxa = fmaxf(a0, a1);
+  mxb = fmaxf(b0, b1);
 }
 
-template <bool kMasked>
-S3OD_DEVICE float row_max_chunk(const uint32_t (&r)[32], int c, int nvalid, float mx) {
+// exp2 of repetitions [I0, I1) against the two row references -> packed bf16 pairs w[2i], w[2i+1]; adds to the row sums
+template <int I0, int I1, bool kMasked>
+S3OD_DEVICE void softmax_reps(const uint32_t (&r)[kAttnRegs], float ma, float mb, int nvq, uint32_t (&w)[kAttnRegs / 2], float& sa,
+                              float& sb) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float v = __uint_as_float(r[i]);
-    mx = fmaxf(mx, (!kMasked || c + i < nvalid) ? v : -INFINITY);
+  for (int i = I0; i < I1; ++i) {
+    float e0 = exp2_sel(__uint_as_float(r[4 * i + 0]) - ma, 4 * i + 0);
+    float e1 = exp2_sel(__uint_as_float(r[4 * i + 1]) - ma, 4 * i + 1);
+    float e2 = exp2_sel(__uint_as_float(r[4 * i + 2]) - mb, 4 * i + 2);
+    float e3 = exp2_sel(__uint_as_float(r[4 * i + 3]) - mb, 4 * i + 3);
+    if (kMasked) {
+      const bool v0 = 8 * i < nvq, v1 = 8 * i + 1 < nvq;
+      e0 = v0 ? e0 : 0.0f;
+      e1 = v1 ? e1 : 0.0f;
+      e2 = v0 ? e2 : 0.0f;
+      e3 = v1 ? e3 : 0.0f;
+    }
+    sa += e0 + e1;
+    sb += e2 + e3;
+    w[2 * i] = pack_bf16x2(e0, e1);
+    w[2 * i + 1] = pack_bf16x2(e2, e3);
   }
-  return mx;
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+S3OD_DEVICE float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+S3OD_DEVICE float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   // align by offsetting the shared array itself (a uintptr_t round trip would turn every access into a generic one)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kAttnQBytes;
+  uint8_t* sQ = smem;                                          // 2 query tiles
+  uint8_t* sK = sQ + 2 * kAttnQBytes;
   uint8_t* sV = sK + kAttnStages * kAttnKBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kAttnStages * kAttnVBytes);
   uint64_t* q_full = bars;                         // 1
   uint64_t* k_full = bars + 1;                     // kAttnStages
-  uint64_t* k_empty = k_full + kAttnStages;
+  uint64_t* k_empty = k_full + kAttnStages;        // 2 arrivals each (one commit per stream)
   uint64_t* v_full = k_empty + kAttnStages;
-  uint64_t* v_empty = v_full + kAttnStages;
-  uint64_t* s_full = v_empty + kAttnStages;        // 1
-  uint64_t* s_empty = s_full + 1;                  // 1 (256 arrivals)
-  uint64_t* p_full = s_empty + 1;                  // 1 (256 arrivals)
-  uint64_t* p_empty = p_full + 1;                  // 1: P V of the tile has completed (P region free, O up to date)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 1);
-  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kAttnBarBytes);   // [2][128]
+  uint64_t* v_empty = v_full + kAttnStages;        // 2 arrivals each
+  uint64_t* strm = v_empty + kAttnStages;          // per stream (6 barriers each):
+  //   [0] s_full   S of the step is in TMEM            [1] s_empty (256 arrivals) S is in registers
+  //   [2,3] p_full (256 arrivals) P buffer j & 1 written   [4,5] p_empty  P V of the step has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(strm + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // Warp roles: the single-thread control warps sit above the softmax warps (the issue arbiter of an SM sub-partition
   // favours its highest warp id).
-  constexpr int kWarpMma = 8, kWarpTma = 9, kWarpAlloc = 10;
-  const int q0 = blockIdx.x * kAttnTile;
+  constexpr int kWarpMma = 16, kWarpTma = 18;       // warps 16, 17 = MMA issuers of stream 0, 1
   const int bh = blockIdx.y;
   const int T = p.kv_tiles;
-  long long* trace = (p.trace != nullptr && blockIdx.x == 5 && blockIdx.y == p.trace_bh) ? p.trace : nullptr;
-#define S3OD_STAMP(slot) do { if (trace != nullptr && lane == 0) trace[j * 8 + (slot)] = clock64(); } while (0)
+  const bool two_streams = (2 * blockIdx.x + 1) * kAttnTile < p.ntok;      // the last CTA of an odd tile count runs one stream
+  long long* trace = (p.trace != nullptr && blockIdx.x == 2 && blockIdx.y == p.trace_bh) ? p.trace : nullptr;
+#define S3OD_STAMP(slot) do { if (trace != nullptr && lane == 0 && j < 64) trace[j * 8 + (slot)] = clock64(); } while (0)
 
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&p.tma_q);
     tma_prefetch_desc(&p.tma_k);
     tma_prefetch_desc(&p.tma_v);
   }
-  if (warp == kWarpMma && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kAttnStages; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+  if (warp == kWarpMma) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < kAttnStages; ++i) {
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], two_streams ? 2 : 1);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], two_streams ? 2 : 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&strm[6 * s + 0], 1);
+        mbar_init(&strm[6 * s + 1], 256);
+        mbar_init(&strm[6 * s + 2], 256);
+        mbar_init(&strm[6 * s + 3], 256);
+        mbar_init(&strm[6 * s + 4], 1);
+        mbar_init(&strm[6 * s + 5], 1);
+      }
+      fence_barrier_init();
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 256);
-    mbar_init(p_full, 256);
-    mbar_init(p_empty, 1);
-    fence_barrier_init();
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
   }
-  if (warp == kWarpAlloc) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;          // 128 columns fp32 scores
-  const uint32_t tmem_p = tmem_base + 128;    // 64 columns: 128 bf16 probabilities per row, two per column
-  const uint32_t tmem_o = tmem_base + 192;    // 64 columns fp32 output accumulator
 
   if (warp == kWarpTma) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      mbar_arrive_expect_tx(q_full, kAttnQBytes);
-      tma_load_3d(sQ, &p.tma_q, q_full, 0, q0, bh);
+      mbar_arrive_expect_tx(q_full, (two_streams ? 2 : 1) * kAttnQBytes);
+      tma_load_3d(sQ, &p.tma_q, q_full, 0, (2 * blockIdx.x) * kAttnTile, bh);
+      if (two_streams) tma_load_3d(sQ + kAttnQBytes, &p.tma_q, q_full, 0, (2 * blockIdx.x + 1) * kAttnTile, bh);
       int st = 0;
       uint32_t par = 0;
       for (int j = 0; j < T; ++j) {
         mbar_wait(&k_empty[st], par ^ 1);
         mbar_arrive_expect_tx(&k_full[st], kAttnKBytes);
-        tma_load_3d(sK + st * kAttnKBytes, &p.tma_k, &k_full[st], 0, j * kAttnTile, bh);
+        tma_load_3d(sK + st * kAttnKBytes, &p.tma_k, &k_full[st], 0, j * kAttnKvTile, bh);
         mbar_wait(&v_empty[st], par ^ 1);
         mbar_arrive_expect_tx(&v_full[st], kAttnVBytes);
-        tma_load_3d(sV + st * kAttnVBytes, &p.tma_v, &v_full[st], 0, j * kAttnTile, bh);
+        tma_load_3d(sV + st * kAttnVBytes, &p.tma_v, &v_full[st], 0, j * kAttnKvTile, bh);
         if (++st == kAttnStages) {
           st = 0;
           par ^= 1;
         }
       }
     }
-  } else if (warp == kWarpMma) {
-    // ===================== MMA issuer =====================
+  } else if (warp == kWarpMma || (warp == kWarpMma + 1 && two_streams)) {
+    // ===================== MMA issuer of one stream =====================
     // The whole warp walks the loop (descriptors and barrier addresses stay in uniform registers); one elected lane
-    // issues the tcgen05 instructions.
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+    // issues the tcgen05 instructions.  Both issuers feed the one tensor pipe of the SM; a K / V stage is released when
+    // both streams have committed their MMAs on it.
+    const int sidx = warp - kWarpMma;
+    uint64_t* s_full = strm + 6 * sidx;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_full + 2;
+    uint64_t* p_empty = s_full + 4;
+    const uint32_t tmem_s = tmem_base + 256 * sidx;             // 96 columns fp32 scores
+    const uint32_t tmem_p = tmem_s + kAttnKvTile;               // 2 x 48 columns: 96 bf16 probabilities per row
+    const uint32_t tmem_o = tmem_s + 192;                       // 64 columns fp32 output accumulator
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, kAttnKvTile);
     constexpr uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);      // B (= V) is MN-major
-    const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ));
+    const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + sidx * kAttnQBytes));
     int ks_st = 0;                                   // ring position of the next S tile
     uint32_t ks_par = 0;
     auto issue_s = [&](int j) {
       mbar_wait(&k_full[ks_st], ks_par);
-      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);     // softmax has drained S_{j-1}
+      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);     // the softmax warps hold S_{j-1} in registers
       tc_fence_after();
       const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + ks_st * kAttnKBytes));
       if (elect_one()) {
@@ -197,131 +334,160 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __grid
     uint32_t par = 0;
     for (int j = 0; j < T; ++j) {
       if (j + 1 < T) issue_s(j + 1);
-      S3OD_STAMP(5);                                  // S_{j+1} issued
-      mbar_wait(p_full, j & 1);
-      S3OD_STAMP(6);                                  // P_j seen
+      if (sidx == 0) S3OD_STAMP(5);                   // S_{j+1} issued
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      if (sidx == 0) S3OD_STAMP(6);                   // P_j seen
       mbar_wait(&v_full[st], par);
       tc_fence_after();
       const uint64_t v_desc = make_sdesc_sw128_mn(smem_u32(sV + st * kAttnVBytes));
+      const uint32_t p_tmem = tmem_p + (j & 1) * (kAttnKvTile / 2);
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = 0; ks < kAttnKvTile / 16; ++ks) {
           // A: 16 keys = 8 packed TMEM columns per step;  B: 16 kv rows = 2048 B (128 x 16 B) of the MN-major V tile
-          umma_bf16_ts(tmem_o, tmem_p + 8 * ks, v_desc + 128 * ks, idesc_o, (j | ks) != 0 ? 1u : 0u);
+          umma_bf16_ts(tmem_o, p_tmem + 8 * ks, v_desc + 128 * ks, idesc_o, (j | ks) != 0 ? 1u : 0u);
         }
         umma_commit(&v_empty[st]);
-        umma_commit(p_empty);
+        umma_commit(&p_empty[j & 1]);
       }
       __syncwarp();
-      S3OD_STAMP(7);                                  // P V_j issued
+      if (sidx == 0) S3OD_STAMP(7);                   // P V_j issued
       if (++st == kAttnStages) {
         st = 0;
         par ^= 1;
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 8 || (warp < 16 && two_streams)) {
     // ===================== softmax / output =====================
-    // Two threads per query row: warp w (half 0) owns key columns 0..63 of every tile, warp w + 4 (half 1) columns
-    // 64..127; both may touch the same TMEM lane quarter (warp % 4).
-    const int quad = warp & 3;
-    const int half = warp >> 2;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    float m_ref = -INFINITY, l_run = 0.0f;
-    uint32_t ra[32];
-    uint32_t w[16];
-    const uint32_t s_addr = tmem_s + lane_addr + half * 64;
-    const uint32_t p_addr = tmem_p + lane_addr + half * 32;
-    const uint32_t o_addr = tmem_o + lane_addr + half * 32;     // the 32 output columns this thread rescales / writes
+    // stream = warp / 8; warps w and w + 4 of a stream share a TMEM lane quarter and take 16 rows of it each; the four
+    // threads lane % 4 = 0..3 share a row (and a second row 8 below), 24 columns of the step each.
+    const int sidx = warp >> 3;
+    uint64_t* s_full = strm + 6 * sidx;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_full + 2;
+    uint64_t* p_empty = s_full + 4;
+    const int lane_base = (warp & 3) * 32 + ((warp >> 2) & 1) * 16;
+    const int row_a = lane_base + (lane >> 2);         // second row: row_a + 8
+    const int q2 = 2 * (lane & 3);
+    const uint32_t s_addr = tmem_base + 256 * sidx + (static_cast<uint32_t>(lane_base) << 16);
+    const uint32_t o_addr = s_addr + 192;
+    float ma = -INFINITY, mb = -INFINITY, la = 0.0f, lb = 0.0f;      // exponent references and partial normalisers
+    uint32_t ra[kAttnRegs];
+    uint32_t w[kAttnRegs / 2];
+#if S3OD_ATTN_PINGPONG
+    // The exponential phases of the two streams alternate (named barriers 1 and 2).
+    const int bar_mine = 1 + sidx, bar_other = 2 - sidx;
+    if (sidx == 1) asm volatile("bar.arrive %0, 512;" ::"r"(bar_other) : "memory");     // stream 0 goes first
+#endif
 
     for (int j = 0; j < T; ++j) {
-      const int nvalid = p.ntok - j * kAttnTile - half * 64;     // my columns >= nvalid are padding (last tile only)
-      const bool masked = nvalid < 64;
+      const int nvalid = p.ntok - j * kAttnKvTile;      // columns >= nvalid are padding (last step only)
+      const bool masked = nvalid < kAttnKvTile;
+      const int nvq = nvalid - q2;
+      const uint32_t p_addr = s_addr + kAttnKvTile + (j & 1) * (kAttnKvTile / 2);
       mbar_wait(s_full, j & 1);
       if (warp == 0) S3OD_STAMP(0);                     // S_j seen
       tc_fence_after();
-      // ---- pass 1: maximum of my 64 columns (one 32-register buffer: the other softmax warps hide the TMEM latency)
-      tmem_ld_32x32(s_addr, ra);
-      tmem_ld_wait(ra);
-      float mx = masked ? row_max_chunk<true>(ra, 0, nvalid, -INFINITY) : row_max_chunk<false>(ra, 0, nvalid, -INFINITY);
-      tmem_ld_32x32(s_addr + 32, ra);
-      tmem_ld_wait(ra);
-      mx = masked ? row_max_chunk<true>(ra, 32, nvalid, mx) : row_max_chunk<false>(ra, 32, nvalid, mx);
-      // row maximum = max over the two halves (exchange through smem; the partner read precedes the partner's s_empty
-      // arrival and tile j+1 cannot start before all 256 arrivals, so one buffer is enough)
-      xchg[half * 128 + row] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-      mx = fmaxf(mx, xchg[(half ^ 1) * 128 + row]);
-
-      // ---- exponent reference: only moves when the maximum grew by more than the threshold
-      const bool need = mx > m_ref + kAttnRescaleThreshold;          // always true for j == 0 (m_ref = -inf)
-      const float m_new = need ? mx : m_ref;
-      if (warp == 0) S3OD_STAMP(1);                     // pass 1 done
-      if (j > 0) {
-        mbar_wait(p_empty, (j - 1) & 1);              // P V of tile j-1 done: P region free, O complete
-        if (warp == 0) S3OD_STAMP(2);                   // P V_{j-1} seen
-        if (__any_sync(0xffffffffu, need)) {          // the partner warp takes the same decision for the same rows
-          const float alpha = need ? fast_exp2(m_ref - m_new) : 1.0f;
-          tc_fence_after();
-          tmem_ld_32x32(o_addr, ra);
-          tmem_ld_wait(ra);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) ra[i] = __float_as_uint(__uint_as_float(ra[i]) * alpha);
-          tmem_st_32x32(o_addr, ra);
-          l_run *= alpha;
-        }
+      if (S3OD_ATTN_LAB & 16) {                         // timing probe: barriers only
+        mbar_arrive(s_empty);
+        if (j >= 2) mbar_wait(&p_empty[j & 1], ((j - 2) >> 1) & 1);
+        mbar_arrive(&p_full[j & 1]);
+        continue;
       }
-      m_ref = m_new;
-
-      // ---- pass 2: P = exp2(S - m_ref) as packed bf16 into tensor memory, partial row sum
-      tmem_ld_32x32(s_addr, ra);
-      tmem_ld_wait(ra);
-      float sum = masked ? softmax_chunk<true>(ra, m_ref, 0, nvalid, w) : softmax_chunk<false>(ra, m_ref, 0, nvalid, w);
-      tmem_st_32x16(p_addr, w);
-      tmem_ld_32x32(s_addr + 32, ra);
-      tmem_ld_wait(ra);
+      tmem_ld_16x256_x8<0>(s_addr, ra);
+      tmem_ld_16x256_x4<32>(s_addr + 64, ra);
+      tmem_ld_wait16<0>(ra);
+      tmem_ld_wait16<16>(ra);
+      tmem_ld_wait16<32>(ra);
       tc_fence_before();
-      mbar_arrive(s_empty);                            // S_j has been read for the last time
-      if (warp == 0) S3OD_STAMP(3);
-      sum += masked ? softmax_chunk<true>(ra, m_ref, 32, nvalid, w) : softmax_chunk<false>(ra, m_ref, 32, nvalid, w);
-      tmem_st_32x16(p_addr + 16, w);
-      l_run += sum;
+      mbar_arrive(s_empty);                            // the scores are in registers: S may be overwritten
+      if (warp == 0) S3OD_STAMP(1);
+
+      float mxa = ma, mxb = mb;
+      if (!(S3OD_ATTN_LAB & 1) || j == 0) {
+        if (masked) row_max2<true>(ra, nvq, mxa, mxb);
+        else row_max2<false>(ra, nvq, mxa, mxb);
+        mxa = quad_max(mxa);
+        mxb = quad_max(mxb);
+      }
+      // ---- exponent references: only move when the maximum grew by more than the threshold
+      const bool need_a = mxa > ma + kAttnRescaleThreshold, need_b = mxb > mb + kAttnRescaleThreshold;   // true for j == 0
+      const float ma_new = need_a ? mxa : ma, mb_new = need_b ? mxb : mb;
+      if (j > 0 && __any_sync(0xffffffffu, need_a || need_b)) {
+        // rare: O has to be rescaled, which needs every P V issued so far to have completed
+        mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        const float alpha_a = need_a ? fast_exp2(ma - ma_new) : 1.0f, alpha_b = need_b ? fast_exp2(mb - mb_new) : 1.0f;
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_16x256_x4<0>(o_addr + 32 * c, w);
+          tmem_ld_wait16<0>(w);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            w[4 * i + 0] = __float_as_uint(__uint_as_float(w[4 * i + 0]) * alpha_a);
+            w[4 * i + 1] = __float_as_uint(__uint_as_float(w[4 * i + 1]) * alpha_a);
+            w[4 * i + 2] = __float_as_uint(__uint_as_float(w[4 * i + 2]) * alpha_b);
+            w[4 * i + 3] = __float_as_uint(__uint_as_float(w[4 * i + 3]) * alpha_b);
+          }
+          tmem_st_16x256_x4<0>(o_addr + 32 * c, w);
+        }
+        la *= alpha_a;
+        lb *= alpha_b;
+      }
+      if (j >= 2) mbar_wait(&p_empty[j & 1], ((j - 2) >> 1) & 1);     // P V_{j-2} has read this P buffer
+      tc_fence_after();
+      ma = ma_new;
+      mb = mb_new;
+#if S3OD_ATTN_PINGPONG
+      asm volatile("bar.sync %0, 512;" ::"r"(bar_mine) : "memory");   // my stream's turn on the SFU
+#endif
+      if (warp == 0) S3OD_STAMP(2);
+
+      // ---- P = exp2(S - m_ref) as packed bf16 into tensor memory, row sums
+      if (masked) {
+        softmax_reps<0, 8, true>(ra, ma, mb, nvq, w, la, lb);
+        tmem_st_16x128_x8<0>(p_addr, w);
+        softmax_reps<8, 12, true>(ra, ma, mb, nvq, w, la, lb);
+        tmem_st_16x128_x4<16>(p_addr + 32, w);
+      } else {
+        softmax_reps<0, 8, false>(ra, ma, mb, nvq, w, la, lb);
+        tmem_st_16x128_x8<0>(p_addr, w);
+        softmax_reps<8, 12, false>(ra, ma, mb, nvq, w, la, lb);
+        tmem_st_16x128_x4<16>(p_addr + 32, w);
+      }
+#if S3OD_ATTN_PINGPONG
+      if (!(sidx == 1 && j == T - 1)) asm volatile("bar.arrive %0, 512;" ::"r"(bar_other) : "memory");
+#endif
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j & 1]);
       if (warp == 0) S3OD_STAMP(4);                     // P_j published
     }
 
-    // ---- epilogue: O / l -> bf16 [B*ntok, heads*64]; the two threads of a row add their partial sums through smem
-    mbar_wait(p_empty, (T - 1) & 1);
+    // ---- epilogue: O / l -> bf16 [B*ntok, heads*64]
+    mbar_wait(&p_empty[(T - 1) & 1], ((T - 1) >> 1) & 1);
     tc_fence_after();
-    xchg[half * 128 + row] = l_run;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-    const float inv = 1.0f / (l_run + xchg[(half ^ 1) * 128 + row]);
-    const int t = q0 + row;
+    const float inv_a = 1.0f / quad_sum(la), inv_b = 1.0f / quad_sum(lb);
+    const int ta = (2 * blockIdx.x + sidx) * kAttnTile + row_a, tb = ta + 8;
     const int b = bh / p.heads, head = bh % p.heads;
-    __nv_bfloat16* dst = p.out + (static_cast<size_t>(b) * p.ntok + t) * (p.heads * 64) + head * 64 + half * 32;
-    tmem_ld_32x32(o_addr, ra);
-    tmem_ld_wait(ra);
-    if (t < p.ntok) {
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
+    __nv_bfloat16* base = p.out + static_cast<size_t>(b) * p.ntok * (p.heads * 64) + head * 64 + q2;
+    uint32_t* dst_a = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(ta) * (p.heads * 64));
+    uint32_t* dst_b = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(tb) * (p.heads * 64));
+    tmem_ld_16x256_x8<0>(o_addr, ra);
+    tmem_ld_wait16<0>(ra);
+    tmem_ld_wait16<16>(ra);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(ra[8 * i + 0]) * inv, __uint_as_float(ra[8 * i + 1]) * inv);
-        u.y = pack_bf16x2(__uint_as_float(ra[8 * i + 2]) * inv, __uint_as_float(ra[8 * i + 3]) * inv);
-        u.z = pack_bf16x2(__uint_as_float(ra[8 * i + 4]) * inv, __uint_as_float(ra[8 * i + 5]) * inv);
-        u.w = pack_bf16x2(__uint_as_float(ra[8 * i + 6]) * inv, __uint_as_float(ra[8 * i + 7]) * inv);
-        d4[i] = u;
-      }
+    for (int i = 0; i < 8; ++i) {
+      if (ta < p.ntok) dst_a[4 * i] = pack_bf16x2(__uint_as_float(ra[4 * i + 0]) * inv_a, __uint_as_float(ra[4 * i + 1]) * inv_a);
+      if (tb < p.ntok) dst_b[4 * i] = pack_bf16x2(__uint_as_float(ra[4 * i + 2]) * inv_b, __uint_as_float(ra[4 * i + 3]) * inv_b);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpAlloc) {
+  if (warp == kWarpMma) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 

@@ -357,14 +357,14 @@ bool build_plan(s3od_ctx* c) {
     const uint64_t BH = static_cast<uint64_t>(mb) * H;
     const uint64_t dq[3] = {64, (uint64_t)ntok, BH};
     const uint64_t sq[2] = {128, (uint64_t)ntok * 128};
-    const uint32_t bq[3] = {64, 128, 1};
+    const uint32_t bq[3] = {64, kAttnTile, 1}, bkv[3] = {64, kAttnKvTile, 1};
     if (!make_tmap(&ap.tma_q, aptr<bf16>(c, "q"), 3, dq, sq, bq)) return false;
-    if (!make_tmap(&ap.tma_k, aptr<bf16>(c, "k"), 3, dq, sq, bq)) return false;
-    if (!make_tmap(&ap.tma_v, aptr<bf16>(c, "v"), 3, dq, sq, bq)) return false;
+    if (!make_tmap(&ap.tma_k, aptr<bf16>(c, "k"), 3, dq, sq, bkv)) return false;
+    if (!make_tmap(&ap.tma_v, aptr<bf16>(c, "v"), 3, dq, sq, bkv)) return false;
     ap.out = actx;
     ap.ntok = ntok;
     ap.heads = H;
-    ap.kv_tiles = (ntok + 127) / 128;
+    ap.kv_tiles = (ntok + kAttnKvTile - 1) / kAttnKvTile;
   }
   for (int l = 0; l < c->L; ++l) {
     const std::string pre = "enc." + std::to_string(l) + ".";
@@ -812,13 +812,13 @@ int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d
   const uint64_t BH = static_cast<uint64_t>(batch) * heads;
   const uint64_t dq[3] = {64, (uint64_t)ntok, BH};
   const uint64_t sq[2] = {128, (uint64_t)ntok * 128};
-  const uint32_t bq[3] = {64, 128, 1};
+  const uint32_t bq[3] = {64, kAttnTile, 1}, bkv[3] = {64, kAttnKvTile, 1};
   if (!make_tmap(&ap.tma_q, d_q, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
-  if (!make_tmap(&ap.tma_k, d_k, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
-  if (!make_tmap(&ap.tma_v, d_v, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
+  if (!make_tmap(&ap.tma_k, d_k, 3, dq, sq, bkv)) return S3OD_ERR_CUDA;
+  if (!make_tmap(&ap.tma_v, d_v, 3, dq, sq, bkv)) return S3OD_ERR_CUDA;
   ap.out = static_cast<bf16*>(d_out);
-  ap.ntok = ntok; ap.heads = heads; ap.kv_tiles = (ntok + 127) / 128;
-  CK(launch_attention(ap, (ntok + 127) / 128, static_cast<int>(BH), static_cast<cudaStream_t>(stream)));
+  ap.ntok = ntok; ap.heads = heads; ap.kv_tiles = (ntok + kAttnKvTile - 1) / kAttnKvTile;
+  CK(launch_attention(ap, (ntok + kAttnTile - 1) / kAttnTile, static_cast<int>(BH), static_cast<cudaStream_t>(stream)));
   return S3OD_OK;
 }
 

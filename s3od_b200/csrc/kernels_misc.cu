@@ -27,7 +27,7 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
   static const char* tb = getenv("S3OD_ATTN_TRACE_BH");
   q.trace_bh = tb != nullptr ? atoi(tb) : 0;
   g_attn_trace = trace_buf;
-  attention_kernel<<<dim3(q_tiles, bh), kAttnThreads, kAttnSmemBytes, stream>>>(q);
+  attention_kernel<<<dim3((q_tiles + 1) / 2, bh), kAttnThreads, kAttnSmemBytes, stream>>>(q);   // two query tiles per CTA
   return cudaGetLastError();
 }
 

@@ -29,12 +29,15 @@ struct PostDesc {              // one output image of the post-process
   const float* xw;             // [W, kx]
 };
 
+constexpr int kAttnTile = 128;      // query rows per attention CTA
+constexpr int kAttnKvTile = 96;     // keys per attention step (attention.cuh explains the choice)
+
 struct AttnParams {
-  CUtensorMap tma_q;    // (64 d, ntok, B*H)  box (64, 128, 1)
-  CUtensorMap tma_k;    // (64 d, ntok, B*H)  box (64, 128, 1)
-  CUtensorMap tma_v;    // (64 d, ntok, B*H)  box (64, 128, 1); consumed as an MN-major B operand
+  CUtensorMap tma_q;    // (64 d, ntok, B*H)  box (64, kAttnTile, 1)
+  CUtensorMap tma_k;    // (64 d, ntok, B*H)  box (64, kAttnKvTile, 1)
+  CUtensorMap tma_v;    // (64 d, ntok, B*H)  box (64, kAttnKvTile, 1); consumed as an MN-major B operand
   __nv_bfloat16* out;   // [B * ntok, heads * 64]
-  int ntok, heads, kv_tiles;
+  int ntok, heads, kv_tiles;   // kv_tiles = ceil(ntok / kAttnKvTile)
   int trace_bh;         // debug: which blockIdx.y is traced
   long long* trace;     // debug: per-tile clock64() stamps of CTA (5, 0) (8 slots per tile: 0-4 softmax warp, 5-7 MMA thread)
 };
