@@ -108,6 +108,9 @@ int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d
 /* NHWC bf16 3x3 / stride 1 / pad 1 convolution, weights [cout, 9*cin] bf16 (tap-major), fp32 bias or NULL */
 int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin,
                     int cout, int relu, s3od_stream stream);
+/* the same convolution for cin = 64, cout = 64 on the row-streaming kernel (w % 128 == 0) */
+int s3od_op_conv3x3_rows(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int relu,
+                         s3od_stream stream);
 
 /* debug aid: per-tile clock64() stamps of one attention CTA (only filled when S3OD_ATTN_TRACE=1 is set) */
 int s3od_debug_attn_trace(long long* host_out /* [64][8] */);

@@ -80,6 +80,17 @@ S3OD_DEVICE void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int
       : "memory");
 }
 
+// TMA store of a shared-memory box (written by this warp, 128B-swizzled) into a 5-D tensor; bulk-group completion
+S3OD_DEVICE void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+S3OD_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+S3OD_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+S3OD_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <uint32_t kCols>
 S3OD_DEVICE void tmem_alloc(uint32_t* dst_smem) {

@@ -1,0 +1,272 @@
+// Row-streaming 3x3 / stride 1 / pad 1 convolution for SMALL output widths (Cin = 64, NOUT = 32 / 64 / 96) on sm_100a.
+//
+// Why not the generic implicit GEMM (gemm_tc.cuh): a 128 x N x 16 tcgen05.mma with both operands in shared memory
+// reads 4 KB of A and 32 N bytes of B; the port delivers 128 B/clk, so for N = 64 the MMA takes 48 clk instead of 32
+// (tools/lab/mma_rate.cu: 66 % of the tensor peak at N = 64, 85 % at N = 96), and the output-stationary tiling re-fetches
+// every input pixel nine times through TMA on top of that (measured 41 % of peak for the mask-head convolutions).
+//
+// Here the INPUT is stationary.  An A tile is 128 consecutive pixels of one input row (x0-1 .. x0+128 are fetched once,
+// 130 pixels x 64 channels = one 128-byte swizzle row per pixel); the three horizontal taps kx are the same smem buffer
+// read from a start address advanced by kx pixel rows, and ONE MMA per (kx, 16-channel step) multiplies the tile with
+// the stacked weights of the three vertical taps: N = 3 x NOUT, accumulated into the TMEM blocks of output rows
+// i-1, i, i+1 at once.  Output row r is complete after input row r+1.  Per MMA the port now moves 4 KB + 96 NOUT bytes
+// for 1.5 NOUT tensor cycles (NOUT = 64: 107 B/clk), every input row is fetched once, the 9 x NOUT x 64 weights
+// stay resident in shared memory for the whole (persistent) CTA, and the accumulators rotate through a ring of
+// TMEM blocks so the epilogue of row r overlaps the MMAs of rows r+1...
+//
+//   warps 0..3         epilogue     : thread = output pixel of the row; tcgen05.ld -> functor (EpiConv / EpiMask) -> global
+//   warp 4 (one lane)  TMA producer : weights once; input rows (64 ch x 130 px box, zero-filled outside the image =
+//                                     the convolution's padding) through a ring of row buffers
+//   warp 5 (one lane)  MMA issuer   : owns the TMEM allocation
+// Work item = strip of 128 output columns x kRowsPerStrip output rows of one image; CTAs walk strips round-robin.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace s3od {
+
+constexpr int kRowPx = 128;                       // output pixels per row tile (UMMA M)
+constexpr int kRowBufBytes = 17 * 1024;           // 130 pixel rows x 128 B, rounded up to keep 1024-byte alignment
+constexpr int kRowLoadBytes = (kRowPx + 2) * 128;
+constexpr int kRowsPerStrip = 64;
+
+template <class Epi>
+struct RowConvParams {
+  CUtensorMap tma_in;      // NHWC input as (C = 64, W, 1, H, B), box (64, 130, 1, 1, 1)
+  CUtensorMap tma_w;       // weights [NOUT, 9 * 64] tap-major (ky*3 + kx), box (64, NOUT)
+  int H, W;                // image size (W % 128 == 0)
+  int strips_x, strips_y;  // W / 128, ceil(H / kRowsPerStrip)
+  int num_strips;          // images * strips_x * strips_y
+  CUtensorMap tma_out;     // EpiConv only: NHWC bf16 output as (C = 64, W, 1, H, B), box (64, 32, 1, 1, 1)
+  typename Epi::Params epi;
+};
+
+template <int NOUT>
+struct RowConvCfg {
+  static constexpr int kAccBlocks = 512 / NOUT;                       // TMEM ring of output-row accumulators
+  static constexpr int kWBytes = 9 * NOUT * 128;                      // resident weights
+  static constexpr int kRing = (192 * 1024 - kWBytes) / kRowBufBytes > 8 ? 8 : (192 * 1024 - kWBytes) / kRowBufBytes;
+  static constexpr int kStageOutBytes = 4 * 32 * 128;                 // EpiConv: per-warp 32 px x 128 B staging for the TMA store
+  static constexpr int kSmemBytes = kWBytes + kRing * kRowBufBytes + kStageOutBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(NOUT % 16 == 0 && (NOUT * 128) % 1024 == 0, "weight blocks must keep the 128B-swizzle alignment");
+  static_assert(kRing >= 4 && kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int NOUT, class Epi>
+__global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant__ RowConvParams<Epi> p) {
+  using Cfg = RowConvCfg<NOUT>;
+  constexpr int NB = Cfg::kAccBlocks;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;                                   // [kx][ky = 2, 1, 0][NOUT rows x 128 B]
+  uint8_t* sRow = smem + Cfg::kWBytes;                  // ring of input rows
+  uint8_t* sOut = sRow + Cfg::kRing * kRowBufBytes;     // 4 x 4 KB (1024-aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + Cfg::kStageOutBytes);
+  uint64_t* w_full = bars;                              // 1
+  uint64_t* row_full = bars + 1;                        // [kRing] TMA -> MMA
+  uint64_t* row_empty = row_full + Cfg::kRing;          // [kRing] MMA -> TMA
+  uint64_t* acc_full = row_empty + Cfg::kRing;          // [NB]    MMA -> epilogue
+  uint64_t* acc_empty = acc_full + NB;                  // [NB]    epilogue -> MMA (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NB);
+  static_assert((1 + 2 * Cfg::kRing + 2 * NB) * 8 + 4 <= 512, "barrier area");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kWarpTma = 4, kWarpMma = 5;
+
+  if (warp == kWarpTma && lane == 0) {
+    tma_prefetch_desc(&p.tma_in);
+    tma_prefetch_desc(&p.tma_w);
+    if constexpr (std::is_same_v<Epi, EpiConv>) tma_prefetch_desc(&p.tma_out);
+  }
+  if (warp == kWarpMma) {
+    if (lane == 0) {
+      mbar_init(w_full, 1);
+      for (int i = 0; i < Cfg::kRing; ++i) {
+        mbar_init(&row_full[i], 1);
+        mbar_init(&row_empty[i], 1);
+      }
+      for (int i = 0; i < NB; ++i) {
+        mbar_init(&acc_full[i], 1);
+        mbar_init(&acc_empty[i], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // strip -> (image, x0, y0, y1)
+  auto strip_geom = [&](int s, int& b, int& x0, int& y0, int& y1) {
+    const int per_img = p.strips_x * p.strips_y;
+    b = s / per_img;
+    const int r = s % per_img;
+    x0 = (r % p.strips_x) * kRowPx;
+    y0 = (r / p.strips_x) * kRowsPerStrip;
+    y1 = y0 + kRowsPerStrip < p.H ? y0 + kRowsPerStrip : p.H;
+  };
+
+  if (warp == kWarpTma) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_arrive_expect_tx(w_full, Cfg::kWBytes);
+      for (int kx = 0; kx < 3; ++kx)
+        for (int s = 0; s < 3; ++s)                       // slot s holds vertical tap ky = 2 - s
+          tma_load_2d(sW + (kx * 3 + s) * (NOUT * 128), &p.tma_w, w_full, ((2 - s) * 3 + kx) * 64, 0);
+      int rs = 0;
+      uint32_t rph = 0;
+      for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
+        int b, x0, y0, y1;
+        strip_geom(strip, b, x0, y0, y1);
+        for (int i = y0 - 1; i <= y1; ++i) {
+          mbar_wait(&row_empty[rs], rph ^ 1);
+          mbar_arrive_expect_tx(&row_full[rs], kRowLoadBytes);
+          tma_load_5d(sRow + rs * kRowBufBytes, &p.tma_in, &row_full[rs], 0, x0 - 1, 0, i, b);
+          if (++rs == Cfg::kRing) {
+            rs = 0;
+            rph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ===================== MMA issuer =====================
+    int rs = 0;
+    uint32_t rph = 0;
+    int seq0 = 0;                                         // running count of output rows of this CTA (TMEM ring position)
+    mbar_wait(w_full, 0);
+    for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
+      int b, x0, y0, y1;
+      strip_geom(strip, b, x0, y0, y1);
+      for (int i = y0 - 1; i <= y1; ++i) {
+        const int rlo = i - 1 > y0 ? i - 1 : y0;
+        const int rhi = i + 1 < y1 - 1 ? i + 1 : y1 - 1;
+        const bool fresh = (i + 1 <= y1 - 1);             // output row i+1 receives its first contribution from row i
+        if (fresh) {
+          const int sq = seq0 + (i + 1 - y0);
+          mbar_wait(&acc_empty[sq % NB], ((sq / NB) & 1) ^ 1);
+        }
+        mbar_wait(&row_full[rs], rph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sRow + rs * kRowBufBytes);
+        const uint32_t w_base = smem_u32(sW);
+        if (elect_one()) {
+          // accumulating output rows [rlo, rhi_acc], then (separately for the very first MMA) the fresh row
+          const int rhi_acc = fresh ? rhi - 1 : rhi;
+#pragma unroll 1
+          for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // The kx-shifted start address is not 1024-byte aligned; the 128B swizzle is a function of the absolute
+              // smem address bits, so the descriptor's base-offset field stays 0 (checked on the device: setting it
+              // to kx gives wrong sums).
+              const uint64_t a_desc = make_sdesc_sw128(a_base + kx * 128 + k * 32);
+              const bool first = (kx | k) == 0;
+              // walk the output rows in runs of TMEM-contiguous blocks (ring wrap, <= 256 columns, fresh row apart)
+              int r = rlo;
+              while (r <= rhi) {
+                const int sq = seq0 + (r - y0);
+                const int blk = sq % NB;
+                int n = 1;
+                const int rend = (first && fresh) ? (r <= rhi_acc ? rhi_acc : rhi) : rhi;
+                while (r + n <= rend && blk + n < NB && (n + 1) * NOUT <= 256) ++n;
+                const bool overwrite = first && fresh && r == rhi;         // the fresh row's first MMA
+                const int slot = r - i + 1;                                 // ky = 2 - slot
+                const uint64_t b_desc = make_sdesc_sw128(w_base + (kx * 3 + slot) * (NOUT * 128) + k * 32);
+                const uint32_t idesc = make_idesc_bf16(128, n * NOUT);
+                umma_bf16_ss(tmem_base + blk * NOUT, a_desc, b_desc, idesc, overwrite ? 0u : 1u);
+                r += n;
+              }
+            }
+          }
+          umma_commit(&row_empty[rs]);
+          if (i - 1 >= y0) {
+            const int sq = seq0 + (i - 1 - y0);
+            umma_commit(&acc_full[sq % NB]);                                // output row i-1 is complete
+          }
+        }
+        __syncwarp();
+        if (++rs == Cfg::kRing) {
+          rs = 0;
+          rph ^= 1;
+        }
+      }
+      seq0 += y1 - y0;
+    }
+  } else {
+    // ===================== epilogue: thread = pixel x0 + row of the output row =====================
+    const int row = warp * 32 + lane;
+    int seq0 = 0;
+    const WarpStage stg{nullptr, lane};
+    for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
+      int b, x0, y0, y1;
+      strip_geom(strip, b, x0, y0, y1);
+      for (int r = y0; r < y1; ++r) {
+        const int sq = seq0 + (r - y0);
+        const int blk = sq % NB;
+        mbar_wait(&acc_full[blk], (sq / NB) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + blk * NOUT;
+        if constexpr (std::is_same_v<Epi, EpiConv>) {
+          // out = [relu](acc + bias) as bf16: the warp's 32 pixels x 128 B go through a 128B-swizzled staging tile
+          // (16-byte chunk c of pixel row t sits at chunk c ^ (t & 7): conflict-free vector stores) and leave as ONE TMA
+          // store; per-thread 128-byte global stores cost 32 cache lines per instruction and bound the whole kernel.
+          static_assert(!std::is_same_v<Epi, EpiConv> || NOUT == 64, "staged store is written for 64 output channels");
+          uint8_t* stage = sOut + warp * 4096;
+          if (lane == 0) tma_store_wait_read();             // the previous row's store has read the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tmem_ld_f32x32(taddr + 32 * c, v);
+            if (p.epi.bias != nullptr) add_vec32(p.epi.bias + 32 * c, v);
+            if (p.epi.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+              u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+              u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+              u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((4 * c + q) ^ (lane & 7)) << 4)) = u;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&p.tma_out, stage, 0, x0 + warp * 32, 0, r, b);
+            tma_store_commit();
+          }
+        } else {
+          RowInfo ri;
+          ri.gm = 0; ri.t = 0; ri.b = b; ri.h = r; ri.w = x0 + row; ri.valid = true;
+          Epi::template run<NOUT>(p.epi, ri, 0, taddr, stg);
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[blk]);
+      }
+      seq0 += y1 - y0;
+    }
+    if constexpr (std::is_same_v<Epi, EpiConv>) {
+      if (lane == 0) tma_store_wait_all();                  // global writes complete before the CTA retires
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace s3od

@@ -96,6 +96,21 @@ bool tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
   return make_tmap(m, base, 5, dims, strides, box);
 }
 
+// NHWC (B, H, W, 64) activation for the row-streaming convolution: box = 64 ch x 130 pixels of one row
+bool tmap_nhwc_row(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, 1, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint32_t box[5] = {64, kRowPx + 2, 1, 1, 1};
+  return make_tmap(m, base, 5, dims, strides, box);
+}
+// ... and its bf16 NHWC output: box = 64 ch x 32 pixels (one epilogue warp)
+bool tmap_nhwc_row_out(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, 1, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint32_t box[5] = {64, 32, 1, 1, 1};
+  return make_tmap(m, base, 5, dims, strides, box);
+}
+
 // the same tensor viewed as (2C, W/2, 2, H/2, B): element (c + px*C, w2, py, h2, b) = in[b, 2*h2+py, 2*w2+px, c]
 bool tmap_nhwc_s2(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
   const uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)B};
@@ -273,6 +288,39 @@ bool add_conv(s3od_ctx* c, const std::string& label, const CUtensorMap& tma_a, c
     q.m_tiles = nb * geom.tiles_h * geom.tiles_w;
     if (patch) patch(q.epi, nb, b0, mo, io);
     return launch_gemm<BN, A_CONV, Epi, EW>(q, sms, st);
+  });
+  return true;
+}
+
+// 3x3 / stride 1 / pad 1 convolution with Cin = 64 and a small Cout on the row-streaming kernel (conv_rows.cuh);
+// needs W % 128 == 0, otherwise the caller falls back to the generic implicit GEMM.
+template <int NOUT, class Epi>
+bool add_conv_rows(s3od_ctx* c, const std::string& label, const bf16* in, int Hs, int Ws, const void* bw, typename Epi::Params ep,
+                   std::function<void(typename Epi::Params&, int, int, float*, float*)> patch = nullptr) {
+  RowConvParams<Epi> p{};
+  if (Ws % kRowPx != 0) {
+    g_err = "row convolution needs W % 128 == 0 for " + label;
+    return false;
+  }
+  if (!tmap_nhwc_row(&p.tma_in, in, c->mb, Hs, Ws, 64)) return false;
+  if (!tmap_matrix(&p.tma_w, bw, NOUT, 9 * 64, NOUT)) return false;
+  p.H = Hs; p.W = Ws;
+  p.strips_x = Ws / kRowPx;
+  p.strips_y = (Hs + kRowsPerStrip - 1) / kRowsPerStrip;
+  p.epi = ep;
+  if constexpr (std::is_same_v<Epi, EpiConv>) {
+    if (ep.res1 != nullptr || ep.res2 != nullptr || ep.out_relu != nullptr || ep.up != 1) {
+      g_err = "row convolution supports bias + relu only: " + label;
+      return false;
+    }
+    if (!tmap_nhwc_row_out(&p.tma_out, ep.out, c->mb, Hs, Ws, 64)) return false;
+  }
+  const int sms = c->num_sms;
+  c->plan.emplace_back(label, [=](int nb, int b0, float* mo, float* io, cudaStream_t st) mutable -> cudaError_t {
+    RowConvParams<Epi> q = p;
+    q.num_strips = nb * q.strips_x * q.strips_y;
+    if (patch) patch(q.epi, nb, b0, mo, io);
+    return launch_conv_rows<NOUT, Epi>(q, sms, st);
   });
   return true;
 }
@@ -533,7 +581,12 @@ bool build_plan(s3od_ctx* c) {
           return false;
       }
   }
-  {
+  const bool rows_ok = (S % kRowPx == 0) && getenv("S3OD_NO_ROWCONV") == nullptr;
+  if (rows_ok) {
+    if (!add_conv_rows<64, EpiConv>(c, "head.mh.c2", feat0, S, S, wptr<bf16>(c, "head.mh.c2.w"),
+                                    conv_epi(feat, nullptr, wptr<float>(c, "head.mh.c2.b"), nullptr, nullptr, 1, 64, S, S)))
+      return false;
+  } else {
     CUtensorMap ta;
     if (!tmap_nhwc(&ta, feat0, mb, S, S, 64)) return false;
     if (!add_conv<64, EpiConv, 4>(c, "head.mh.c2", ta, geom_3x3(S, S, 64), wptr<bf16>(c, "head.mh.c2.w"), 64, 0, 9 * 64, 64,
@@ -546,7 +599,11 @@ bool build_plan(s3od_ctx* c) {
     EpiMask::Params e{nullptr, wptr<float>(c, "head.mh.heads.b"), wptr<float>(c, "head.mh.heads.w2"), wptr<float>(c, "head.mh.heads.b2"), S, K};
     auto patch = [S, K](EpiMask::Params& q, int, int b0, float* mo, float*) { q.out = mo + static_cast<size_t>(b0) * K * S * S; };
     bool r;
-    if (K == 3)
+    if (rows_ok && K == 3)
+      r = add_conv_rows<96, EpiMask>(c, "head.mh.heads", feat, S, S, wptr<bf16>(c, "head.mh.heads.w"), e, patch);
+    else if (rows_ok && K == 1)
+      r = add_conv_rows<32, EpiMask>(c, "head.mh.heads", feat, S, S, wptr<bf16>(c, "head.mh.heads.w"), e, patch);
+    else if (K == 3)
       r = add_conv<96, EpiMask, 4>(c, "head.mh.heads", ta, geom_3x3(S, S, 64), wptr<bf16>(c, "head.mh.heads.w"), 96, 0, 9 * 64, 96, e, patch);
     else
       r = add_conv<32, EpiMask, 4>(c, "head.mh.heads", ta, geom_3x3(S, S, 64), wptr<bf16>(c, "head.mh.heads.w"), 32, 0, 9 * 64, 32, e, patch);
@@ -844,6 +901,25 @@ int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   CK((launch_gemm<256, A_CONV, EpiConv, 8>(p, sms, static_cast<cudaStream_t>(stream))));
+  return S3OD_OK;
+}
+
+int s3od_op_conv3x3_rows(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int relu,
+                         s3od_stream stream) {
+  if (w % kRowPx != 0 || batch < 1 || h < 1) return fail(S3OD_ERR_ARG, "s3od_op_conv3x3_rows needs w % 128 == 0");
+  RowConvParams<EpiConv> p{};
+  if (!tmap_nhwc_row(&p.tma_in, d_in, batch, h, w, 64)) return S3OD_ERR_CUDA;
+  if (!tmap_matrix(&p.tma_w, d_w, 64, 9 * 64, 64)) return S3OD_ERR_CUDA;
+  p.H = h; p.W = w;
+  p.strips_x = w / kRowPx;
+  p.strips_y = (h + kRowsPerStrip - 1) / kRowsPerStrip;
+  p.num_strips = batch * p.strips_x * p.strips_y;
+  p.epi = conv_epi(static_cast<bf16*>(d_out), nullptr, d_bias, nullptr, nullptr, relu, 64, h, w);
+  if (!tmap_nhwc_row_out(&p.tma_out, d_out, batch, h, w, 64)) return S3OD_ERR_CUDA;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK((launch_conv_rows<64, EpiConv>(p, sms, static_cast<cudaStream_t>(stream))));
   return S3OD_OK;
 }
 

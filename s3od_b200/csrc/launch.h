@@ -1,12 +1,16 @@
 // Host-side launch declarations; kernels are instantiated in kernels_gemm_*.cu / kernels_misc.cu.
 #pragma once
 #include "gemm_tc.cuh"
+#include "conv_rows.cuh"
 #include "types.h"
 
 namespace s3od {
 
 template <int BN, int AMODE, class Epi, int EPI_WARPS>
 cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stream);
+
+template <int NOUT, class Epi>
+cudaError_t launch_conv_rows(const RowConvParams<Epi>& p, int num_sms, cudaStream_t stream);
 
 extern long long* g_attn_trace;
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream);

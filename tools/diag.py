@@ -139,6 +139,38 @@ def diag_conv():
     print(f"conv3x3 B=4 256x256 256->256: {ms:.3f} ms  {2 * B * h * w * cout * 9 * cin / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def diag_convrows():
+    lib = load_library()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for mode in (0,):
+        for (B, h, w) in [(1, 1, 128), (1, 5, 128), (2, 70, 256), (1, 130, 384)]:
+            x = torch.randn(B, h, w, 64, device="cuda", generator=g).bfloat16()
+            wt = (torch.randn(64, 64, 3, 3, device="cuda", generator=g) / 24).bfloat16()
+            bias = torch.randn(64, device="cuda", generator=g)
+            wp = wt.permute(0, 2, 3, 1).reshape(64, 9 * 64).contiguous()
+            y = torch.full((B, h, w, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+            rc = lib.s3od_op_conv3x3_rows(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), y.data_ptr(), B, h, w, 1, _st())
+            torch.cuda.synchronize()
+            ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1)).permute(0, 2, 3, 1)
+            r, m = rel(y, ref)
+            print(f"conv_rows base_offset={mode} B={B} {h}x{w} rc={rc} rel={r:.3e} maxabs={m:.3e} nan={int(torch.isnan(y.float()).sum())}", flush=True)
+    B, h, w = 16, 1024, 1024
+    x = torch.randn(B, h, w, 64, device="cuda").bfloat16()
+    wp = torch.randn(64, 9 * 64, device="cuda").bfloat16()
+    y = torch.empty(B, h, w, 64, device="cuda", dtype=torch.bfloat16)
+    for mode in (1,):
+        for _ in range(2):
+            lib.s3od_op_conv3x3_rows(x.data_ptr(), wp.data_ptr(), None, y.data_ptr(), B, h, w, 1, _st())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            lib.s3od_op_conv3x3_rows(x.data_ptr(), wp.data_ptr(), None, y.data_ptr(), B, h, w, 1, _st())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"conv_rows B=16 1024x1024 64->64: {ms:.3f} ms  {2 * B * h * w * 64 * 9 * 64 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def diag_model():
     from s3od_b200.synth import synth_state_dict
     from oracle import model as om
@@ -225,6 +257,7 @@ def diag_step():
 
 
 FAMILIES["step"] = diag_step
+FAMILIES["convrows"] = diag_convrows
 
 
 def diag_stall():
