@@ -129,6 +129,19 @@ S3OD_DEVICE void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
       : "memory");
 }
 
+// Same, predicated INSIDE the asm: every lane of the issuing warp executes the statement with warp-uniform operands
+// (which the compiler can then keep in uniform registers) and only the lane whose `issue` is non-zero launches the MMA.
+S3OD_DEVICE void umma_bf16_ss_if(uint32_t issue, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (bits 4-5 = 1), a/b format BF16
 // (bits 7-9, 10-12 = 1), a/b K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {

@@ -25,6 +25,10 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
+#ifndef S3OD_ROWCONV_LAB
+#define S3OD_ROWCONV_LAB 0          // tools/lab only: bit 0 = no epilogue work, bit 1 = no MMAs, bit 2 = no output store
+#endif
+
 namespace s3od {
 
 constexpr int kRowPx = 128;                       // output pixels per row tile (UMMA M)
@@ -126,8 +130,12 @@ __global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant
         strip_geom(strip, b, x0, y0, y1);
         for (int i = y0 - 1; i <= y1; ++i) {
           mbar_wait(&row_empty[rs], rph ^ 1);
-          mbar_arrive_expect_tx(&row_full[rs], kRowLoadBytes);
-          tma_load_5d(sRow + rs * kRowBufBytes, &p.tma_in, &row_full[rs], 0, x0 - 1, 0, i, b);
+          if (S3OD_ROWCONV_LAB & 8) {
+            mbar_arrive(&row_full[rs]);
+          } else {
+            mbar_arrive_expect_tx(&row_full[rs], kRowLoadBytes);
+            tma_load_5d(sRow + rs * kRowBufBytes, &p.tma_in, &row_full[rs], 0, x0 - 1, 0, i, b);
+          }
           if (++rs == Cfg::kRing) {
             rs = 0;
             rph ^= 1;
@@ -140,6 +148,7 @@ __global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant
     int rs = 0;
     uint32_t rph = 0;
     int seq0 = 0;                                         // running count of output rows of this CTA (TMEM ring position)
+    const bool leader = elect_one();
     mbar_wait(w_full, 0);
     for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
       int b, x0, y0, y1;
@@ -154,37 +163,57 @@ __global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant
         }
         mbar_wait(&row_full[rs], rph);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sRow + rs * kRowBufBytes);
-        const uint32_t w_base = smem_u32(sW);
-        if (elect_one()) {
-          // accumulating output rows [rlo, rhi_acc], then (separately for the very first MMA) the fresh row
-          const int rhi_acc = fresh ? rhi - 1 : rhi;
-#pragma unroll 1
-          for (int kx = 0; kx < 3; ++kx) {
+        // Runs = TMEM-contiguous blocks of output rows (split at the ring wrap and at 256 columns).  They are worked out
+        // once per input row; the 12 (kx, 16-channel step) MMAs per run then only add constants to the descriptors.
+        // For the very first step (kx = 0, k = 0) the fresh output row i+1 is a run of its own that OVERWRITES its TMEM
+        // block (list F: the accumulating rows in <= 2 runs, then the fresh row); the other 11 steps accumulate into
+        // all rows (list G: <= 2 runs).
+        constexpr int kMaxRun = 256 / NOUT;
+        auto make_runs = [&](int r0, int r1, uint32_t (&d)[2], uint32_t (&id)[2], uint32_t (&bo)[2]) {
+          d[0] = d[1] = id[0] = id[1] = bo[0] = bo[1] = 0;
+          int r = r0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // The kx-shifted start address is not 1024-byte aligned; the 128B swizzle is a function of the absolute
-              // smem address bits, so the descriptor's base-offset field stays 0 (checked on the device: setting it
-              // to kx gives wrong sums).
-              const uint64_t a_desc = make_sdesc_sw128(a_base + kx * 128 + k * 32);
-              const bool first = (kx | k) == 0;
-              // walk the output rows in runs of TMEM-contiguous blocks (ring wrap, <= 256 columns, fresh row apart)
-              int r = rlo;
-              while (r <= rhi) {
-                const int sq = seq0 + (r - y0);
-                const int blk = sq % NB;
-                int n = 1;
-                const int rend = (first && fresh) ? (r <= rhi_acc ? rhi_acc : rhi) : rhi;
-                while (r + n <= rend && blk + n < NB && (n + 1) * NOUT <= 256) ++n;
-                const bool overwrite = first && fresh && r == rhi;         // the fresh row's first MMA
-                const int slot = r - i + 1;                                 // ky = 2 - slot
-                const uint64_t b_desc = make_sdesc_sw128(w_base + (kx * 3 + slot) * (NOUT * 128) + k * 32);
-                const uint32_t idesc = make_idesc_bf16(128, n * NOUT);
-                umma_bf16_ss(tmem_base + blk * NOUT, a_desc, b_desc, idesc, overwrite ? 0u : 1u);
-                r += n;
-              }
+          for (int q = 0; q < 2; ++q) {
+            if (r <= r1) {
+              const int blk = (seq0 + (r - y0)) % NB;
+              int n = r1 - r + 1;
+              n = n < NB - blk ? n : NB - blk;
+              n = n < kMaxRun ? n : kMaxRun;
+              d[q] = tmem_base + blk * NOUT;
+              id[q] = make_idesc_bf16(128, n * NOUT);
+              bo[q] = static_cast<uint32_t>((r - i + 1) * (NOUT * 128)) >> 4;      // slot = r - i + 1, ky = 2 - slot
+              r += n;
             }
           }
+        };
+        uint32_t f_d[2], f_id[2], f_b[2], g_d[2], g_id[2], g_b[2];
+        make_runs(rlo, fresh ? rhi - 1 : rhi, f_d, f_id, f_b);
+        make_runs(rlo, rhi, g_d, g_id, g_b);
+        const uint32_t fresh_d = tmem_base + ((seq0 + (rhi - y0)) % NB) * NOUT;
+        const uint32_t fresh_b = static_cast<uint32_t>((rhi - i + 1) * (NOUT * 128)) >> 4;
+        const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(sRow + rs * kRowBufBytes));
+        const uint64_t w_desc0 = make_sdesc_sw128(smem_u32(sW));
+        constexpr uint32_t idesc1 = make_idesc_bf16(128, NOUT);
+        // Warp-uniform issue: every lane walks the loop with uniform operands, the MMA is predicated on the elected lane
+        // inside the asm (a divergent `if (leader)` around the loop makes the compiler move every descriptor from vector
+        // to uniform registers again for each MMA: 10 R2UR per step, measured 190 clk per step instead of 96).
+        const uint32_t lead = (leader && !(S3OD_ROWCONV_LAB & 2)) ? 1u : 0u;
+        umma_bf16_ss_if(f_id[0] != 0 ? lead : 0u, f_d[0], a_desc0, w_desc0 + f_b[0], f_id[0], 1u);
+        umma_bf16_ss_if(f_id[1] != 0 ? lead : 0u, f_d[1], a_desc0, w_desc0 + f_b[1], f_id[1], 1u);
+        umma_bf16_ss_if(fresh ? lead : 0u, fresh_d, a_desc0, w_desc0 + fresh_b, idesc1, 0u);
+        const uint32_t lead1 = g_id[1] != 0 ? lead : 0u;
+#pragma unroll
+        for (int step = 1; step < 12; ++step) {
+          // The kx-shifted start address is not 1024-byte aligned; the 128B swizzle is a function of the absolute
+          // smem address bits, so the descriptor's base-offset field stays 0 (checked on the device: setting it
+          // to kx gives wrong sums).  Descriptor addresses count 16-byte units: one pixel row = 8, 16 channels = 2.
+          const int kx = step >> 2, k = step & 3;
+          const uint64_t a_desc = a_desc0 + (kx * 8 + k * 2);
+          const uint64_t w_desc = w_desc0 + ((kx * 3 * NOUT * 128 + k * 32) >> 4);
+          umma_bf16_ss_if(lead, g_d[0], a_desc, w_desc + g_b[0], g_id[0], 1u);
+          umma_bf16_ss_if(lead1, g_d[1], a_desc, w_desc + g_b[1], g_id[1], 1u);
+        }
+        if (leader) {
           umma_commit(&row_empty[rs]);
           if (i - 1 >= y0) {
             const int sq = seq0 + (i - 1 - y0);
@@ -213,7 +242,8 @@ __global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant
         mbar_wait(&acc_full[blk], (sq / NB) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + blk * NOUT;
-        if constexpr (std::is_same_v<Epi, EpiConv>) {
+        if (S3OD_ROWCONV_LAB & 1) {
+        } else if constexpr (std::is_same_v<Epi, EpiConv>) {
           // out = [relu](acc + bias) as bf16: the warp's 32 pixels x 128 B go through a 128B-swizzled staging tile
           // (16-byte chunk c of pixel row t sits at chunk c ^ (t & 7): conflict-free vector stores) and leave as ONE TMA
           // store; per-thread 128-byte global stores cost 32 cache lines per instruction and bound the whole kernel.
@@ -242,7 +272,7 @@ __global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(S3OD_ROWCONV_LAB & 4)) {
             tma_store_5d(&p.tma_out, stage, 0, x0 + warp * 32, 0, r, b);
             tma_store_commit();
           }
