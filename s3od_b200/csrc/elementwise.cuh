@@ -186,66 +186,102 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
 // ------------------------------------------------------------------------------------------------------------------
 // 2x bilinear up-sampling, align_corners=False, NHWC bf16 (FeatureFusionBlock, model.py:394-402; the following 1x1
 // out_conv has been applied at low resolution - it commutes with the interpolation because the weights sum to 1).
-// Thread = one INPUT pixel x 8 channels -> the 2x2 output pixels it generates (9 taps read, 4 pixels written).  With
-// `pool` != nullptr each block also writes per-channel partial sums of its outputs (deterministic two-stage average
+// Thread = one INPUT column x 8 channels walking DOWN a strip of rows: the horizontally interpolated values of the last
+// two input rows stay in registers, so each step reads ONE new input row (3 taps: the x neighbours belong to the other
+// warps of the block and hit in L1) and writes the 2x2 output pixels of its input pixel.  (Reading all 9 taps per pixel
+// made the kernel L2-bound at 3.5 TB/s of output-equivalent traffic.)
+// With `pool` != nullptr each block also writes per-channel partial sums of its outputs (deterministic two-stage average
 // pool for the IoU head, model.py:185-191).
-// grid = (blocks_per_image, B), block = 256 threads = (C/8) channel groups x (256 / (C/8)) input pixels per step.
+// grid = (blocks_per_image, B), block = 256 threads = (C/8) channel groups x (256 / (C/8)) input columns; a block walks
+// work units (8-column tile, kUpsRows-row strip) grid-stride.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kUpsRows = 32;
+
 template <int C>
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                          float* __restrict__ pool, int h, int w) {
   constexpr int CG = C / 8;                 // channel groups (threads along channels)
-  constexpr int PP = 256 / CG;              // input pixels per block step
+  constexpr int PP = 256 / CG;              // input columns per block
   const int b = blockIdx.y;
   const int cg = threadIdx.x % CG;
   const int pl = threadIdx.x / CG;
   const int OW = 2 * w;
-  const int npix = h * w;
+  const size_t npix = static_cast<size_t>(h) * w;
   const __nv_bfloat16* ib = in + static_cast<size_t>(b) * npix * C + cg * 8;
   __nv_bfloat16* ob = out + static_cast<size_t>(b) * 4 * npix * C + cg * 8;
   float psum[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) psum[i] = 0.0f;
-  for (int ip = blockIdx.x * PP + pl; ip < npix; ip += gridDim.x * PP) {
-    const int iy = ip / w, ix = ip - iy * w;
-    const int ym = max(iy - 1, 0), yp = min(iy + 1, h - 1);
+  const int x_tiles = (w + PP - 1) / PP;
+  const int units = x_tiles * ((h + kUpsRows - 1) / kUpsRows);
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int ix = (unit % x_tiles) * PP + pl;
+    const int y0 = (unit / x_tiles) * kUpsRows;
+    const int y1 = min(y0 + kUpsRows, h);
+    if (ix >= w) continue;
     const int xm = max(ix - 1, 0), xp = min(ix + 1, w - 1);
     // source coordinate (o + 0.5)/2 - 0.5 clamped at 0: output 2i uses taps (i-1: .25, i: .75) [(0, 1) at i = 0],
     // output 2i+1 uses (i: .75, i+1: .25)
     const float wl0 = ix == 0 ? 0.0f : 0.25f, wl1 = 1.0f - wl0;
-    const float wt0 = iy == 0 ? 0.0f : 0.25f, wt1 = 1.0f - wt0;
-    float L[3][8], R[3][8];                 // horizontally interpolated rows (ym, iy, yp) for output columns 2ix, 2ix+1
-    const int rows[3] = {ym, iy, yp};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const __nv_bfloat16* rp = ib + static_cast<size_t>(rows[r]) * w * C;
+    // horizontally interpolated input row for output columns 2ix (L) and 2ix+1 (R)
+    auto hrow = [&](int row, float (&L)[8], float (&R)[8]) {
+      const __nv_bfloat16* rp = ib + static_cast<size_t>(row) * w * C;
       const uint4 a = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(xm) * C);
       const uint4 m = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(ix) * C);
       const uint4 c = *reinterpret_cast<const uint4*>(rp + static_cast<size_t>(xp) * C);
       const uint32_t av[4] = {a.x, a.y, a.z, a.w}, mv[4] = {m.x, m.y, m.z, m.w}, cv[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        L[r][2 * i] = wl0 * bf16_lo(av[i]) + wl1 * bf16_lo(mv[i]);
-        L[r][2 * i + 1] = wl0 * bf16_hi(av[i]) + wl1 * bf16_hi(mv[i]);
-        R[r][2 * i] = 0.75f * bf16_lo(mv[i]) + 0.25f * bf16_lo(cv[i]);
-        R[r][2 * i + 1] = 0.75f * bf16_hi(mv[i]) + 0.25f * bf16_hi(cv[i]);
+        L[2 * i] = wl0 * bf16_lo(av[i]) + wl1 * bf16_lo(mv[i]);
+        L[2 * i + 1] = wl0 * bf16_hi(av[i]) + wl1 * bf16_hi(mv[i]);
+        R[2 * i] = 0.75f * bf16_lo(mv[i]) + 0.25f * bf16_lo(cv[i]);
+        R[2 * i + 1] = 0.75f * bf16_hi(mv[i]) + 0.25f * bf16_hi(cv[i]);
+      }
+    };
+    // the 2x2 outputs of input pixel (iy, ix) from the rows above (0), at (1) and below (2)
+    auto emit = [&](int iy, const float (&L0)[8], const float (&R0)[8], const float (&L1)[8], const float (&R1)[8],
+                    const float (&L2)[8], const float (&R2)[8]) {
+      const float wt0 = iy == 0 ? 0.0f : 0.25f, wt1 = 1.0f - wt0;
+      uint32_t o00[4], o01[4], o10[4], o11[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = 2 * i + u;
+          v[u] = wt0 * L0[e] + wt1 * L1[e];
+          v[2 + u] = wt0 * R0[e] + wt1 * R1[e];
+          v[4 + u] = 0.75f * L1[e] + 0.25f * L2[e];
+          v[6 + u] = 0.75f * R1[e] + 0.25f * R2[e];
+          psum[e] += (v[u] + v[2 + u]) + (v[4 + u] + v[6 + u]);
+        }
+        o00[i] = pack_bf16x2(v[0], v[1]);
+        o01[i] = pack_bf16x2(v[2], v[3]);
+        o10[i] = pack_bf16x2(v[4], v[5]);
+        o11[i] = pack_bf16x2(v[6], v[7]);
+      }
+      __nv_bfloat16* o0 = ob + (static_cast<size_t>(2 * iy) * OW + 2 * ix) * C;
+      __nv_bfloat16* o1 = o0 + static_cast<size_t>(OW) * C;
+      *reinterpret_cast<uint4*>(o0) = make_uint4(o00[0], o00[1], o00[2], o00[3]);
+      *reinterpret_cast<uint4*>(o0 + C) = make_uint4(o01[0], o01[1], o01[2], o01[3]);
+      *reinterpret_cast<uint4*>(o1) = make_uint4(o10[0], o10[1], o10[2], o10[3]);
+      *reinterpret_cast<uint4*>(o1 + C) = make_uint4(o11[0], o11[1], o11[2], o11[3]);
+    };
+    float La[8], Ra[8], Lb[8], Rb[8], Lc[8], Rc[8];
+    hrow(max(y0 - 1, 0), La, Ra);
+    hrow(y0, Lb, Rb);
+    for (int iy = y0; iy < y1; iy += 3) {          // the three register rows rotate roles
+      hrow(min(iy + 1, h - 1), Lc, Rc);
+      emit(iy, La, Ra, Lb, Rb, Lc, Rc);
+      if (iy + 1 < y1) {
+        hrow(min(iy + 2, h - 1), La, Ra);
+        emit(iy + 1, Lb, Rb, Lc, Rc, La, Ra);
+      }
+      if (iy + 2 < y1) {
+        hrow(min(iy + 3, h - 1), Lb, Rb);
+        emit(iy + 2, Lc, Rc, La, Ra, Lb, Rb);
       }
     }
-    float o00[8], o01[8], o10[8], o11[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o00[i] = wt0 * L[0][i] + wt1 * L[1][i];
-      o01[i] = wt0 * R[0][i] + wt1 * R[1][i];
-      o10[i] = 0.75f * L[1][i] + 0.25f * L[2][i];
-      o11[i] = 0.75f * R[1][i] + 0.25f * R[2][i];
-      psum[i] += (o00[i] + o01[i]) + (o10[i] + o11[i]);
-    }
-    __nv_bfloat16* o0 = ob + (static_cast<size_t>(2 * iy) * OW + 2 * ix) * C;
-    __nv_bfloat16* o1 = o0 + static_cast<size_t>(OW) * C;
-    *reinterpret_cast<uint4*>(o0) = make_uint4(pack_bf16x2(o00[0], o00[1]), pack_bf16x2(o00[2], o00[3]), pack_bf16x2(o00[4], o00[5]), pack_bf16x2(o00[6], o00[7]));
-    *reinterpret_cast<uint4*>(o0 + C) = make_uint4(pack_bf16x2(o01[0], o01[1]), pack_bf16x2(o01[2], o01[3]), pack_bf16x2(o01[4], o01[5]), pack_bf16x2(o01[6], o01[7]));
-    *reinterpret_cast<uint4*>(o1) = make_uint4(pack_bf16x2(o10[0], o10[1]), pack_bf16x2(o10[2], o10[3]), pack_bf16x2(o10[4], o10[5]), pack_bf16x2(o10[6], o10[7]));
-    *reinterpret_cast<uint4*>(o1 + C) = make_uint4(pack_bf16x2(o11[0], o11[1]), pack_bf16x2(o11[2], o11[3]), pack_bf16x2(o11[4], o11[5]), pack_bf16x2(o11[6], o11[7]));
   }
   if (pool != nullptr) {
     __shared__ float red[PP][C + 1];

@@ -378,7 +378,7 @@ bool build_plan(s3od_ctx* c) {
   ok = ok && alloc_act(c, "mh1", static_cast<size_t>(mb) * R0 * R0 * 128 * 2);
   ok = ok && alloc_act(c, "feat0", static_cast<size_t>(mb) * S * S * 64 * 2);
   ok = ok && alloc_act(c, "feat", static_cast<size_t>(mb) * S * S * 64 * 2);
-  c->pool_blocks = std::max(1, std::min(4 * c->num_sms / std::max(1, mb) + 1, (R0 * R0 + 63) / 64));
+  c->pool_blocks = std::max(1, std::min(8 * c->num_sms / std::max(1, mb) + 1, ((R0 / 2 + 7) / 8) * ((R0 / 2 + 31) / 32)));
   ok = ok && alloc_act(c, "pool", static_cast<size_t>(mb) * c->pool_blocks * 256 * 4);
   if (!ok) return false;
 

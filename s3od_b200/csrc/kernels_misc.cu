@@ -65,13 +65,13 @@ cudaError_t launch_fill_prefix(float* x, const float* prefix, int ntok, int D, i
 
 cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float* pool, int pool_blocks, int B, int h, int w,
                               int num_sms, cudaStream_t stream) {
-  const int npix = h * w;                                        // input pixels; a block handles 8 per step
+  const int units = ((w + 7) / 8) * ((h + kUpsRows - 1) / kUpsRows);   // (8-column tile, row strip) work units per image
   int blocks;
   if (pool != nullptr) {
-    blocks = pool_blocks;
+    blocks = pool_blocks;                                           // the partial-sum buffer is sized for this grid
   } else {
-    blocks = (npix + 31) / 32;                                   // >= 4 steps per block
-    const int cap = (8 * num_sms + B - 1) / B;
+    blocks = units;
+    const int cap = (16 * num_sms + B - 1) / B;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
   }
