@@ -111,6 +111,10 @@ int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void
 /* the same convolution for cin = 64, cout = 64 on the row-streaming kernel (w % 128 == 0) */
 int s3od_op_conv3x3_rows(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int relu,
                          s3od_stream stream);
+/* ConvTranspose2d(128 -> 64, k4, s2, p1) on the row-streaming kernel: NHWC bf16 in (batch, h, w, 128) -> (batch, 2h, 2w, 64);
+   weights packed as weights.py "head.mh.up.wr": row ((b*2 + t)*4 + kh)*64 + co, 128 ci columns; w % 128 == 0 */
+int s3od_op_convt_rows(const void* d_in, const void* d_wr, const float* d_bias, void* d_out, int batch, int h, int w, int relu,
+                       s3od_stream stream);
 
 /* debug aid: per-tile clock64() stamps of one attention CTA (only filled when S3OD_ATTN_TRACE=1 is set) */
 int s3od_debug_attn_trace(long long* host_out /* [64][8] */);

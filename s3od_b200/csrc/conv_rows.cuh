@@ -299,4 +299,236 @@ __global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant
   }
 }
 
+// ================================================================================================
+// Row-streaming ConvTranspose2d(k = 4, stride 2, pad 1), Cin = 128 -> Cout = 64 (mask head `upsample_2x.0`,
+// model.py:446-449), one launch per output-column phase b (output column 2j + b).
+//
+// Output row 2i - 1 + kh receives input row i through kernel row kh, output column 2j - 1 + kw input column j through
+// kernel column kw.  Input-stationary like conv_rows_kernel: the A tile is 128 consecutive pixels of input row i (both
+// 64-channel halves, 130 pixels each); for phase b only two kernel columns matter (b = 0: kw = 1 at column shift 0 and
+// kw = 3 at shift -1;  b = 1: kw = 0 at shift +1 and kw = 2 at shift 0), and ONE N = 256 MMA per (column tap,
+// 16-channel step) multiplies the tile with the four kernel rows stacked: kh = 0, 1 complete the output row pair
+// (2i-1, 2i), kh = 2, 3 start the pair (2i+1, 2i+2).  A "pair block" = 2 output rows x 64 channels = 128 TMEM columns;
+// four of them form a ring.  The 2 x 4 x 64 x 128 weights of the phase (128 KB) stay resident in shared memory.
+// (The four sub-pixel 2x2 convolutions this replaces ran N = 64 MMAs with a 512-deep K: 41 % of the tensor peak.)
+// ================================================================================================
+constexpr int kCtPairsPerStrip = 32;
+
+struct ConvTRowParams {
+  CUtensorMap tma_in;      // NHWC input as (C = 128, W, 1, H, B), box (64, 130, 1, 1, 1)
+  CUtensorMap tma_w;       // weights [(b*2 + t)*256 + kh*64 + co, 128 ci], box (64, 256)
+  CUtensorMap tma_out;     // NHWC output (B, 2H, 2W, 64) as (C = 64, 2, W, 2H, B), box (64, 1, 32, 1, 1)
+  int H, W;                // INPUT size (W % 128 == 0)
+  int strips_x, strips_y;
+  int num_strips;
+  int phase_b;             // output column phase of this launch
+  const float* bias;       // [64] or nullptr
+  int relu;
+};
+
+struct ConvTRowCfg {
+  static constexpr int kWBytes = 4 * 256 * 128;                       // (2 column taps) x (2 channel halves) x [256 rows x 128 B]
+  static constexpr int kRing = 2;                                     // input rows in flight (2 channel halves each)
+  static constexpr int kRowBytes = 2 * kRowBufBytes;
+  static constexpr int kStageOutBytes = 4 * 32 * 128;
+  static constexpr int kSmemBytes = kWBytes + kRing * kRowBytes + kStageOutBytes + 1024 + 512;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <int kUnused = 0>      // a template only so that the header can be included by several translation units
+__global__ void __launch_bounds__(192, 1) convt_rows_kernel(const __grid_constant__ ConvTRowParams p) {
+  using Cfg = ConvTRowCfg;
+  constexpr int NB = 4;                                   // pair blocks in the TMEM ring (128 columns each)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;                                     // [t][kb][kh*64 + co rows x 128 B]
+  uint8_t* sRow = smem + Cfg::kWBytes;                    // ring of input rows: [slot][kb][130 px x 128 B]
+  uint8_t* sOut = sRow + Cfg::kRing * Cfg::kRowBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + Cfg::kStageOutBytes);
+  uint64_t* w_full = bars;
+  uint64_t* row_full = bars + 1;
+  uint64_t* row_empty = row_full + Cfg::kRing;
+  uint64_t* acc_full = row_empty + Cfg::kRing;            // [NB]
+  uint64_t* acc_empty = acc_full + NB;                    // [NB] (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NB);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kWarpTma = 4, kWarpMma = 5;
+
+  if (warp == kWarpTma && lane == 0) {
+    tma_prefetch_desc(&p.tma_in);
+    tma_prefetch_desc(&p.tma_w);
+    tma_prefetch_desc(&p.tma_out);
+  }
+  if (warp == kWarpMma) {
+    if (lane == 0) {
+      mbar_init(w_full, 1);
+      for (int i = 0; i < Cfg::kRing; ++i) {
+        mbar_init(&row_full[i], 1);
+        mbar_init(&row_empty[i], 1);
+      }
+      for (int i = 0; i < NB; ++i) {
+        mbar_init(&acc_full[i], 1);
+        mbar_init(&acc_empty[i], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // strip -> image, first input column, pair blocks [q0, q1): pair block q = output rows (2q-1, 2q), q in [0, H]
+  auto strip_geom = [&](int s, int& b, int& x0, int& q0, int& q1) {
+    const int per_img = p.strips_x * p.strips_y;
+    b = s / per_img;
+    const int r = s % per_img;
+    x0 = (r % p.strips_x) * kRowPx;
+    const int sy = r / p.strips_x;
+    q0 = sy * kCtPairsPerStrip;
+    q1 = sy == p.strips_y - 1 ? p.H + 1 : q0 + kCtPairsPerStrip;
+  };
+  // column shift of tap t for this phase: b = 0: (0, -1);  b = 1: (+1, 0)
+  const int dj0 = p.phase_b == 0 ? 0 : 1, dj1 = p.phase_b == 0 ? -1 : 0;
+
+  if (warp == kWarpTma) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, Cfg::kWBytes);
+      for (int t = 0; t < 2; ++t)
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_2d(sW + (t * 2 + kb) * (256 * 128), &p.tma_w, w_full, kb * 64, (p.phase_b * 2 + t) * 256);
+      int rs = 0;
+      uint32_t rph = 0;
+      for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
+        int b, x0, q0, q1;
+        strip_geom(strip, b, x0, q0, q1);
+        for (int i = q0 - 1; i <= q1 - 1; ++i) {
+          mbar_wait(&row_empty[rs], rph ^ 1);
+          mbar_arrive_expect_tx(&row_full[rs], 2 * kRowLoadBytes);
+          tma_load_5d(sRow + rs * Cfg::kRowBytes, &p.tma_in, &row_full[rs], 0, x0 - 1, 0, i, b);
+          tma_load_5d(sRow + rs * Cfg::kRowBytes + kRowBufBytes, &p.tma_in, &row_full[rs], 64, x0 - 1, 0, i, b);
+          if (++rs == Cfg::kRing) {
+            rs = 0;
+            rph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    int rs = 0;
+    uint32_t rph = 0;
+    int seq0 = 0;                                         // running count of pair blocks of this CTA
+    const bool leader = elect_one();
+    mbar_wait(w_full, 0);
+    const uint64_t w_desc0 = make_sdesc_sw128(smem_u32(sW));
+    constexpr uint32_t idesc128 = make_idesc_bf16(128, 128), idesc256 = make_idesc_bf16(128, 256);
+    for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
+      int b, x0, q0, q1;
+      strip_geom(strip, b, x0, q0, q1);
+      for (int i = q0 - 1; i <= q1 - 1; ++i) {
+        const bool comp = i >= q0;                        // kernel rows 0, 1 complete pair block i
+        const bool fresh = i + 1 <= q1 - 1;               // kernel rows 2, 3 start pair block i + 1
+        const int sq_c = seq0 + (i - q0), sq_f = sq_c + 1;
+        if (fresh) mbar_wait(&acc_empty[sq_f % NB], ((sq_f / NB) & 1) ^ 1);
+        mbar_wait(&row_full[rs], rph);
+        tc_fence_after();
+        const uint32_t d_c = tmem_base + (sq_c % NB) * 128, d_f = tmem_base + (sq_f % NB) * 128;
+        const bool merged = comp && fresh && (sq_c % NB) != NB - 1;     // one N = 256 MMA covers both pair blocks
+        const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(sRow + rs * Cfg::kRowBytes));
+        const uint32_t lead = leader ? 1u : 0u;
+        const uint32_t lead_m = merged ? lead : 0u, lead_c = (comp && !merged) ? lead : 0u, lead_f = (fresh && !merged) ? lead : 0u;
+#pragma unroll
+        for (int step = 0; step < 16; ++step) {
+          const int t = step >> 3, kb = (step >> 2) & 1, k = step & 3;
+          const int dj = t == 0 ? dj0 : dj1;
+          // descriptor addresses count 16-byte units: pixel row = 8, 16 channels = 2, channel half = kRowBufBytes / 16
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((kb * kRowBufBytes + (1 + dj) * 128 + k * 32) >> 4);
+          const uint64_t w_desc = w_desc0 + static_cast<uint64_t>(((t * 2 + kb) * (256 * 128) + k * 32) >> 4);
+          if (step == 0) {
+            // the fresh pair block is overwritten by its very first MMA, the completing one accumulates
+            umma_bf16_ss_if(comp ? lead : 0u, d_c, a_desc, w_desc, idesc128, 1u);
+            umma_bf16_ss_if(fresh ? lead : 0u, d_f, a_desc, w_desc + ((128 * 128) >> 4), idesc128, 0u);
+          } else {
+            umma_bf16_ss_if(lead_m, d_c, a_desc, w_desc, idesc256, 1u);
+            umma_bf16_ss_if(lead_c, d_c, a_desc, w_desc, idesc128, 1u);
+            umma_bf16_ss_if(lead_f, d_f, a_desc, w_desc + ((128 * 128) >> 4), idesc128, 1u);
+          }
+        }
+        if (leader) {
+          umma_commit(&row_empty[rs]);
+          if (comp) umma_commit(&acc_full[sq_c % NB]);
+        }
+        __syncwarp();
+        if (++rs == Cfg::kRing) {
+          rs = 0;
+          rph ^= 1;
+        }
+      }
+      seq0 += q1 - q0;
+    }
+  } else {
+    // ===================== epilogue: thread = input column x0 + row -> output column 2 (x0 + row) + b =====================
+    int seq0 = 0;
+    uint8_t* stage = sOut + warp * 4096;
+    for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
+      int b, x0, q0, q1;
+      strip_geom(strip, b, x0, q0, q1);
+      for (int q = q0; q < q1; ++q) {
+        const int sq = seq0 + (q - q0);
+        const int blk = sq % NB;
+        mbar_wait(&acc_full[blk], (sq / NB) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + blk * 128;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {            // output rows 2q - 1 and 2q
+          const int orow = 2 * q - 1 + half;
+          if (orow < 0 || orow >= 2 * p.H) continue;      // warp-uniform
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tmem_ld_f32x32(taddr + half * 64 + 32 * c, v);
+            if (p.bias != nullptr) add_vec32(p.bias + 32 * c, v);
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * qq + 0], v[8 * qq + 1]);
+              u.y = pack_bf16x2(v[8 * qq + 2], v[8 * qq + 3]);
+              u.z = pack_bf16x2(v[8 * qq + 4], v[8 * qq + 5]);
+              u.w = pack_bf16x2(v[8 * qq + 6], v[8 * qq + 7]);
+              *reinterpret_cast<uint4*>(stage + lane * 128 + (((4 * c + qq) ^ (lane & 7)) << 4)) = u;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&p.tma_out, stage, 0, p.phase_b, x0 + warp * 32, orow, b);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[blk]);
+      }
+      seq0 += q1 - q0;
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace s3od

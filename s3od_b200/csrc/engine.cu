@@ -111,6 +111,33 @@ bool tmap_nhwc_row_out(CUtensorMap* m, const void* base, int B, int H, int W, in
   return make_tmap(m, base, 5, dims, strides, box);
 }
 
+// transposed-convolution rows: input (B, H, W, 128) fetched as 64-channel halves, box = 64 ch x 130 pixels of one row
+bool tmap_nhwc_row128(CUtensorMap* m, const void* base, int B, int H, int W) {
+  const uint64_t dims[5] = {128, (uint64_t)W, 1, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[4] = {256, (uint64_t)W * 256, (uint64_t)W * 256, (uint64_t)H * W * 256};
+  const uint32_t box[5] = {64, kRowPx + 2, 1, 1, 1};
+  return make_tmap(m, base, 5, dims, strides, box);
+}
+// ... and its output (B, 2H, 2W, 64) seen as (64 ch, column phase, W, 2H, B): box = 64 ch x 32 same-phase pixels
+bool tmap_convt_out(CUtensorMap* m, const void* base, int B, int H, int W) {
+  const uint64_t dims[5] = {64, 2, (uint64_t)W, (uint64_t)2 * H, (uint64_t)B};
+  const uint64_t strides[4] = {128, 256, (uint64_t)2 * W * 128, (uint64_t)2 * H * 2 * W * 128};
+  const uint32_t box[5] = {64, 1, 32, 1, 1};
+  return make_tmap(m, base, 5, dims, strides, box);
+}
+
+bool make_convt_rows(ConvTRowParams* p, const void* in, const void* wr, const float* bias, void* out, int B, int H, int W, int relu) {
+  if (!tmap_nhwc_row128(&p->tma_in, in, B, H, W)) return false;
+  if (!tmap_matrix(&p->tma_w, wr, 4 * 256, 128, 256)) return false;
+  if (!tmap_convt_out(&p->tma_out, out, B, H, W)) return false;
+  p->H = H; p->W = W;
+  p->strips_x = W / kRowPx;
+  p->strips_y = std::max(1, H / kCtPairsPerStrip);
+  p->bias = bias;
+  p->relu = relu;
+  return true;
+}
+
 // the same tensor viewed as (2C, W/2, 2, H/2, B): element (c + px*C, w2, py, h2, b) = in[b, 2*h2+py, 2*w2+px, c]
 bool tmap_nhwc_s2(CUtensorMap* m, const void* base, int B, int H, int W, int C) {
   const uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)B};
@@ -569,7 +596,21 @@ bool build_plan(s3od_ctx* c) {
   if (!add_conv3x3<128, 8>(c, "head.mh.c1", p1, R0, R0, 256, "head.mh.c1.w", 128,
                            conv_epi(mh1, nullptr, wptr<float>(c, "head.mh.c1.b"), nullptr, nullptr, 0, 128, R0, R0)))
     return false;
-  {
+  const bool rows_ok = (S % kRowPx == 0) && getenv("S3OD_NO_ROWCONV") == nullptr;
+  if (rows_ok && R0 % kRowPx == 0) {
+    // ConvTranspose2d k4 s2 p1 + ReLU on the row-streaming kernel, one launch per output-column phase
+    ConvTRowParams p{};
+    if (!make_convt_rows(&p, mh1, wptr<bf16>(c, "head.mh.up.wr"), wptr<float>(c, "head.mh.up.b"), feat0, mb, R0, R0, 1)) return false;
+    const int sms = c->num_sms;
+    for (int b = 0; b < 2; ++b) {
+      p.phase_b = b;
+      c->plan.emplace_back("head.mh.up.rows" + std::to_string(b), [=](int nb, int, float*, float*, cudaStream_t st) -> cudaError_t {
+        ConvTRowParams q = p;
+        q.num_strips = nb * q.strips_x * q.strips_y;
+        return launch_convt_rows(q, sms, st);
+      });
+    }
+  } else {
     CUtensorMap ta;
     if (!tmap_nhwc(&ta, mh1, mb, R0, R0, 128)) return false;
     for (int a = 0; a < 2; ++a)
@@ -581,7 +622,6 @@ bool build_plan(s3od_ctx* c) {
           return false;
       }
   }
-  const bool rows_ok = (S % kRowPx == 0) && getenv("S3OD_NO_ROWCONV") == nullptr;
   if (rows_ok) {
     if (!add_conv_rows<64, EpiConv>(c, "head.mh.c2", feat0, S, S, wptr<bf16>(c, "head.mh.c2.w"),
                                     conv_epi(feat, nullptr, wptr<float>(c, "head.mh.c2.b"), nullptr, nullptr, 1, 64, S, S)))
@@ -625,7 +665,7 @@ std::vector<std::string> required_tensors(const s3od_ctx* c) {
     r.push_back("head.rn" + std::to_string(j + 1) + ".w");
   }
   for (const char* s : {"head.rs0.w", "head.rs0.b", "head.rs1.w", "head.rs1.b", "head.rs3.w", "head.rs3.b", "head.mh.c1.w", "head.mh.c1.b",
-                        "head.mh.up.w", "head.mh.up.b", "head.mh.c2.w", "head.mh.c2.b", "head.mh.heads.w", "head.mh.heads.b",
+                        "head.mh.up.w", "head.mh.up.wr", "head.mh.up.b", "head.mh.c2.w", "head.mh.c2.b", "head.mh.heads.w", "head.mh.heads.b",
                         "head.mh.heads.w2", "head.mh.heads.b2", "head.cls.w1", "head.cls.b1", "head.cls.w2", "head.cls.b2"})
     r.push_back(s);
   for (int k = 1; k <= 4; ++k) {
@@ -920,6 +960,22 @@ int s3od_op_conv3x3_rows(const void* d_in, const void* d_w, const float* d_bias,
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   CK((launch_conv_rows<64, EpiConv>(p, sms, static_cast<cudaStream_t>(stream))));
+  return S3OD_OK;
+}
+
+int s3od_op_convt_rows(const void* d_in, const void* d_wr, const float* d_bias, void* d_out, int batch, int h, int w, int relu,
+                       s3od_stream stream) {
+  if (w % kRowPx != 0 || batch < 1 || h < 1) return fail(S3OD_ERR_ARG, "s3od_op_convt_rows needs w % 128 == 0");
+  ConvTRowParams p{};
+  if (!make_convt_rows(&p, d_in, d_wr, d_bias, d_out, batch, h, w, relu)) return S3OD_ERR_CUDA;
+  p.num_strips = batch * p.strips_x * p.strips_y;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  for (int b = 0; b < 2; ++b) {
+    p.phase_b = b;
+    CK(launch_convt_rows(p, sms, static_cast<cudaStream_t>(stream)));
+  }
   return S3OD_OK;
 }
 

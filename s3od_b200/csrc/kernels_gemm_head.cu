@@ -10,4 +10,17 @@ S3OD_INSTANTIATE_GEMM(32, A_CONV, EpiMask, 4)
 S3OD_INSTANTIATE_CONV_ROWS(64, EpiConv)
 S3OD_INSTANTIATE_CONV_ROWS(96, EpiMask)
 S3OD_INSTANTIATE_CONV_ROWS(32, EpiMask)
+
+cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(convt_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTRowCfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (p.num_strips <= 0) return cudaSuccess;
+  const int grid = p.num_strips < num_sms ? p.num_strips : num_sms;
+  convt_rows_kernel<0><<<grid, 192, ConvTRowCfg::kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
 }  // namespace s3od

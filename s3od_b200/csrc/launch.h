@@ -12,6 +12,8 @@ cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stre
 template <int NOUT, class Epi>
 cudaError_t launch_conv_rows(const RowConvParams<Epi>& p, int num_sms, cudaStream_t stream);
 
+cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t stream);
+
 extern long long* g_attn_trace;
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream);
 // x += dx (optional), tap = bf16(x) on patch rows (optional), y = LayerNorm(x) (optional)

@@ -72,6 +72,21 @@ def normalisation_lut() -> torch.Tensor:
 _CT_K = {0: (1, 3), 1: (0, 2)}
 
 
+# Row-streaming form of the same transposed conv: output column 2j+b takes kernel columns (kw, input column shift)
+# b=0: (1, 0), (3, -1);  b=1: (0, +1), (2, 0);  all four kernel rows are stacked (output row 2i - 1 + kh).
+_CT_ROW_KW = {0: (1, 3), 1: (0, 2)}
+
+
+def convt_rows_weights(wt: torch.Tensor) -> torch.Tensor:
+    """(Cin, Cout, 4, 4) -> [((b*2 + t)*4 + kh)*Cout + co, Cin]"""
+    blocks = []
+    for b in (0, 1):
+        for kw in _CT_ROW_KW[b]:
+            for kh in range(4):
+                blocks.append(wt[:, :, kh, kw].t())                                   # (Cout, Cin)
+    return torch.cat(blocks, dim=0)
+
+
 def pack_weights(sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int) -> Dict[str, torch.Tensor]:
     D, I, K = arch.hidden, arch.mlp, arch.num_outputs
     out: Dict[str, torch.Tensor] = {}
@@ -137,6 +152,7 @@ def pack_weights(sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int) -
             taps = [wt[:, :, kh, kw].t() for kh in _CT_K[a] for kw in _CT_K[b]]       # each (Cout, Cin); tap = r*2 + c
             phases.append(torch.cat(taps, dim=1))                                     # (Cout, 4*Cin)
     out["head.mh.up.w"] = _bf16(torch.cat(phases, dim=0))                             # row = (a*2+b)*Cout + co
+    out["head.mh.up.wr"] = _bf16(convt_rows_weights(wt))                              # row-streaming kernel (conv_rows.cuh)
     out["head.mh.up.b"] = _f32(sd[m + "upsample_2x.0.bias"])
     out["head.mh.c2.w"] = _bf16(conv_to_gemm(sd[m + "upsample_2x.2.weight"]))
     out["head.mh.c2.b"] = _f32(sd[m + "upsample_2x.2.bias"])

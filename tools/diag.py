@@ -171,6 +171,37 @@ def diag_convrows():
         print(f"conv_rows B=16 1024x1024 64->64: {ms:.3f} ms  {2 * B * h * w * 64 * 9 * 64 / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def diag_convt():
+    from s3od_b200.weights import convt_rows_weights
+    lib = load_library()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for (B, h, w) in [(1, 1, 128), (1, 3, 128), (2, 40, 256), (1, 70, 128)]:
+        x = torch.randn(B, h, w, 128, device="cuda", generator=g).bfloat16()
+        wt = (torch.randn(128, 64, 4, 4, device="cuda", generator=g) / 32).bfloat16()
+        bias = torch.randn(64, device="cuda", generator=g)
+        wr = convt_rows_weights(wt).contiguous()
+        y = torch.full((B, 2 * h, 2 * w, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        rc = lib.s3od_op_convt_rows(x.data_ptr(), wr.data_ptr(), bias.data_ptr(), y.data_ptr(), B, h, w, 1, _st())
+        torch.cuda.synchronize()
+        ref = F.relu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2, padding=1)).permute(0, 2, 3, 1)
+        r, m = rel(y, ref)
+        print(f"convt_rows B={B} {h}x{w} rc={rc} rel={r:.3e} maxabs={m:.3e} nan={int(torch.isnan(y.float()).sum())}", flush=True)
+    B, h, w = 16, 512, 512
+    x = torch.randn(B, h, w, 128, device="cuda").bfloat16()
+    wr = torch.randn(1024, 128, device="cuda").bfloat16()
+    y = torch.empty(B, 2 * h, 2 * w, 64, device="cuda", dtype=torch.bfloat16)
+    for _ in range(2):
+        lib.s3od_op_convt_rows(x.data_ptr(), wr.data_ptr(), None, y.data_ptr(), B, h, w, 1, _st())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        lib.s3od_op_convt_rows(x.data_ptr(), wr.data_ptr(), None, y.data_ptr(), B, h, w, 1, _st())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"convt_rows B=16 512x512 128->64 (both phases): {ms:.3f} ms  {2 * B * h * w * 128 * 16 * 64 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def diag_model():
     from s3od_b200.synth import synth_state_dict
     from oracle import model as om
@@ -258,6 +289,7 @@ def diag_step():
 
 FAMILIES["step"] = diag_step
 FAMILIES["convrows"] = diag_convrows
+FAMILIES["convt"] = diag_convt
 
 
 def diag_stall():
