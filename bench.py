@@ -202,10 +202,19 @@ def run_b200(args, rank, local_rank, world):
     flops_known = S == 1024 and args.model == "dinob"
     gflop_img = GFLOP_PER_IMAGE if args.model == "dinob" else 4958.1     # ViT-L, one mask
     achieved = FAMILY_GFLOP[dom] * images / fam_ms[dom] if flops_known else None
+    # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (same command, same micro-batch)
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01b_traffic.json")) as f:
+            t = json.load(f).get(dom)
+        if t and t["micro_batch"] == model.micro_batch and t["model"] == args.model and t["image_size"] == S:
+            traffic = t["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        traffic = None
     roofline = {"kernel": dom, "bound": "tensor", "achieved": round(achieved, 1) if achieved else None,
                 "peak": peaks["tflops_sustained"], "peak_source": peaks["source"] + " (sustained: timed inside a long step)",
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4) if achieved else None,
-                "traffic": None, "avg_launch_ms": round(fam_ms[dom] / fam_n[dom], 4),
+                "traffic": traffic, "avg_launch_ms": round(fam_ms[dom] / fam_n[dom], 4),
                 "whole_step_tflops": round(gflop_img * value / world / 1e3, 1) if S == 1024 else None,
                 "whole_step_frac": round(gflop_img * value / world / 1e3 / peaks["tflops_sustained"], 4) if S == 1024 else None}
     line = {
