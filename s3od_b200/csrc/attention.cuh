@@ -32,12 +32,14 @@
 // (tcgen05.ld / mul / tcgen05.st); otherwise P = exp2(S - m_ref) is at most 2^8 and nothing is rescaled.
 // The normaliser l follows the same reference, so the final O / l is the exact softmax average.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "types.h"
 
 namespace s3od {
 
-constexpr int kAttnThreads = 608;                 // 2 streams x 8 softmax warps, 2 MMA warps, TMA warp (104 registers each)
+constexpr int kAttnThreads = 608;                 // 2 streams x 8 softmax warps, 2 MMA warps, TMA warp (96 registers each)
 // kAttnTile = 128 query rows per CTA; kAttnKvTile = 96 keys per step (types.h): S (96) + two P buffers (2 x 48) + O (64)
 // = the 256 TMEM columns a CTA may hold at 2 CTAs/SM.
 static_assert(kAttnKvTile == 96 && kAttnTile == 128, "attention kernel is written for 128 x 96 steps");
@@ -81,10 +83,6 @@ S3OD_DEVICE float exp2_sel(float x, int e) {
   if (S3OD_ATTN_LAB & 2) return x;
   return (kPolyEvery > 0 && e % (kPolyEvery > 0 ? kPolyEvery : 1) == kPolyEvery - 1) ? exp2_poly(x) : fast_exp2(x);
 }
-
-#ifndef S3OD_ATTN_PINGPONG
-#define S3OD_ATTN_PINGPONG 0                          // 1: the exponential phases of the two streams alternate (named barriers)
-#endif
 
 // tcgen05.ld / st in the 16-lane shapes (layout measured with tools/lab/tmem_layout.cu): for repetition i, thread t holds
 //   .16x256b : r[4i+0..1] = (lane t/4,     columns 8i + 2(t%4) + {0,1}),  r[4i+2..3] = (lane t/4 + 8, same columns)
@@ -374,26 +372,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     float ma = -INFINITY, mb = -INFINITY, la = 0.0f, lb = 0.0f;      // exponent references and partial normalisers
     uint32_t ra[kAttnRegs];
     uint32_t w[kAttnRegs / 2];
-#if S3OD_ATTN_PINGPONG
-    // The exponential phases of the two streams alternate (named barriers 1 and 2).
-    const int bar_mine = 1 + sidx, bar_other = 2 - sidx;
-    if (sidx == 1) asm volatile("bar.arrive %0, 512;" ::"r"(bar_other) : "memory");     // stream 0 goes first
-#endif
 
-    for (int j = 0; j < T; ++j) {
+    // One key/value step.  The last step (ragged tail) runs a separate, masked copy of the code: with the choice made at
+    // run time inside one body the compiler predicates both variants into every step (one select per score, measured).
+    auto step = [&](const int j, auto masked_c) {
+      constexpr bool kMasked = decltype(masked_c)::value;
       const int nvalid = p.ntok - j * kAttnKvTile;      // columns >= nvalid are padding (last step only)
-      const bool masked = nvalid < kAttnKvTile;
       const int nvq = nvalid - q2;
       const uint32_t p_addr = s_addr + kAttnKvTile + (j & 1) * (kAttnKvTile / 2);
       mbar_wait(s_full, j & 1);
       if (warp == 0) S3OD_STAMP(0);                     // S_j seen
       tc_fence_after();
-      if (S3OD_ATTN_LAB & 16) {                         // timing probe: barriers only
-        mbar_arrive(s_empty);
-        if (j >= 2) mbar_wait(&p_empty[j & 1], ((j - 2) >> 1) & 1);
-        mbar_arrive(&p_full[j & 1]);
-        continue;
-      }
       tmem_ld_16x256_x8<0>(s_addr, ra);
       tmem_ld_16x256_x4<32>(s_addr + 64, ra);
       tmem_ld_wait16<0>(ra);
@@ -405,8 +394,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
 
       float mxa = ma, mxb = mb;
       if (!(S3OD_ATTN_LAB & 1) || j == 0) {
-        if (masked) row_max2<true>(ra, nvq, mxa, mxb);
-        else row_max2<false>(ra, nvq, mxa, mxb);
+        row_max2<kMasked>(ra, nvq, mxa, mxb);
         mxa = quad_max(mxa);
         mxb = quad_max(mxb);
       }
@@ -438,31 +426,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       tc_fence_after();
       ma = ma_new;
       mb = mb_new;
-#if S3OD_ATTN_PINGPONG
-      asm volatile("bar.sync %0, 512;" ::"r"(bar_mine) : "memory");   // my stream's turn on the SFU
-#endif
       if (warp == 0) S3OD_STAMP(2);
 
       // ---- P = exp2(S - m_ref) as packed bf16 into tensor memory, row sums
-      if (masked) {
-        softmax_reps<0, 8, true>(ra, ma, mb, nvq, w, la, lb);
-        tmem_st_16x128_x8<0>(p_addr, w);
-        softmax_reps<8, 12, true>(ra, ma, mb, nvq, w, la, lb);
-        tmem_st_16x128_x4<16>(p_addr + 32, w);
-      } else {
-        softmax_reps<0, 8, false>(ra, ma, mb, nvq, w, la, lb);
-        tmem_st_16x128_x8<0>(p_addr, w);
-        softmax_reps<8, 12, false>(ra, ma, mb, nvq, w, la, lb);
-        tmem_st_16x128_x4<16>(p_addr + 32, w);
-      }
-#if S3OD_ATTN_PINGPONG
-      if (!(sidx == 1 && j == T - 1)) asm volatile("bar.arrive %0, 512;" ::"r"(bar_other) : "memory");
-#endif
+      softmax_reps<0, 4, kMasked>(ra, ma, mb, nvq, w, la, lb);
+      tmem_st_16x128_x4<0>(p_addr, w);
+      softmax_reps<4, 8, kMasked>(ra, ma, mb, nvq, w, la, lb);
+      tmem_st_16x128_x4<8>(p_addr + 16, w);
+      softmax_reps<8, 12, kMasked>(ra, ma, mb, nvq, w, la, lb);
+      tmem_st_16x128_x4<16>(p_addr + 32, w);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[j & 1]);
       if (warp == 0) S3OD_STAMP(4);                     // P_j published
-    }
+    };
+    for (int j = 0; j + 1 < T; ++j) step(j, std::false_type{});
+    step(T - 1, std::true_type{});
 
     // ---- epilogue: O / l -> bf16 [B*ntok, heads*64]
     mbar_wait(&p_empty[(T - 1) & 1], ((T - 1) >> 1) & 1);
