@@ -97,6 +97,7 @@ def encoder_taps(sd, x, arch, stages=None) -> List[torch.Tensor]:
     """hidden_states[taps][:, 5:]  - un-normed residual streams (model.py:72-84)."""
     gh, gw = x.shape[-2] // arch.patch, x.shape[-1] // arch.patch
     cos, sin = rope_tables(gh, gw, arch.head_dim, arch.rope_theta)
+    cos, sin = cos.to(x.device), sin.to(x.device)          # the tests also run this restatement with torch on a GPU
     pre = _enc_prefix(sd)
     h = embed(sd, x)
     if stages is not None:

@@ -306,3 +306,47 @@ def test_config3_shape_2048_source(predictors):
     patches = br.model.stage("patches", torch.bfloat16, (gp * gp, 768)).float().cpu()
     got = patches.reshape(gp, gp, 3, 16, 16).permute(2, 0, 3, 1, 4).reshape(3, 1024, 1024)
     assert torch.equal(got, torch.from_numpy(x[0]).bfloat16().float())
+
+
+def test_fullsize_1024_matches_oracle_on_device(models, vitb_sd, capsys):
+    """Full configs[1] resolution: the CUDA path against the oracle's fp32 arithmetic run with torch on the SAME GPU
+    (TF32 off), two noise images.  Also prints the eager timings (fp32 and bf16 autocast) of that torch path - the
+    'PyTorch on B200' figure quoted in DESIGN.md; informational, not a benchmark."""
+    import time
+    S = 1024
+    x = torch.from_numpy(np.concatenate([opp.preprocess(synth_noise_image(S, S, seed=900 + i), S)[0] for i in range(2)], 0))
+    m = models(S, max_batch=2)
+    out = m(x.cuda())
+    torch.cuda.synchronize()
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd_dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in vitb_sd.items()}
+        xd = x.cuda()
+        with torch.no_grad():
+            ref = om.forward(sd_dev, xd, VITB)
+            torch.cuda.synchronize()
+            timings = {}
+            for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16 autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+                with ctx:
+                    om.forward(sd_dev, xd, VITB)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(2):
+                        om.forward(sd_dev, xd, VITB)
+                    torch.cuda.synchronize()
+                    timings[name] = 2 * 2 / (time.perf_counter() - t0)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    t0 = time.perf_counter()
+    for _ in range(4):
+        m(xd)
+    torch.cuda.synchronize()
+    ours = 4 * 2 / (time.perf_counter() - t0)
+    with capsys.disabled():
+        print(f"\n[eager torch on this GPU, model forward only, batch 2 @1024] fp32 {timings['fp32']:.2f} img/s, "
+              f"bf16 autocast {timings['bf16 autocast']:.2f} img/s; this library (same call, batch 2) {ours:.1f} img/s")
+    _assert_masks(out["pred_masks"].cpu(), ref["pred_masks"].cpu(), max_abs=5e-2)
+    assert float((out["pred_iou"].cpu() - ref["pred_iou"].cpu()).abs().max()) <= 3e-2
+    assert torch.equal(out["pred_iou"].cpu().argmax(1), ref["pred_iou"].cpu().argmax(1))
