@@ -122,14 +122,14 @@ __global__ void fill_prefix_kernel(float* __restrict__ x, const float* __restric
 
 // ------------------------------------------------------------------------------------------------------------------
 // Residual add + LayerNorm (eps 1e-5), one warp per token row, the row lives in registers (fp32):
-//   if (dx)  x += dx            the LayerScale'd branch output the previous GEMM left in `dx` (HF:440-441, 447-448);
+//   if (dx)  x += dx            the LayerScale'd branch output the previous GEMM left in `dx` (bf16; HF:440-441, 447-448);
 //                               keeping the read-modify-write of the fp32 residual stream out of the GEMM epilogue makes
 //                               it a pure streaming pass with full memory-level parallelism
 //   if (tap) tap = bf16(x)      patch rows only: hidden_states[k][:, 5:] for the DPT head (model.py:72-84)
 //   if (y)   y = LN(x) in bf16  two-pass mean / variance (HF:411,416,433,445): the A operand of the next GEMM
 // ------------------------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const float* __restrict__ dx,
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ dx,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ tap, int M,
                                                         int ntok, float eps) {
@@ -142,11 +142,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
 #pragma unroll
   for (int i = 0; i < V; ++i) v[i] = xr[lane + 32 * i];
   if (dx != nullptr) {
-    const float4* dr = reinterpret_cast<const float4*>(dx + static_cast<size_t>(row) * D);
+    const uint2* dr = reinterpret_cast<const uint2*>(dx + static_cast<size_t>(row) * D);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const float4 d = dr[lane + 32 * i];
-      v[i].x += d.x; v[i].y += d.y; v[i].z += d.z; v[i].w += d.w;
+      const uint2 d = dr[lane + 32 * i];
+      v[i].x += bf16_lo(d.x); v[i].y += bf16_hi(d.x); v[i].z += bf16_lo(d.y); v[i].w += bf16_hi(d.y);
       xr[lane + 32 * i] = v[i];
     }
   }

@@ -377,7 +377,7 @@ bool build_plan(s3od_ctx* c) {
   bool ok = true;
   ok = ok && alloc_act(c, "patches", static_cast<size_t>(c->max_batch) * P * 768 * 2);
   ok = ok && alloc_act(c, "x", MT * D * 4);
-  ok = ok && alloc_act(c, "dx", MT * D * 4);
+  ok = ok && alloc_act(c, "dx", MT * D * 2);
   ok = ok && alloc_act(c, "xn", MT * D * 2);
   ok = ok && alloc_act(c, "ctx", MT * D * 2);
   ok = ok && alloc_act(c, "q", MT * D * 2);
@@ -410,7 +410,7 @@ bool build_plan(s3od_ctx* c) {
   if (!ok) return false;
 
   float* x = aptr<float>(c, "x");
-  float* dx = aptr<float>(c, "dx");
+  bf16* dx = aptr<bf16>(c, "dx");
   bf16* xn = aptr<bf16>(c, "xn");
   bf16* actx = aptr<bf16>(c, "ctx");
   bf16* hmid = aptr<bf16>(c, "hmid");
@@ -450,7 +450,7 @@ bool build_plan(s3od_ctx* c) {
       bf16* tap = nullptr;
       for (int j = 0; j < 4; ++j)
         if (c->taps[j] == l) tap = aptr<bf16>(c, "tap" + std::to_string(j));
-      const float* dprev = l > 0 ? dx : nullptr;
+      const bf16* dprev = l > 0 ? dx : nullptr;
       c->plan.emplace_back(pre + "ln1", [=](int nb, int, float*, float*, cudaStream_t st) {
         return launch_layernorm(x, dprev, ln1w, ln1b, xn, tap, nb * ntok, ntok, D, 1e-5f, st);
       });

@@ -418,12 +418,14 @@ struct EpiQKV {
   }
 };
 
-// ---- o_proj / down_proj: dx = lambda * (acc + bias) in fp32 (LayerScale, HF:342-343).  The residual add x += dx is
-//      fused into the following layernorm_kernel, so this epilogue only streams stores.
+// ---- o_proj / down_proj: dx = lambda * (acc + bias) (LayerScale, HF:342-343), stored as bf16.  The residual add
+//      x += dx is fused into the following layernorm_kernel (fp32 residual stream), so this epilogue only streams stores.
+//      bf16 for the increment: its rounding (2^-9 relative to dx) is below what the bf16 LayerNorm output already carries,
+//      and it takes 100 MB per GEMM off both this store and the LayerNorm's load (o_proj was HBM-bound on the fp32 store).
 struct EpiResidual {
   static constexpr bool kPrefetch = false;
   struct Params {
-    float* dx;            // [B * ntok, D] fp32
+    __nv_bfloat16* dx;    // [B * ntok, D] bf16
     const float* bias;    // [D]
     const float* lambda;  // [D]
     int ntok, D;
@@ -431,22 +433,23 @@ struct EpiResidual {
   template <int NCOLS>
   static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
     const int t0 = ri.t - stg.lane;
-    float* ob = e.dx + static_cast<size_t>(ri.b) * e.ntok * e.D + n0 + stg.seg() * 4;
+    __nv_bfloat16* ob = e.dx + static_cast<size_t>(ri.b) * e.ntok * e.D + n0 + stg.seg() * 8;
 #pragma unroll 1
-    for (int c = 0; c < NCOLS; c += 16) {
-      float v[16];
-      tmem_ld_f32x16(taddr + c, v);
-      uint32_t w[16];
+    for (int c = 0; c < NCOLS; c += 32) {
+      float v[32];
+      tmem_ld_f32x32(taddr + c, v);
       const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0 + c);
       const float4* l4 = reinterpret_cast<const float4*>(e.lambda + n0 + c);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         const float4 bv = __ldg(b4 + i), lv = __ldg(l4 + i);
-        w[4 * i + 0] = __float_as_uint((v[4 * i + 0] + bv.x) * lv.x);
-        w[4 * i + 1] = __float_as_uint((v[4 * i + 1] + bv.y) * lv.y);
-        w[4 * i + 2] = __float_as_uint((v[4 * i + 2] + bv.z) * lv.z);
-        w[4 * i + 3] = __float_as_uint((v[4 * i + 3] + bv.w) * lv.w);
+        v[4 * i + 0] = (v[4 * i + 0] + bv.x) * lv.x;
+        v[4 * i + 1] = (v[4 * i + 1] + bv.y) * lv.y;
+        v[4 * i + 2] = (v[4 * i + 2] + bv.z) * lv.z;
+        v[4 * i + 3] = (v[4 * i + 3] + bv.w) * lv.w;
       }
+      uint32_t w[16];
+      pack_bf16x32(v, w);
       stg.write(w);
       __syncwarp();
 #pragma unroll

@@ -31,7 +31,7 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
   return cudaGetLastError();
 }
 
-cudaError_t launch_layernorm(float* x, const float* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,
+cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,
                              int ntok, int D, float eps, cudaStream_t stream) {
   const int rows_per_block = 8;
   const int grid = (M + rows_per_block - 1) / rows_per_block;

@@ -17,7 +17,7 @@ cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t
 extern long long* g_attn_trace;
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream);
 // x += dx (optional), tap = bf16(x) on patch rows (optional), y = LayerNorm(x) (optional)
-cudaError_t launch_layernorm(float* x, const float* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,
+cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,
                              int ntok, int D, float eps, cudaStream_t stream);
 cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, __nv_bfloat16* patches, int S, int B,
                               cudaStream_t stream);
