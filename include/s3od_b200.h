@@ -96,6 +96,19 @@ void s3od_destroy(s3od_ctx* ctx);
 const char* s3od_last_error(void);
 const char* s3od_version(void);
 
+/* ---- visualisation on device-resident results
+ * s3od_vis_composite replaces s3od.visualizer.visualize_removal (src/s3od/visualizer.py:8-24):
+ *     out (h, w, 3) u8 = trunc(mask * image + (1 - mask) * background), float32 arithmetic in numpy's order (bit-identical)
+ * s3od_vis_mask_grid replaces visualize_all_masks (visualizer.py:27-48): grid of ceil(K/4) x min(K,4) cells, cell k =
+ *     trunc(mask_k * image); out is (ceil(K/4)*h, min(K,4)*w, 3) u8; cells beyond K are NOT written (caller zero-fills)
+ * s3od_mask_pair_counts: for every pair i < j of the K <= 4 masks, counts[2p] = |m_i > 0.5 and m_j > 0.5|,
+ *     counts[2p+1] = |m_i > 0.5 or m_j > 0.5|  (demo/app.py:38-42 compute_mask_iou; the IoU ratio and the is_ambiguous
+ *     decision of demo/app.py:45-56 are taken on the host from these exact integers) */
+int s3od_vis_composite(const uint8_t* d_image, const float* d_mask, uint8_t* d_out, int h, int w, int bg_r, int bg_g, int bg_b,
+                       s3od_stream stream);
+int s3od_vis_mask_grid(const uint8_t* d_image, const float* d_masks, int num_masks, uint8_t* d_out, int h, int w, s3od_stream stream);
+int s3od_mask_pair_counts(const float* d_masks, int num_masks, int h, int w, unsigned long long* d_counts, s3od_stream stream);
+
 /* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
 /* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */
 int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream);

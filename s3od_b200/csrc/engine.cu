@@ -979,4 +979,31 @@ int s3od_op_convt_rows(const void* d_in, const void* d_wr, const float* d_bias, 
   return S3OD_OK;
 }
 
+// ---- visualisation: device-resident composites of visualizer.py and the pair counts behind is_ambiguous
+int s3od_vis_composite(const uint8_t* d_image, const float* d_mask, uint8_t* d_out, int h, int w, int bg_r, int bg_g, int bg_b,
+                       s3od_stream stream) {
+  if (d_image == nullptr || d_mask == nullptr || d_out == nullptr || h < 0 || w < 0) return fail(S3OD_ERR_ARG, "bad argument for s3od_vis_composite");
+  CK(launch_composite(d_image, d_mask, d_out, static_cast<size_t>(h) * w, static_cast<float>(bg_r & 255), static_cast<float>(bg_g & 255),
+                      static_cast<float>(bg_b & 255), static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
+int s3od_vis_mask_grid(const uint8_t* d_image, const float* d_masks, int num_masks, uint8_t* d_out, int h, int w, s3od_stream stream) {
+  if (d_image == nullptr || d_masks == nullptr || d_out == nullptr || num_masks < 1 || h < 0 || w < 0)
+    return fail(S3OD_ERR_ARG, "bad argument for s3od_vis_mask_grid");
+  const int gw = num_masks < 4 ? num_masks : 4;
+  CK(launch_mask_grid(d_image, d_masks, d_out, num_masks, h, w, gw, static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
+int s3od_mask_pair_counts(const float* d_masks, int num_masks, int h, int w, unsigned long long* d_counts, s3od_stream stream) {
+  if (d_masks == nullptr || d_counts == nullptr || num_masks < 1 || num_masks > 4 || h < 0 || w < 0)
+    return fail(S3OD_ERR_ARG, "s3od_mask_pair_counts takes 1..4 masks");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(launch_mask_pair_counts(d_masks, num_masks, static_cast<size_t>(h) * w, d_counts, sms, static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
 }  // extern "C"

@@ -1,6 +1,7 @@
 // Attention and bandwidth-bound kernel launchers.
 #include "attention.cuh"
 #include "elementwise.cuh"
+#include "visualize.cuh"
 #include "launch.h"
 
 #include <cstdlib>
@@ -101,6 +102,35 @@ cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, 
     else
       postprocess_kernel<1><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
   }
+  return cudaGetLastError();
+}
+
+
+cudaError_t launch_composite(const uint8_t* img, const float* mask, uint8_t* out, size_t npix, float br, float bg, float bb,
+                             cudaStream_t stream) {
+  if (npix == 0) return cudaSuccess;
+  const size_t threads = (npix + 3) / 4;
+  composite_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(img, mask, out, npix, br, bg, bb);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mask_grid(const uint8_t* img, const float* masks, uint8_t* out, int K, int H, int W, int grid_w, cudaStream_t stream) {
+  const size_t npix = static_cast<size_t>(H) * W;
+  if (npix == 0 || K == 0) return cudaSuccess;
+  const size_t threads = (npix + 3) / 4;
+  mask_grid_kernel<<<dim3(static_cast<unsigned>((threads + 255) / 256), K), 256, 0, stream>>>(img, masks, out, H, W, grid_w);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mask_pair_counts(const float* masks, int K, size_t npix, unsigned long long* counts, int num_sms, cudaStream_t stream) {
+  const int npairs = K * (K - 1) / 2;
+  if (npairs == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 2 * npairs, stream);
+  if (e != cudaSuccess) return e;
+  size_t blocks = (npix / 4 + 255) / 256;
+  if (blocks > static_cast<size_t>(8 * num_sms)) blocks = 8 * num_sms;
+  if (blocks < 1) blocks = 1;
+  mask_pair_counts_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(masks, K, npix, counts);
   return cudaGetLastError();
 }
 

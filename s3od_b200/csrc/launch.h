@@ -30,4 +30,10 @@ cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, cons
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
                                int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, cudaStream_t stream);
 
+// visualisation (visualize.cuh)
+cudaError_t launch_composite(const uint8_t* img, const float* mask, uint8_t* out, size_t npix, float br, float bg, float bb,
+                             cudaStream_t stream);
+cudaError_t launch_mask_grid(const uint8_t* img, const float* masks, uint8_t* out, int K, int H, int W, int grid_w, cudaStream_t stream);
+cudaError_t launch_mask_pair_counts(const float* masks, int K, size_t npix, unsigned long long* counts, int num_sms, cudaStream_t stream);
+
 }  // namespace s3od

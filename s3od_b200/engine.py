@@ -69,6 +69,9 @@ def load_library() -> ctypes.CDLL:
     lib.s3od_op_layernorm.argtypes = [vp, vp, vp, vp, ci, ci, cf, vp]
     lib.s3od_op_attention.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     lib.s3od_op_conv3x3.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    lib.s3od_vis_composite.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.s3od_vis_mask_grid.argtypes = [vp, vp, ci, vp, ci, ci, vp]
+    lib.s3od_mask_pair_counts.argtypes = [vp, ci, ci, ci, vp, vp]
     lib.s3od_op_convt_rows.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
     lib.s3od_op_conv3x3_rows.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
     _LIB = lib

@@ -90,3 +90,20 @@ def test_full_size_golden_subsample(vitb_sd, golden_dir):
     np.testing.assert_allclose(res["pred_iou"][None], g["pred_iou"], atol=2e-4)
     np.testing.assert_allclose(res["pred_masks"][None][:, :, 5::16, 3::16], g["pred_masks_sub"], atol=2e-3)
     np.testing.assert_allclose(res["all_masks"][:, 5::16, 3::16], g["all_masks_sub"], atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["vis_36x52_k3", "vis_31x45_k3", "vis_20x24_k1", "vis_16x16_k4"])
+def test_visualizer_oracle_matches_reference_golden(golden_dir, name):
+    """oracle/visualizer.py against the outputs of the unmodified reference (oracle/make_golden_vis.py): bit-exact."""
+    from oracle import visualizer as ov
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    image, masks = g["image"], g["masks"]
+    assert np.array_equal(ov.visualize_removal(image, masks[0]), g["green"])
+    assert np.array_equal(ov.visualize_removal(image, masks[0], (255, 255, 255)), g["white"])
+    assert np.array_equal(ov.visualize_removal(image, masks[0], (13, 77, 201)), g["odd"])
+    assert np.array_equal(ov.visualize_all_masks(image, masks), g["grid"])
+    assert bool(ov.is_ambiguous(masks)) == bool(g["ambiguous"])
+    assert bool(ov.is_ambiguous(masks, 0.95)) == bool(g["ambiguous_095"])
+    if len(masks) >= 2:
+        ious = [ov.compute_mask_iou(masks[i], masks[j]) for i in range(len(masks)) for j in range(i + 1, len(masks))]
+        assert np.array_equal(np.array(ious, np.float64), g["ious"])
