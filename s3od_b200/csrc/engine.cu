@@ -269,7 +269,7 @@ bool add_linear(s3od_ctx* c, const std::string& label, const void* a, uint64_t a
   }
   GemmParams<Epi> p{};
   if (!tmap_matrix(&p.tma_a, a, a_rows_total, Kdim, kBM)) return false;
-  if (!tmap_matrix(&p.tma_b, bw, N, Kdim, BN)) return false;
+  if (!tmap_matrix(&p.tma_b, bw, N, Kdim, b_box_rows<BN>())) return false;
   p.n_tiles = N / BN;
   p.num_k_blocks = Kdim / 64;
   p.b_row_offset = 0;
@@ -302,7 +302,7 @@ bool add_conv(s3od_ctx* c, const std::string& label, const CUtensorMap& tma_a, c
   }
   GemmParams<Epi> p{};
   p.tma_a = tma_a;
-  if (!tmap_matrix(&p.tma_b, bw, b_rows_total, Kdim, BN)) return false;
+  if (!tmap_matrix(&p.tma_b, bw, b_rows_total, Kdim, b_box_rows<BN>())) return false;
   p.n_tiles = N / BN;
   p.num_k_blocks = Kdim / 64;
   p.b_row_offset = b_row_offset;
@@ -892,6 +892,12 @@ int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N,
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (N % 256 == 0) {                               // the 256-wide tile configuration every encoder GEMM uses (CTA-pair kernel)
+    if (!tmap_matrix(&p.tma_b, d_b, N, K, b_box_rows<256>())) return S3OD_ERR_CUDA;
+    p.n_tiles = N / 256;
+    CK((launch_gemm<256, A_LINEAR, EpiStoreF32, 8>(p, sms, static_cast<cudaStream_t>(stream))));
+    return S3OD_OK;
+  }
   CK((launch_gemm<128, A_LINEAR, EpiStoreF32, 8>(p, sms, static_cast<cudaStream_t>(stream))));
   return S3OD_OK;
 }
@@ -931,7 +937,7 @@ int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void
   if (cin % 64 != 0 || cout % 256 != 0) return fail(S3OD_ERR_ARG, "s3od_op_conv3x3 needs cin % 64 == 0 and cout % 256 == 0");
   GemmParams<EpiConv> p{};
   if (!tmap_nhwc(&p.tma_a, d_in, batch, h, w, cin)) return S3OD_ERR_CUDA;
-  if (!tmap_matrix(&p.tma_b, d_w, cout, 9 * cin, 256)) return S3OD_ERR_CUDA;
+  if (!tmap_matrix(&p.tma_b, d_w, cout, 9 * cin, b_box_rows<256>())) return S3OD_ERR_CUDA;
   p.geom = geom_3x3(h, w, cin);
   p.m_tiles = batch * p.geom.tiles_h * p.geom.tiles_w;
   p.n_tiles = cout / 256;

@@ -6,4 +6,5 @@ S3OD_INSTANTIATE_GEMM(256, A_LINEAR, EpiQKV, 8)
 S3OD_INSTANTIATE_GEMM(256, A_LINEAR, EpiResidual, 8)
 S3OD_INSTANTIATE_GEMM(256, A_LINEAR, EpiGelu, 8)
 S3OD_INSTANTIATE_GEMM(128, A_LINEAR, EpiStoreF32, 8)
+S3OD_INSTANTIATE_GEMM(256, A_LINEAR, EpiStoreF32, 8)
 }  // namespace s3od

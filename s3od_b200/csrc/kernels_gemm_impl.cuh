@@ -1,11 +1,30 @@
 // Definition of launch_gemm; included by the kernels_gemm_*.cu translation units that instantiate it.
 #pragma once
+#include "gemm_tc2.cuh"
 #include "launch.h"
 
 namespace s3od {
 
 template <int BN, int AMODE, class Epi, int EPI_WARPS>
 cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stream) {
+  const int total = p.m_tiles * p.n_tiles;
+  if (total <= 0) return cudaSuccess;
+  if constexpr (BN == 256) {
+    if (use_pair_kernel()) {
+      using Cfg2 = Gemm2Cfg<BN, EPI_WARPS>;
+      auto kern2 = gemm_tc2_kernel<BN, AMODE, Epi, EPI_WARPS>;
+      static bool configured2 = false;
+      if (!configured2) {
+        cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured2 = true;
+      }
+      const int items = ((p.m_tiles + 1) / 2) * p.n_tiles;            // (M-tile pair, N tile) work items
+      const int pairs = items < num_sms / 2 ? items : num_sms / 2;
+      kern2<<<2 * pairs, 128 + 32 * EPI_WARPS, Cfg2::kSmemBytes, stream>>>(p);
+      return cudaGetLastError();
+    }
+  }
   using Cfg = GemmCfg<BN, EPI_WARPS>;
   auto kern = gemm_tc_kernel<BN, AMODE, Epi, EPI_WARPS>;
   static bool configured = false;
@@ -14,8 +33,6 @@ cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stre
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
-  if (total <= 0) return cudaSuccess;
   const int grid = total < num_sms ? total : num_sms;
   kern<<<grid, 128 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(p);
   return cudaGetLastError();
