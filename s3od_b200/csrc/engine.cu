@@ -886,7 +886,7 @@ int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N,
   if (N % 128 != 0 || K % 64 != 0 || M < 1) return fail(S3OD_ERR_ARG, "s3od_op_gemm_f32 needs N % 128 == 0 and K % 64 == 0");
   GemmParams<EpiStoreF32> p{};
   if (!tmap_matrix(&p.tma_a, d_a, M, K, kBM)) return S3OD_ERR_CUDA;
-  if (!tmap_matrix(&p.tma_b, d_b, N, K, 128)) return S3OD_ERR_CUDA;
+  if (!tmap_matrix(&p.tma_b, d_b, N, K, b_box_rows<128>())) return S3OD_ERR_CUDA;
   p.M = M; p.m_tiles = (M + kBM - 1) / kBM; p.n_tiles = N / 128; p.num_k_blocks = K / 64;
   p.epi = EpiStoreF32::Params{d_c, N};
   int dev = 0, sms = 148;

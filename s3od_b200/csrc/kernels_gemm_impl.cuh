@@ -9,7 +9,7 @@ template <int BN, int AMODE, class Epi, int EPI_WARPS>
 cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stream) {
   const int total = p.m_tiles * p.n_tiles;
   if (total <= 0) return cudaSuccess;
-  if constexpr (BN == 256) {
+  if constexpr (BN == 256 || BN == 128) {
     if (use_pair_kernel()) {
       using Cfg2 = Gemm2Cfg<BN, EPI_WARPS>;
       auto kern2 = gemm_tc2_kernel<BN, AMODE, Epi, EPI_WARPS>;

@@ -8,7 +8,7 @@
 
 namespace s3od {
 
-// BN = 256 tiles run on the CTA-pair kernel (gemm_tc2.cuh); S3OD_PAIR=0 selects the one-CTA kernel (A/B measurements).
+// BN = 256 / 128 tiles run on the CTA-pair kernel (gemm_tc2.cuh); S3OD_PAIR=0 selects the one-CTA kernel (A/B measurements).
 // The B tensor map's box must match: each CTA of a pair fetches a 128-row half of the 256-row tile.
 inline bool use_pair_kernel() {
   static const bool on = [] {
@@ -18,7 +18,7 @@ inline bool use_pair_kernel() {
   return on;
 }
 template <int BN>
-inline int b_box_rows() { return (BN == 256 && use_pair_kernel()) ? BN / 2 : BN; }
+inline int b_box_rows() { return ((BN == 256 || BN == 128) && use_pair_kernel()) ? BN / 2 : BN; }
 
 template <int BN, int AMODE, class Epi, int EPI_WARPS>
 cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stream);
