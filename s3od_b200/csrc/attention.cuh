@@ -182,10 +182,11 @@ S3OD_DEVICE void softmax_reps(const uint32_t (&r)[kAttnRegs], float ma, float mb
                               float& sb) {
 #pragma unroll
   for (int i = I0; i < I1; ++i) {
-    float e0 = exp2_sel(__uint_as_float(r[4 * i + 0]) - ma, 4 * i + 0);
-    float e1 = exp2_sel(__uint_as_float(r[4 * i + 1]) - ma, 4 * i + 1);
-    float e2 = exp2_sel(__uint_as_float(r[4 * i + 2]) - mb, 4 * i + 2);
-    float e3 = exp2_sel(__uint_as_float(r[4 * i + 3]) - mb, 4 * i + 3);
+    const float ma_ = (S3OD_ATTN_LAB & 64) ? 0.0f : ma, mb_ = (S3OD_ATTN_LAB & 64) ? 0.0f : mb;     // lab: no subtraction
+    float e0 = exp2_sel(__uint_as_float(r[4 * i + 0]) - ma_, 4 * i + 0);
+    float e1 = exp2_sel(__uint_as_float(r[4 * i + 1]) - ma_, 4 * i + 1);
+    float e2 = exp2_sel(__uint_as_float(r[4 * i + 2]) - mb_, 4 * i + 2);
+    float e3 = exp2_sel(__uint_as_float(r[4 * i + 3]) - mb_, 4 * i + 3);
     if (kMasked) {
       const bool v0 = 8 * i < nvq, v1 = 8 * i + 1 < nvq;
       e0 = v0 ? e0 : 0.0f;
@@ -193,8 +194,13 @@ S3OD_DEVICE void softmax_reps(const uint32_t (&r)[kAttnRegs], float ma, float mb
       e2 = v0 ? e2 : 0.0f;
       e3 = v1 ? e3 : 0.0f;
     }
-    sa += e0 + e1;
-    sb += e2 + e3;
+    if (!(S3OD_ATTN_LAB & 32)) {                        // lab: no row sums
+      sa += e0 + e1;
+      sb += e2 + e3;
+    } else if (i == 0) {
+      sa += e0;
+      sb += e2;
+    }
     w[2 * i] = pack_bf16x2(e0, e1);
     w[2 * i + 1] = pack_bf16x2(e2, e3);
   }
@@ -235,8 +241,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   const int bh = blockIdx.y;
   const int T = p.kv_tiles;
   const bool two_streams = (2 * blockIdx.x + 1) * kAttnTile < p.ntok;      // the last CTA of an odd tile count runs one stream
-  long long* trace = (p.trace != nullptr && blockIdx.x == 2 && blockIdx.y == p.trace_bh) ? p.trace : nullptr;
+  [[maybe_unused]] long long* trace = (p.trace != nullptr && blockIdx.x == 2 && blockIdx.y == p.trace_bh) ? p.trace : nullptr;
+#ifdef S3OD_ATTN_TRACE_BUILD      // tools/lab/attn_lab.cu: per-step clock64() stamps of one CTA
 #define S3OD_STAMP(slot) do { if (trace != nullptr && lane == 0 && j < 64) trace[j * 8 + (slot)] = clock64(); } while (0)
+#else
+#define S3OD_STAMP(slot) do { } while (0)
+#endif
 
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&p.tma_q);

@@ -1,5 +1,6 @@
 // Lab harness (not part of the product): times attention_kernel variants selected with -D macros.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -lcuda -o attn_lab tools/lab/attn_lab.cu [-DS3OD_ATTN_...]
+#define S3OD_ATTN_TRACE_BUILD
 #include "../../s3od_b200/csrc/attention.cuh"
 #include <cstdio>
 #include <cstdlib>

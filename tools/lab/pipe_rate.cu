@@ -26,6 +26,10 @@ __global__ void pipe_kernel(float* out, long long* clk, float seed, int iters) {
 #pragma unroll
           for (int q = 0; q < 6; ++q) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[(i + 1 + q) & 15]) : "f"(c0), "f"(c1)); }
         if (MODE == 7) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(c0), "f"(c1)); asm volatile("max.f32 %0, %0, %1;" : "+f"(a[(i + 8) & 15]) : "f"(c0)); }
+        if (MODE == 9) { unsigned short h = (unsigned short)__float_as_uint(a[i]); asm volatile("ex2.approx.f16 %0, %0;" : "+h"(h)); a[i] = __uint_as_float((unsigned)h | 0x3c000000u); }
+        if (MODE == 10) { unsigned u = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u)); a[i] = __uint_as_float(u & 0x3bff3bffu); }
+        if (MODE == 11) { unsigned short h = (unsigned short)__float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16 %0, %0;" : "+h"(h)); a[i] = __uint_as_float((unsigned)h | 0x3c000000u); }
+        if (MODE == 12) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
         if (MODE == 8) asm volatile("fma.rn.f32 %0, %0, %1, 0f3F800000;" : "+f"(a[i]) : "f"(c0));
       }
     }
@@ -52,6 +56,10 @@ void run(const char* name, int per_iter) {
 }
 int main() {
   run<0>("MUFU.EX2", 1);
+  run<9>("MUFU.EX2.F16 (+LOP)", 2);
+  run<10>("ex2.f16x2 (2 elts, +LOP)", 2);
+  run<11>("MUFU.EX2.BF16 (+LOP)", 2);
+  run<12>("MUFU.TANH", 1);
   run<1>("FADD", 1);
   run<2>("FFMA 3-reg", 1);
   run<8>("FFMA imm", 1);
