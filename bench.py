@@ -217,6 +217,13 @@ def run_b200(args, rank, local_rank, world):
                 "traffic": traffic, "avg_launch_ms": round(fam_ms[dom] / fam_n[dom], 4),
                 "whole_step_tflops": round(gflop_img * value / world / 1e3, 1) if S == 1024 else None,
                 "whole_step_frac": round(gflop_img * value / world / 1e3 / peaks["tflops_sustained"], 4) if S == 1024 else None}
+    if dom == "attention" and achieved and clocks and clocks.get("sm_mhz"):
+        # the attention kernel is bound by the SFU (one MUFU.EX2 per score = per 256 tensor FLOP at head_dim 64; 16 per clock
+        # and SM at every precision, tools/lab/pipe_rate.cu) - reported next to the tensor fraction the contract asks for
+        exps_per_s = achieved * 1e12 / 256.0
+        sfu_peak = 16.0 * torch.cuda.get_device_properties(dev).multi_processor_count * clocks["sm_mhz"] * 1e6
+        roofline["sfu"] = {"achieved_gexp_s": round(exps_per_s / 1e9, 1), "peak_gexp_s": round(sfu_peak / 1e9, 1),
+                           "frac": round(exps_per_s / sfu_peak, 4), "note": "16 MUFU.EX2 / clk / SM at the sampled SM clock"}
     line = {
         "metric": METRIC.replace("dinob", args.model), "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

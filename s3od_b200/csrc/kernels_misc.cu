@@ -28,7 +28,8 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
   static const char* tb = getenv("S3OD_ATTN_TRACE_BH");
   q.trace_bh = tb != nullptr ? atoi(tb) : 0;
   g_attn_trace = trace_buf;
-  attention_kernel<<<dim3((q_tiles + 1) / 2, bh), kAttnThreads, kAttnSmemBytes, stream>>>(q);   // two query tiles per CTA
+  q.bh_total = bh;
+  attention_kernel<<<((q_tiles + 1) / 2) * bh, kAttnThreads, kAttnSmemBytes, stream>>>(q);   // two query tiles per CTA, 1-D grid
   return cudaGetLastError();
 }
 

@@ -38,6 +38,7 @@ struct AttnParams {
   CUtensorMap tma_v;    // (64 d, ntok, B*H)  box (64, kAttnKvTile, 1); consumed as an MN-major B operand
   __nv_bfloat16* out;   // [B * ntok, heads * 64]
   int ntok, heads, kv_tiles;   // kv_tiles = ceil(ntok / kAttnKvTile)
+  int bh_total;                // images * heads of this launch
   int trace_bh;         // debug: which blockIdx.y is traced
   long long* trace;     // debug: per-tile clock64() stamps of CTA (5, 0) (8 slots per tile: 0-4 softmax warp, 5-7 MMA thread)
 };

@@ -29,12 +29,12 @@ int main(int argc, char** argv) {
   fill<<<(n + 255) / 256, 256>>>(q, n, 1, 0.18f); fill<<<(n + 255) / 256, 256>>>(k, n, 2, 1.0f); fill<<<(n + 255) / 256, 256>>>(v, n, 3, 1.0f);
   AttnParams p{};
   if (!tmap(&p.tma_q, q, ntok, BH, kAttnTile) || !tmap(&p.tma_k, k, ntok, BH, kAttnKvTile) || !tmap(&p.tma_v, v, ntok, BH, kAttnKvTile)) { printf("tmap failed\n"); return 1; }
-  p.out = o; p.ntok = ntok; p.heads = H; p.kv_tiles = (ntok + kAttnKvTile - 1) / kAttnKvTile;
+  p.bh_total = (int)BH; p.out = o; p.ntok = ntok; p.heads = H; p.kv_tiles = (ntok + kAttnKvTile - 1) / kAttnKvTile;
   long long* trace; cudaMalloc(&trace, 64 * 8 * 8); cudaMemset(trace, 0, 64 * 8 * 8);
   p.trace = trace; p.trace_bh = 40;
   cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  auto run = [&] { attention_kernel<<<dim3(((ntok + 127) / 128 + 1) / 2, BH), kAttnThreads, kAttnSmemBytes>>>(p); };
+  auto run = [&] { attention_kernel<<<(((ntok + 127) / 128 + 1) / 2) * BH, kAttnThreads, kAttnSmemBytes>>>(p); };
   for (int i = 0; i < 5; ++i) run();
   cudaEventRecord(e0);
   const int it = 20;
