@@ -96,6 +96,21 @@ void s3od_destroy(s3od_ctx* ctx);
 const char* s3od_last_error(void);
 const char* s3od_version(void);
 
+/* ---- saliency metrics on the device: the reductions of EvaluationMetrics.step
+ * (synth_sod/model_training/metrics.py:213-421).  d_pred, d_mask: (h, w) fp32.
+ * s3od_metrics_stats fills (layout of struct SodStats, csrc/metrics.cuh; all 8-byte fields):
+ *     double abs_err, sum_p, sum_y, fg_p, fg_p2, bg_q, bg_q2;  uint64 n_fg, sum_mx, sum_my;  uint64 hist_cnt[256];  double hist_y[256]
+ *   hist bin = number of the 255 thresholds (d_thresholds, ascending) that are <= pred: replaces the 255-pass `_eval_pr`
+ *   (metrics.py:316-327); the fg / bg moments feed `_S_object` (:329-344), n_fg / sum_mx / sum_my the centroid (:358-378).
+ * s3od_metrics_region fills struct SodRegion { double sp[4], sm[4], spp[4], smm[4], spm[4]; }: moments of pred and of the
+ *   binarised mask in the four quadrants split at (x_split, y_split), for `_ssim` (metrics.py:405-421). */
+int s3od_metrics_stats(const float* d_pred, const float* d_mask, int h, int w, const float* d_thresholds, void* d_stats, size_t stats_bytes,
+                       s3od_stream stream);
+int s3od_metrics_region(const float* d_pred, const float* d_mask, int h, int w, int x_split, int y_split, void* d_region,
+                        size_t region_bytes, s3od_stream stream);
+size_t s3od_metrics_stats_bytes(void);
+size_t s3od_metrics_region_bytes(void);
+
 /* ---- visualisation on device-resident results
  * s3od_vis_composite replaces s3od.visualizer.visualize_removal (src/s3od/visualizer.py:8-24):
  *     out (h, w, 3) u8 = trunc(mask * image + (1 - mask) * background), float32 arithmetic in numpy's order (bit-identical)

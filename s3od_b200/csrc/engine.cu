@@ -985,6 +985,33 @@ int s3od_op_convt_rows(const void* d_in, const void* d_wr, const float* d_bias, 
   return S3OD_OK;
 }
 
+// ---- saliency metrics: device reductions behind EvaluationMetrics.step (metrics.py:213-421)
+int s3od_metrics_stats(const float* d_pred, const float* d_mask, int h, int w, const float* d_thresholds, void* d_stats, size_t stats_bytes,
+                       s3od_stream stream) {
+  if (d_pred == nullptr || d_mask == nullptr || d_thresholds == nullptr || d_stats == nullptr || h < 0 || w < 0 ||
+      stats_bytes < sod_stats_bytes())
+    return fail(S3OD_ERR_ARG, "bad argument for s3od_metrics_stats (stats buffer needs s3od_metrics_stats_bytes() bytes)");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(launch_sod_stats(d_pred, d_mask, h, w, d_thresholds, d_stats, sms, static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
+int s3od_metrics_region(const float* d_pred, const float* d_mask, int h, int w, int x_split, int y_split, void* d_region,
+                        size_t region_bytes, s3od_stream stream) {
+  if (d_pred == nullptr || d_mask == nullptr || d_region == nullptr || h < 0 || w < 0 || region_bytes < sod_region_bytes())
+    return fail(S3OD_ERR_ARG, "bad argument for s3od_metrics_region");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(launch_sod_region(d_pred, d_mask, h, w, x_split, y_split, d_region, sms, static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
+size_t s3od_metrics_stats_bytes(void) { return sod_stats_bytes(); }
+size_t s3od_metrics_region_bytes(void) { return sod_region_bytes(); }
+
 // ---- visualisation: device-resident composites of visualizer.py and the pair counts behind is_ambiguous
 int s3od_vis_composite(const uint8_t* d_image, const float* d_mask, uint8_t* d_out, int h, int w, int bg_r, int bg_g, int bg_b,
                        s3od_stream stream) {

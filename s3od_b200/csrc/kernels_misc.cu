@@ -2,6 +2,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "visualize.cuh"
+#include "metrics.cuh"
 #include "launch.h"
 
 #include <cstdlib>
@@ -106,6 +107,33 @@ cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, 
   return cudaGetLastError();
 }
 
+
+cudaError_t launch_sod_stats(const float* pred, const float* mask, int H, int W, const float* thresholds, void* stats, int num_sms,
+                             cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(SodStats), stream);
+  if (e != cudaSuccess) return e;
+  const size_t n = static_cast<size_t>(H) * W;
+  if (n == 0) return cudaSuccess;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > static_cast<size_t>(8 * num_sms)) blocks = 8 * num_sms;
+  sod_stats_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pred, mask, H, W, thresholds, static_cast<SodStats*>(stats));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sod_region(const float* pred, const float* mask, int H, int W, int X, int Y, void* region, int num_sms,
+                              cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(region, 0, sizeof(SodRegion), stream);
+  if (e != cudaSuccess) return e;
+  const size_t n = static_cast<size_t>(H) * W;
+  if (n == 0) return cudaSuccess;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > static_cast<size_t>(8 * num_sms)) blocks = 8 * num_sms;
+  sod_region_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pred, mask, H, W, X, Y, static_cast<SodRegion*>(region));
+  return cudaGetLastError();
+}
+
+size_t sod_stats_bytes() { return sizeof(SodStats); }
+size_t sod_region_bytes() { return sizeof(SodRegion); }
 
 cudaError_t launch_composite(const uint8_t* img, const float* mask, uint8_t* out, size_t npix, float br, float bg, float bb,
                              cudaStream_t stream) {

@@ -44,6 +44,13 @@ cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, cons
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
                                int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, cudaStream_t stream);
 
+// saliency metrics (metrics.cuh)
+cudaError_t launch_sod_stats(const float* pred, const float* mask, int H, int W, const float* thresholds, void* stats, int num_sms,
+                             cudaStream_t stream);
+cudaError_t launch_sod_region(const float* pred, const float* mask, int H, int W, int X, int Y, void* region, int num_sms,
+                              cudaStream_t stream);
+size_t sod_stats_bytes();
+size_t sod_region_bytes();
 // visualisation (visualize.cuh)
 cudaError_t launch_composite(const uint8_t* img, const float* mask, uint8_t* out, size_t npix, float br, float bg, float bb,
                              cudaStream_t stream);

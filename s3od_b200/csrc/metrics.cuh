@@ -1,0 +1,113 @@
+// Saliency metrics on the device: the reductions behind the torch half of the reference's
+// EvaluationMetrics (synth_sod/model_training/metrics.py:213-421) - MAE, the 255-threshold precision / recall sweep and
+// the S-measure moments.  The reference launches ~770 torch kernels per image for the sweep (`_eval_pr` loops over the
+// thresholds); here one pass builds a 256-bin histogram of the prediction (bin = number of thresholds <= p), weighted by
+// the ground truth, from which every (tp, count) pair is a suffix sum taken on the host.
+// Sums are accumulated in double (block partials) and merged with atomics, so they are exact to ~1e-15 relative whatever
+// the order; integer quantities (counts, centroid sums) are exact.
+#pragma once
+#include "common.cuh"
+
+namespace s3od {
+
+struct SodStats {                       // written by sod_stats_kernel (zero-initialised by the launcher)
+  double abs_err, sum_p, sum_y;         // sum |p - y|, sum p, sum y
+  double fg_p, fg_p2, bg_q, bg_q2;      // over m == 1: sum p, sum p^2;  over m == 0: sum (1-p), sum (1-p)^2   (m = y >= 0.5)
+  unsigned long long n_fg, sum_mx, sum_my;   // |m|, sum m * x, sum m * y   (centroid, metrics.py:358-378)
+  unsigned long long hist_cnt[256];     // pixels per bin
+  double hist_y[256];                   // sum of y per bin
+};
+
+struct SodRegion {                      // per quadrant (LT, RT, LB, RB): moments of p and m for _ssim (metrics.py:405-421)
+  double sp[4], sm[4], spp[4], smm[4], spm[4];
+};
+
+S3OD_DEVICE double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+S3OD_DEVICE unsigned long long warp_sum_u(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) sod_stats_kernel(const float* __restrict__ pred, const float* __restrict__ mask, int H, int W,
+                                                        const float* __restrict__ thresholds, SodStats* __restrict__ out) {
+  __shared__ float th[256];
+  __shared__ unsigned int h_cnt[256];
+  __shared__ float h_y[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    th[i] = i < 255 ? thresholds[i] : 3.0e38f;
+    h_cnt[i] = 0;
+    h_y[i] = 0.0f;
+  }
+  __syncthreads();
+  double a_err = 0, s_p = 0, s_y = 0, fp = 0, fp2 = 0, bq = 0, bq2 = 0;
+  unsigned long long nfg = 0, smx = 0, smy = 0;
+  const size_t n = static_cast<size_t>(H) * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float p = pred[i], y = mask[i];
+    a_err += fabsf(p - y);
+    s_p += p;
+    s_y += y;
+    int lo = 0, hi = 255;                               // number of thresholds <= p (thresholds ascending)
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int mid = (lo + hi) >> 1;
+      if (th[mid] <= p) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&h_cnt[lo], 1u);
+    if (y != 0.0f) atomicAdd(&h_y[lo], y);
+    if (y >= 0.5f) {
+      const float pf = p;
+      fp += pf;
+      fp2 += static_cast<double>(pf) * pf;
+      nfg += 1;
+      smx += static_cast<unsigned long long>(i % W);
+      smy += static_cast<unsigned long long>(i / W);
+    } else {
+      const float q = 1.0f - p;
+      bq += q;
+      bq2 += static_cast<double>(q) * q;
+    }
+  }
+  a_err = warp_sum_d(a_err); s_p = warp_sum_d(s_p); s_y = warp_sum_d(s_y);
+  fp = warp_sum_d(fp); fp2 = warp_sum_d(fp2); bq = warp_sum_d(bq); bq2 = warp_sum_d(bq2);
+  nfg = warp_sum_u(nfg); smx = warp_sum_u(smx); smy = warp_sum_u(smy);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out->abs_err, a_err); atomicAdd(&out->sum_p, s_p); atomicAdd(&out->sum_y, s_y);
+    atomicAdd(&out->fg_p, fp); atomicAdd(&out->fg_p2, fp2); atomicAdd(&out->bg_q, bq); atomicAdd(&out->bg_q2, bq2);
+    atomicAdd(&out->n_fg, nfg); atomicAdd(&out->sum_mx, smx); atomicAdd(&out->sum_my, smy);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    if (h_cnt[i] != 0) atomicAdd(&out->hist_cnt[i], static_cast<unsigned long long>(h_cnt[i]));
+    if (h_y[i] != 0.0f) atomicAdd(&out->hist_y[i], static_cast<double>(h_y[i]));
+  }
+}
+
+// quadrants split at column X and row Y (the centroid of the binarised ground truth)
+__global__ void __launch_bounds__(256) sod_region_kernel(const float* __restrict__ pred, const float* __restrict__ mask, int H, int W,
+                                                         int X, int Y, SodRegion* __restrict__ out) {
+  double sp[4] = {0, 0, 0, 0}, sm[4] = {0, 0, 0, 0}, spp[4] = {0, 0, 0, 0}, smm[4] = {0, 0, 0, 0}, spm[4] = {0, 0, 0, 0};
+  const size_t n = static_cast<size_t>(H) * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W), y = static_cast<int>(i / W);
+    const int q = (y >= Y ? 2 : 0) + (x >= X ? 1 : 0);
+    const double p = pred[i], m = mask[i] >= 0.5f ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k == q) { sp[k] += p; sm[k] += m; spp[k] += p * p; smm[k] += m * m; spm[k] += p * m; }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double a = warp_sum_d(sp[k]), b = warp_sum_d(sm[k]), c = warp_sum_d(spp[k]), d = warp_sum_d(smm[k]), e = warp_sum_d(spm[k]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&out->sp[k], a); atomicAdd(&out->sm[k], b); atomicAdd(&out->spp[k], c); atomicAdd(&out->smm[k], d); atomicAdd(&out->spm[k], e);
+    }
+  }
+}
+
+}  // namespace s3od

@@ -69,6 +69,10 @@ def load_library() -> ctypes.CDLL:
     lib.s3od_op_layernorm.argtypes = [vp, vp, vp, vp, ci, ci, cf, vp]
     lib.s3od_op_attention.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     lib.s3od_op_conv3x3.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    lib.s3od_metrics_stats.argtypes = [vp, vp, ci, ci, vp, vp, ctypes.c_size_t, vp]
+    lib.s3od_metrics_region.argtypes = [vp, vp, ci, ci, ci, ci, vp, ctypes.c_size_t, vp]
+    lib.s3od_metrics_stats_bytes.restype = ctypes.c_size_t
+    lib.s3od_metrics_region_bytes.restype = ctypes.c_size_t
     lib.s3od_vis_composite.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
     lib.s3od_vis_mask_grid.argtypes = [vp, vp, ci, vp, ci, ci, vp]
     lib.s3od_mask_pair_counts.argtypes = [vp, ci, ci, ci, vp, vp]

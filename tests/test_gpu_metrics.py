@@ -1,0 +1,60 @@
+"""SURVEY 8f rank 4 on the GPU: s3od_b200.metrics.EvaluationMetrics against the reference's golden values
+(tests/golden/metrics.npz, written by oracle/make_golden_metrics.py from the unmodified reference) and against the CPU oracle
+at 1024 x 1024.  Tolerance: 2e-6 absolute - the reference sums in float32, the device path in double."""
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-6
+
+
+def test_metrics_match_reference_golden(golden_dir):
+    from s3od_b200.metrics import EvaluationMetrics
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    em = EvaluationMetrics("cuda:0")
+    sm = EvaluationMetrics("cuda:0", sm_only=True)
+    for i, name in enumerate(g["names"]):
+        pred, mask = torch.from_numpy(g[name + "_pred"]), torch.from_numpy(g[name + "_mask"])
+        keep = mask.clone()
+        em.step(pred, mask)
+        sm.step(pred, mask)
+        assert torch.equal(mask, keep)                                  # the caller's mask is left alone
+        got = np.array([em.metrics[k][i] for k in ("mae", "max_f", "avg_f", "s_score")])
+        assert np.abs(got - g[name + "_vals"]).max() <= TOL, (name, got, g[name + "_vals"])
+        assert abs(sm.metrics["s_score"][i] - g[name + "_vals"][3]) <= TOL
+    out = em.compute_metrics()
+    assert set(out) == {"MAE", "MaxF", "AvgF", "Sm"} and set(sm.compute_metrics()) == {"Sm"}
+    vals = np.stack([g[n + "_vals"] for n in g["names"]])
+    assert abs(out["MAE"] - vals[:, 0].mean()) <= TOL and abs(out["Sm"] - vals[:, 3].mean()) <= TOL
+    em.reset()
+    assert em.metrics["mae"] == []
+
+
+def test_metrics_fullsize_matches_oracle(capsys):
+    from s3od_b200.metrics import EvaluationMetrics
+    g = torch.Generator().manual_seed(11)
+    H = W = 1024
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    mask = (((yy - 420) / 300) ** 2 + ((xx - 560) / 260) ** 2 < 1).float()
+    pred = (0.75 * mask + 0.3 * torch.rand(H, W, generator=g)).clamp(0, 1)
+    ref = om.step(pred, mask)
+    em = EvaluationMetrics("cuda:0")
+    d_pred, d_mask = pred.cuda(), mask.cuda()
+    em.step(d_pred, d_mask)
+    got = {k: em.metrics[k][0] for k in ("mae", "max_f", "avg_f", "s_score")}
+    for k in got:
+        assert abs(got[k] - ref[k]) <= 2e-5, (k, got[k], ref[k])      # float32 sums over 1 M pixels in the oracle
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        em.step(d_pred, d_mask)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 20
+    with capsys.disabled():
+        print(f"\n[metrics 1024x1024] step (2 device passes + 2 small D2H): {dt * 1e3:.2f} ms per image")

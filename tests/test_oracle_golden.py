@@ -107,3 +107,13 @@ def test_visualizer_oracle_matches_reference_golden(golden_dir, name):
     if len(masks) >= 2:
         ious = [ov.compute_mask_iou(masks[i], masks[j]) for i in range(len(masks)) for j in range(i + 1, len(masks))]
         assert np.array_equal(np.array(ious, np.float64), g["ious"])
+
+
+def test_metrics_oracle_matches_reference_golden(golden_dir):
+    """oracle/metrics.py against the values of the unmodified reference (oracle/make_golden_metrics.py)."""
+    from oracle import metrics as omt
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    for name in g["names"]:
+        r = omt.step(torch.from_numpy(g[name + "_pred"]), torch.from_numpy(g[name + "_mask"]))
+        got = np.array([r["mae"], r["max_f"], r["avg_f"], r["s_score"]])
+        assert np.abs(got - g[name + "_vals"]).max() <= 1e-7, name
