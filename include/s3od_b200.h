@@ -92,6 +92,10 @@ int s3od_profile_read(s3od_ctx* ctx, char* buf, size_t buf_bytes);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 long long s3od_launch_count(s3od_ctx* ctx);
 
+/* 1 when the preprocess kernel evaluates the normalisation as fma(v, a, b) (optional tensor "pre.affine", accepted only if it
+ * reproduces every entry of "pre.lut" bit for bit), 0 when it looks the values up in "pre.lut"; < 0 on error. */
+int s3od_preprocess_mode(s3od_ctx* ctx);
+
 void s3od_destroy(s3od_ctx* ctx);
 const char* s3od_last_error(void);
 const char* s3od_version(void);

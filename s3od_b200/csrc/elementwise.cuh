@@ -32,64 +32,94 @@ S3OD_DEVICE int resized_px(const ImageDesc& d, int y, int x, int c) {
   return (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
 }
 
+// Block = 16 canvas rows x 128 canvas columns = 8 patches of one patch row; thread = 8 consecutive pixels of one row
+// (24 contiguous source bytes in the copy mode, 2 x 48 in the exact-2x mode).  The normalised values are staged in shared
+// memory in patch order, so the block writes ONE contiguous run of 8 x 1536 bytes with 128-bit stores (writing the 16-byte
+// pieces straight from the pixel threads scattered every warp store over 16 patches: 2.5 TB/s).
+constexpr int kPrePatchBytes = 1536 + 32;     // +32: the 16-byte pieces of the 4 patches of a quarter warp land in different banks
+
+// AFFINE: the normalisation is evaluated as bf16(fma(v, a_c, b_c)) instead of the table look-up (24 shared loads with
+// random bank conflicts per thread); the host only selects it after checking that it reproduces all 768 table entries.
+struct PreAffine { float a[3], b[3]; };
+
+template <bool AFFINE>
 __global__ void __launch_bounds__(256) preprocess_kernel(const ImageDesc* __restrict__ descs, const __nv_bfloat16* __restrict__ lut,
-                                                         __nv_bfloat16* __restrict__ patches, int S) {
-  __shared__ __nv_bfloat16 s_lut[768];
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
-  __syncthreads();
-  const int b = blockIdx.y;
+                                                         PreAffine aff, __nv_bfloat16* __restrict__ patches, int S) {
+  __shared__ __nv_bfloat16 s_lut[AFFINE ? 8 : 768];
+  __shared__ __align__(16) uint8_t s_out[8 * kPrePatchBytes];
+  if constexpr (!AFFINE) {
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+  }
+  const int b = blockIdx.z;
   const ImageDesc d = descs[b];
   const int g = S >> 4;
-  const int x8_per_row = S >> 3;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= S * x8_per_row) return;
-  const int Y = idx / x8_per_row;
-  const int X = (idx % x8_per_row) << 3;
-  const int ry = Y - d.pad_h;
-  const bool row_in = ry >= 0 && ry < d.new_h;
-  const int rx0 = X - d.pad_w;
-  const size_t prow = static_cast<size_t>(b) * g * g + (Y >> 4) * g + (X >> 4);
-  __nv_bfloat16* dst = patches + prow * 768 + (Y & 15) * 16 + (X & 15);
-  uint8_t px[8][3];
-  // fast paths: all 8 pixels inside the resized image and the source row segment is 8- / 16-byte aligned
-  const bool inside = row_in && rx0 >= 0 && rx0 + 8 <= d.new_w;
-  if (inside && d.mode == 0 && ((d.w * 3) & 7) == 0 && (rx0 & 7) == 0) {
-    // 8 pixels = 24 contiguous bytes
-    const uint2* sp = reinterpret_cast<const uint2*>(d.src + (static_cast<size_t>(ry) * d.w + rx0) * 3);
-    uint2 v[3] = {__ldg(sp), __ldg(sp + 1), __ldg(sp + 2)};
-    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(v);
+  const int py = blockIdx.y, px0 = blockIdx.x * 8;
+  const int row = threadIdx.x >> 4, x8 = threadIdx.x & 15;
+  const int Y = py * 16 + row;
+  const int X = px0 * 16 + x8 * 8;
+  if (X < S) {
+    const int ry = Y - d.pad_h;
+    const bool row_in = ry >= 0 && ry < d.new_h;
+    const int rx0 = X - d.pad_w;
+    uint8_t px[8][3];
+    // fast paths: all 8 pixels inside the resized image and the source row segment is 8- / 16-byte aligned
+    const bool inside = row_in && rx0 >= 0 && rx0 + 8 <= d.new_w;
+    if (inside && d.mode == 0 && ((d.w * 3) & 7) == 0 && (rx0 & 7) == 0) {
+      // 8 pixels = 24 contiguous bytes
+      const uint2* sp = reinterpret_cast<const uint2*>(d.src + (static_cast<size_t>(ry) * d.w + rx0) * 3);
+      uint2 v[3] = {__ldg(sp), __ldg(sp + 1), __ldg(sp + 2)};
+      const uint8_t* bytes = reinterpret_cast<const uint8_t*>(v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) px[i][c] = bytes[i * 3 + c];
-  } else if (inside && d.mode == 1 && ((d.w * 3) & 15) == 0 && (rx0 & 7) == 0) {
-    // exact 2x: (a + b + c + d + 2) >> 2 over 2 source rows x 16 source pixels = 2 x 48 contiguous bytes
-    const uint4* r0 = reinterpret_cast<const uint4*>(d.src + (static_cast<size_t>(2 * ry) * d.w + 2 * rx0) * 3);
-    const uint4* r1 = reinterpret_cast<const uint4*>(d.src + (static_cast<size_t>(2 * ry + 1) * d.w + 2 * rx0) * 3);
-    uint4 a[3] = {__ldg(r0), __ldg(r0 + 1), __ldg(r0 + 2)};
-    uint4 bq[3] = {__ldg(r1), __ldg(r1 + 1), __ldg(r1 + 2)};
-    const uint8_t* ba = reinterpret_cast<const uint8_t*>(a);
-    const uint8_t* bb = reinterpret_cast<const uint8_t*>(bq);
+        for (int c = 0; c < 3; ++c) px[i][c] = bytes[i * 3 + c];
+    } else if (inside && d.mode == 1 && ((d.w * 3) & 15) == 0 && (rx0 & 7) == 0) {
+      // exact 2x: (a + b + c + d + 2) >> 2 over 2 source rows x 16 source pixels = 2 x 48 contiguous bytes
+      const uint4* r0 = reinterpret_cast<const uint4*>(d.src + (static_cast<size_t>(2 * ry) * d.w + 2 * rx0) * 3);
+      const uint4* r1 = reinterpret_cast<const uint4*>(d.src + (static_cast<size_t>(2 * ry + 1) * d.w + 2 * rx0) * 3);
+      uint4 a[3] = {__ldg(r0), __ldg(r0 + 1), __ldg(r0 + 2)};
+      uint4 bq[3] = {__ldg(r1), __ldg(r1 + 1), __ldg(r1 + 2)};
+      const uint8_t* ba = reinterpret_cast<const uint8_t*>(a);
+      const uint8_t* bb = reinterpret_cast<const uint8_t*>(bq);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        px[i][c] = static_cast<uint8_t>((ba[i * 6 + c] + ba[i * 6 + 3 + c] + bb[i * 6 + c] + bb[i * 6 + 3 + c] + 2) >> 2);
-  } else {
+        for (int c = 0; c < 3; ++c)
+          px[i][c] = static_cast<uint8_t>((ba[i * 6 + c] + ba[i * 6 + 3 + c] + bb[i * 6 + c] + bb[i * 6 + 3 + c] + 2) >> 2);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rx = rx0 + i;
-      const bool in = row_in && rx >= 0 && rx < d.new_w;
+      for (int i = 0; i < 8; ++i) {
+        const int rx = rx0 + i;
+        const bool in = row_in && rx >= 0 && rx < d.new_w;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) px[i][c] = in ? static_cast<uint8_t>(resized_px(d, ry, rx, c)) : 0;
+        for (int c = 0; c < 3; ++c) px[i][c] = in ? static_cast<uint8_t>(resized_px(d, ry, rx, c)) : 0;
+      }
+    }
+    uint8_t* so = s_out + (x8 >> 1) * kPrePatchBytes + row * 32 + (x8 & 1) * 16;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if constexpr (AFFINE) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)          // 0x4B000000 | v is the float 2^23 + v: integer -> float on the FMA pipe
+          f[i] = fmaf(__uint_as_float(0x4B000000u | px[i][c]) - 8388608.0f, aff.a[c], aff.b[c]);
+        *reinterpret_cast<uint4*>(so + c * 512) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      } else {
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = s_lut[c * 256 + px[i][c]];
+        *reinterpret_cast<uint4*>(so + c * 512) = *reinterpret_cast<const uint4*>(v);
+      }
     }
   }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    __align__(16) __nv_bfloat16 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = s_lut[c * 256 + px[i][c]];
-    *reinterpret_cast<uint4*>(dst + c * 256) = *reinterpret_cast<const uint4*>(v);
+  __syncthreads();
+  const int npatch = min(8, g - px0);
+  uint4* dst = reinterpret_cast<uint4*>(patches + (static_cast<size_t>(b) * g * g + static_cast<size_t>(py) * g + px0) * 768);
+  for (int j = threadIdx.x; j < npatch * 96; j += 256) {
+    const int p = j / 96, q = j - p * 96;
+    dst[j] = *reinterpret_cast<const uint4*>(s_out + p * kPrePatchBytes + q * 16);
   }
 }
 
@@ -333,6 +363,10 @@ __global__ void __launch_bounds__(256) iou_head_kernel(const float* __restrict__
 // ATen does), sigmoid of the IoU logits, first-max argmax, alpha = trunc(best * 255), RGBA = [R, G, B, alpha].
 // Thread = one output pixel; grid = (ceil(W/128), H, B)... x is the fastest dimension for coalesced stores.
 // ------------------------------------------------------------------------------------------------------------------
+S3OD_DEVICE void cp_async_f32(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+S3OD_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 S3OD_DEVICE float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 S3OD_DEVICE float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
@@ -406,6 +440,137 @@ __global__ void __launch_bounds__(128) postprocess4_kernel(const PostDesc* __res
   o.z = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | a[2];
   o.w = (s2 >> 8) | a[3];
   reinterpret_cast<uint4*>(d.rgba)[(static_cast<size_t>(oy) * d.W + ox) >> 2] = o;
+}
+
+// Tile path (every image width a multiple of 4, at most 3 taps per axis = up-sampling or identity, the bench configs):
+// block = 128 threads = kPostTileW output columns x kPostTileRows output rows of one image, one mask plane at a time.
+//   1. the block loads the input region of its tile (rows ystart[oy0] .. ystart[oy1-1]+ky-1, columns likewise) with
+//      coalesced reads and applies the sigmoid ONCE per input pixel into shared memory (the per-pixel kernels evaluated
+//      it for every tap: 12-27 times per output pixel, which made them instruction / SFU bound at < 1 TB/s);
+//   2. each thread walks down its 4 output columns: the horizontally filtered values of three consecutive input rows
+//      roll through registers (a new input row costs 12 shared loads per 4 pixels), the vertical filter is 3 FMAs;
+//   3. 128-bit streaming stores of the mask plane; the best plane goes last and also emits the RGBA pixels.
+// Same summation order as the per-pixel kernels (taps left to right, rows top to bottom; zero-weight taps add +0).
+// Shared column c lives at c + (c >> 5): adjacent threads read columns 4*scale apart, the skew spreads them over banks.
+constexpr int kPostTileRows = 16;
+constexpr int kPostTileW = 512;
+__host__ __device__ __forceinline__ int post_skew(int c) { return c + (c >> 5); }
+
+template <int K>
+__global__ void __launch_bounds__(128, 6) postprocess_tile_kernel(const PostDesc* __restrict__ descs, const float* __restrict__ mask_logits,
+                                                               const float* __restrict__ iou_logits, float* __restrict__ ious,
+                                                               int* __restrict__ best_idx, int S, int rows_max, int pitch) {
+  extern __shared__ float s_sig[];                 // [rows_max][pitch]
+  const int b = blockIdx.z;
+  const PostDesc d = descs[b];
+  const int oy0 = blockIdx.y * kPostTileRows;
+  const int ox0 = blockIdx.x * kPostTileW;
+  if (oy0 >= d.H || ox0 >= d.W) return;            // block-uniform
+  float sc[K];
+  int best = 0;
+  float bestv = -1.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    sc[k] = sigmoidf_acc(iou_logits[b * K + k]);
+    if (sc[k] > bestv) { bestv = sc[k]; best = k; }      // strict >: first maximum wins, like numpy argmax
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) ious[b * K + k] = sc[k];
+    best_idx[b] = best;
+  }
+  const int oy1 = min(oy0 + kPostTileRows, d.H);
+  const int ox1 = min(ox0 + kPostTileW, d.W);
+  const int row0 = d.ystart[oy0] + d.pad_h;
+  const int nrows = min(d.ystart[oy1 - 1] + d.pad_h + d.ky - 1, S - 1) - row0 + 1;
+  const int col0 = d.xstart[ox0] + d.pad_w;
+  const int ncols = min(d.xstart[ox1 - 1] + d.pad_w + d.kx - 1, S - 1) - col0 + 1;
+  if (nrows > rows_max || post_skew(ncols - 1) >= pitch) __trap();     // the host sized the tile from the same tables
+  // this thread's 4 output columns: shared-memory tap positions and weights (3 taps, zero-padded)
+  const int ox = ox0 + threadIdx.x * 4;
+  const bool active = ox < d.W;
+  int tap[4][3];
+  float xw[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int xs = active ? d.xstart[ox + i] + d.pad_w - col0 : 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      tap[i][t] = post_skew(min(xs + t, ncols - 1));
+      xw[i][t] = (active && t < d.kx) ? d.xw[static_cast<size_t>(ox + i) * d.kx + t] : 0.0f;
+    }
+  }
+  if (active) {                                     // source RGB rows of the tile towards L2 while the planes are processed
+    for (int r = oy0 + (threadIdx.x & 15); r < oy1; r += 16)
+      for (int seg = threadIdx.x >> 4; seg * 128 < (ox1 - ox0) * 3; seg += 8)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.src + (static_cast<size_t>(r) * d.W + ox0) * 3 + seg * 128));
+  }
+  auto hrow = [&](int r, float (&h)[4]) {
+    const float* sr = s_sig + min(r, nrows - 1) * pitch;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = (sr[tap[i][0]] * xw[i][0] + sr[tap[i][1]] * xw[i][1]) + sr[tap[i][2]] * xw[i][2];
+  };
+#pragma unroll 1
+  for (int kk = 0; kk < K; ++kk) {
+    const int k = (best + 1 + kk) % K;             // the best plane last: its values are the alpha channel
+    const float* plane = mask_logits + (static_cast<size_t>(b) * K + k) * S * S + static_cast<size_t>(row0) * S + col0;
+    if (kk > 0) __syncthreads();
+    // all loads of the region in flight at once (4-byte cp.async: the region starts at an arbitrary column), then the
+    // sigmoid in place on the elements this thread fetched itself
+    for (int c = threadIdx.x; c < ncols; c += 128) {
+      float* sp = s_sig + post_skew(c);
+      const float* gp = plane + c;
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) cp_async_f32(sp + r * pitch, gp + static_cast<size_t>(r) * S);
+    }
+    cp_async_wait_all();
+    for (int c = threadIdx.x; c < ncols; c += 128) {
+      float* sp = s_sig + post_skew(c);
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) sp[r * pitch] = sigmoidf_fast(sp[r * pitch]);
+    }
+    __syncthreads();
+    if (!active) continue;
+    float h0[4], h1[4], h2[4];
+    int cur = 0;                                   // input row (relative to row0) held in h0
+    hrow(0, h0); hrow(1, h1); hrow(2, h2);
+    float* op = d.all_masks + (static_cast<size_t>(k) * d.H + oy0) * d.W + ox;
+    const bool last = kk == K - 1;
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(d.src + (static_cast<size_t>(oy0) * d.W + ox) * 3);
+    const int sp_step = d.W * 3 / 4;                 // W % 4 == 0
+    uint32_t n0 = 0, n1 = 0, n2 = 0;                 // source pixels of the NEXT row (loaded one row ahead)
+    if (last) { n0 = __ldg(sp); n1 = __ldg(sp + 1); n2 = __ldg(sp + 2); }
+#pragma unroll 1
+    for (int oy = oy0; oy < oy1; ++oy, op += d.W) {
+      const int ys = d.ystart[oy] + d.pad_h - row0;
+#pragma unroll 1
+      while (cur < ys) {                           // block-uniform
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h0[i] = h1[i]; h1[i] = h2[i]; }
+        hrow(cur + 3, h2);
+        ++cur;
+      }
+      const float* yw = d.yw + static_cast<size_t>(oy) * d.ky;
+      const float w0 = yw[0], w1 = d.ky > 1 ? yw[1] : 0.0f, w2 = d.ky > 2 ? yw[2] : 0.0f;
+      float acc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = (h0[i] * w0 + h1[i] * w1) + h2[i] * w2;
+      __stcs(reinterpret_cast<float4*>(op), make_float4(acc[0], acc[1], acc[2], acc[3]));
+      if (last) {
+        const uint32_t s0 = n0, s1 = n1, s2 = n2;                                  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        if (oy + 1 < oy1) { sp += sp_step; n0 = __ldg(sp); n1 = __ldg(sp + 1); n2 = __ldg(sp + 2); }
+        uint32_t a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = static_cast<uint32_t>(static_cast<int>(acc[i] * 255.0f)) << 24;   // truncation, predictor.py:130
+        uint4 o;
+        o.x = (s0 & 0x00FFFFFFu) | a[0];
+        o.y = (s0 >> 24) | ((s1 & 0x0000FFFFu) << 8) | a[1];
+        o.z = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | a[2];
+        o.w = (s2 >> 8) | a[3];
+        __stcs(reinterpret_cast<uint4*>(d.rgba) + ((static_cast<size_t>(oy) * d.W + ox) >> 2), o);
+      }
+    }
+  }
 }
 
 template <int K>

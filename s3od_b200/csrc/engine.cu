@@ -217,6 +217,8 @@ struct s3od_ctx {
   std::unordered_map<std::string, DevBuf> w;     // packed weights by name
   std::unordered_map<std::string, DevBuf> act;   // activations by name
   std::vector<void*> allocs;
+  bool pre_affine = false;                       // "pre.affine" reproduces every entry of "pre.lut" (checked in s3od_finalize)
+  float pre_ab[6] = {0, 0, 0, 0, 0, 0};
   ImageDesc* d_img = nullptr;
   PostDesc* d_post = nullptr;
   int last_nb = 0;
@@ -739,6 +741,26 @@ int s3od_finalize(s3od_ctx* c) {
     if (c->w.find(n) == c->w.end()) return fail(S3OD_ERR_MISSING, "missing tensor: " + n);
   CK(cudaMalloc(reinterpret_cast<void**>(&c->d_img), sizeof(ImageDesc) * c->max_batch));
   CK(cudaMalloc(reinterpret_cast<void**>(&c->d_post), sizeof(PostDesc) * c->max_batch));
+  // Optional "pre.affine" = {a[3], b[3]} fp32: the preprocess kernel evaluates bf16(fma(v, a, b)) instead of the table
+  // look-up when - and only when - that reproduces all 3 x 256 entries of "pre.lut" bit for bit (fmaf and the
+  // round-to-nearest-even bf16 conversion are the same IEEE operations on the host and on the device).
+  c->pre_affine = false;
+  auto aff = c->w.find("pre.affine");
+  if (aff != c->w.end() && aff->second.bytes == 6 * sizeof(float) && c->w["pre.lut"].bytes == 768 * sizeof(uint16_t)) {
+    uint16_t lut[768];
+    CK(cudaMemcpy(lut, c->w["pre.lut"].p, sizeof(lut), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c->pre_ab, aff->second.p, sizeof(c->pre_ab), cudaMemcpyDeviceToHost));
+    bool same = true;
+    for (int ch = 0; ch < 3 && same; ++ch)
+      for (int v = 0; v < 256 && same; ++v) {
+        const float f = fmaf(static_cast<float>(v), c->pre_ab[ch], c->pre_ab[3 + ch]);
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        const uint16_t bf = static_cast<uint16_t>((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);     // RNE (finite values)
+        same = bf == lut[ch * 256 + v];
+      }
+    c->pre_affine = same;
+  }
   if (!build_plan(c)) return S3OD_ERR_CUDA;
   c->finalized = true;
   return S3OD_OK;
@@ -752,7 +774,8 @@ int s3od_preprocess_u8(s3od_ctx* c, const s3od_image* images, int batch, s3od_st
   if (images == nullptr || batch < 1 || batch > c->max_batch) return fail(S3OD_ERR_ARG, "bad batch for s3od_preprocess_u8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CK(cudaMemcpyAsync(c->d_img, images, sizeof(ImageDesc) * batch, cudaMemcpyHostToDevice, st));
-  CK(launch_preprocess(c->d_img, wptr<bf16>(c, "pre.lut"), aptr<bf16>(c, "patches"), c->S, batch, st));
+  CK(launch_preprocess(c->d_img, wptr<bf16>(c, "pre.lut"), c->pre_affine ? c->pre_ab : nullptr, aptr<bf16>(c, "patches"), c->S, batch,
+                       st));
   c->launches += 1;
   return S3OD_OK;
 }
@@ -805,13 +828,27 @@ int s3od_postprocess(s3od_ctx* c, const float* d_mask_logits, const float* d_iou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int maxH = 0, maxW = 0;
   bool mult4 = true;
+  // Tile kernel (up-sampling or identity, <= 3 taps per axis): the largest input region one 16 x 512 output tile reads.
+  // ATen's first tap is trunc(scale * (i + 0.5) - support + 0.5) clamped at 0, so n outputs span <= scale * (n - 1) + 1 + k inputs.
+  bool tile_ok = true;
+  int tile_rows = 0, tile_cols = 0;
   for (int i = 0; i < batch; ++i) {
-    maxH = std::max(maxH, images[i].H);
-    maxW = std::max(maxW, images[i].W);
-    mult4 = mult4 && (images[i].W % 4 == 0);
+    const s3od_post& im = images[i];
+    maxH = std::max(maxH, im.H);
+    maxW = std::max(maxW, im.W);
+    mult4 = mult4 && (im.W % 4 == 0);
+    const int in_h = c->S - 2 * im.pad_h, in_w = c->S - 2 * im.pad_w;
+    if (im.H < 1 || im.W < 1 || in_h < 1 || in_w < 1) return fail(S3OD_ERR_ARG, "bad image geometry in s3od_postprocess");
+    tile_ok = tile_ok && im.ky <= 3 && im.kx <= 3 && im.H >= in_h && im.W >= in_w;
+    const long long rows = (16LL * in_h + im.H - 1) / im.H + im.ky + 1;
+    const long long cols = (512LL * in_w + im.W - 1) / im.W + im.kx + 1;
+    tile_rows = std::max(tile_rows, static_cast<int>(std::min<long long>(rows, c->S)));
+    tile_cols = std::max(tile_cols, static_cast<int>(std::min<long long>(cols, c->S)));
   }
+  if (!tile_ok) tile_rows = tile_cols = 0;
   CK(cudaMemcpyAsync(c->d_post, images, sizeof(PostDesc) * batch, cudaMemcpyHostToDevice, st));
-  CK(launch_postprocess(c->d_post, d_mask_logits, d_iou_logits, d_ious, d_best_idx, c->S, c->K, batch, maxH, maxW, mult4, st));
+  CK(launch_postprocess(c->d_post, d_mask_logits, d_iou_logits, d_ious, d_best_idx, c->S, c->K, batch, maxH, maxW, mult4, tile_rows,
+                        tile_cols, st));
   c->launches += 1;
   return S3OD_OK;
 }
@@ -869,6 +906,11 @@ int s3od_profile_read(s3od_ctx* c, char* buf, size_t buf_bytes) {
 }
 
 long long s3od_launch_count(s3od_ctx* c) { return c == nullptr ? 0 : c->launches; }
+
+int s3od_preprocess_mode(s3od_ctx* c) {
+  if (c == nullptr || !c->finalized) return fail(S3OD_ERR_STATE, "context not finalized");
+  return c->pre_affine ? 1 : 0;
+}
 
 void s3od_destroy(s3od_ctx* c) {
   if (c == nullptr) return;

@@ -47,10 +47,17 @@ cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, __nv_bfloat16* patches, int S, int B,
-                              cudaStream_t stream) {
-  const int n = S * (S / 8);
-  preprocess_kernel<<<dim3((n + 255) / 256, B), 256, 0, stream>>>(descs, lut, patches, S);
+cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, const float* affine, __nv_bfloat16* patches, int S,
+                              int B, cudaStream_t stream) {
+  const int g = S / 16;
+  const dim3 grid((g + 7) / 8, g, B);
+  if (affine != nullptr) {
+    PreAffine aff;
+    for (int c = 0; c < 3; ++c) { aff.a[c] = affine[c]; aff.b[c] = affine[3 + c]; }
+    preprocess_kernel<true><<<grid, 256, 0, stream>>>(descs, lut, aff, patches, S);
+  } else {
+    preprocess_kernel<false><<<grid, 256, 0, stream>>>(descs, lut, PreAffine{}, patches, S);
+  }
   return cudaGetLastError();
 }
 
@@ -89,9 +96,19 @@ cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, cons
 }
 
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
-                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, cudaStream_t stream) {
+                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, int tile_rows, int tile_cols,
+                               cudaStream_t stream) {
   if (K != 1 && K != 3) return cudaErrorInvalidValue;
-  if (all_w_mult4) {
+  if (all_w_mult4 && tile_rows > 0) {
+    // up-sampling / identity: shared-memory tile kernel (tile_rows x tile_cols = largest input region of one tile)
+    const int pitch = post_skew(tile_cols - 1) + 1;
+    const size_t smem = static_cast<size_t>(tile_rows) * pitch * sizeof(float);
+    dim3 grid((maxW + kPostTileW - 1) / kPostTileW, (maxH + kPostTileRows - 1) / kPostTileRows, B);
+    if (K == 3)
+      postprocess_tile_kernel<3><<<grid, 128, smem, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S, tile_rows, pitch);
+    else
+      postprocess_tile_kernel<1><<<grid, 128, smem, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S, tile_rows, pitch);
+  } else if (all_w_mult4) {
     dim3 grid((maxW / 4 + 127) / 128, maxH, B);
     if (K == 3)
       postprocess4_kernel<3><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);

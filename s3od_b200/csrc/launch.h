@@ -33,8 +33,9 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
 // x += dx (optional), tap = bf16(x) on patch rows (optional), y = LayerNorm(x) (optional)
 cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,
                              int ntok, int D, float eps, cudaStream_t stream);
-cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, __nv_bfloat16* patches, int S, int B,
-                              cudaStream_t stream);
+// affine = host pointer to {a0, a1, a2, b0, b1, b2} (normalisation as fma(v, a, b)), or nullptr for the table look-up
+cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, const float* affine, __nv_bfloat16* patches, int S,
+                              int B, cudaStream_t stream);
 cudaError_t launch_pack_input(const float* x, __nv_bfloat16* patches, int S, int B, cudaStream_t stream);
 cudaError_t launch_fill_prefix(float* x, const float* prefix, int ntok, int D, int B, cudaStream_t stream);
 cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float* pool, int pool_blocks, int B, int h, int w,
@@ -42,7 +43,8 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float
 cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, const float* w1, const float* b1, const float* w2,
                             const float* b2, float* iou_logits, int K, int B, cudaStream_t stream);
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
-                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, cudaStream_t stream);
+                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, int tile_rows, int tile_cols,
+                               cudaStream_t stream);
 
 // saliency metrics (metrics.cuh)
 cudaError_t launch_sod_stats(const float* pred, const float* mask, int H, int W, const float* thresholds, void* stats, int num_sms,

@@ -63,6 +63,7 @@ def load_library() -> ctypes.CDLL:
     lib.s3od_profile_read.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
     lib.s3od_launch_count.argtypes = [vp]
     lib.s3od_launch_count.restype = ctypes.c_longlong
+    lib.s3od_preprocess_mode.argtypes = [vp]
     lib.s3od_destroy.argtypes = [vp]
     lib.s3od_destroy.restype = None
     lib.s3od_op_gemm_f32.argtypes = [vp, vp, vp, ci, ci, ci, vp]
@@ -262,6 +263,10 @@ class B200DPTSegmentation:
             label, n, imgs, ms = line.split("\t")
             rows.append((label, int(n), int(imgs), float(ms)))
         return rows
+
+    def preprocess_mode(self) -> int:
+        """1 = normalisation as one FMA (verified against the table by the library), 0 = table look-up."""
+        return int(self.lib.s3od_preprocess_mode(self._ctx))
 
     def launch_count(self) -> int:
         return int(self.lib.s3od_launch_count(self._ctx))

@@ -67,6 +67,14 @@ def normalisation_lut() -> torch.Tensor:
     return torch.from_numpy(lut).reshape(-1).to(torch.bfloat16).contiguous()
 
 
+def normalisation_affine() -> torch.Tensor:
+    """fp32[6] = (a_c, b_c): (v/255 - mean)/std ~= fma(v, a_c, b_c).  Only a hint: s3od_finalize uses it if it reproduces
+    every bf16 entry of `normalisation_lut` exactly, otherwise the kernel keeps the table."""
+    mean = np.array([0.485, 0.456, 0.406])
+    std = np.array([0.229, 0.224, 0.225])
+    return torch.from_numpy(np.concatenate([1.0 / (255.0 * std), -mean / std]).astype(np.float32)).contiguous()
+
+
 # ConvTranspose2d(k4, s2, p1): output row 2i+a gets input rows / kernel rows  a=0: (i, kh=1), (i-1, kh=3);
 # a=1: (i+1, kh=0), (i, kh=2).  engine.cu::geom_convt_phase uses the same (offset, tap) order.
 _CT_K = {0: (1, 3), 1: (0, 2)}
@@ -97,6 +105,7 @@ def pack_weights(sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int) -
     g = image_size // arch.patch
     out["rope.cos"], out["rope.sin"] = rope_tables(g, g, arch.head_dim, arch.rope_theta)
     out["pre.lut"] = normalisation_lut()
+    out["pre.affine"] = normalisation_affine()      # optional fast form; the library verifies it against pre.lut
 
     pre = _enc_prefix(sd)
     for l in range(arch.layers_needed):                                               # layer 12 / final norm are dead (F3)

@@ -180,6 +180,7 @@ def test_preprocess_bit_exact(models, h, w, S):
             models(S).geometry(h, w)
         return
     m = models(S)
+    assert m.preprocess_mode() == 1          # the FMA form reproduces the normalisation table, so the library selected it
     m.preprocess([torch.from_numpy(img).cuda()])
     gp = S // 16
     patches = m.stage("patches", torch.bfloat16, (gp * gp, 768)).float().cpu()
@@ -188,7 +189,10 @@ def test_preprocess_bit_exact(models, h, w, S):
 
 
 @pytest.mark.parametrize("H,W,S,hp,wp", [(128, 128, 64, 0, 0), (120, 160, 128, 16, 0), (160, 120, 128, 0, 16), (50, 50, 128, 0, 0),
-                                         (300, 300, 128, 0, 0), (64, 64, 64, 0, 0)])
+                                         (300, 300, 128, 0, 0), (64, 64, 64, 0, 0),
+                                         # shared-memory tile kernel: several 16 x 512 tiles, ragged edges, 2x / identity / odd ratios
+                                         (1024, 1024, 512, 0, 0), (512, 512, 512, 0, 0), (520, 1040, 256, 64, 0),
+                                         (1100, 600, 512, 0, 116), (700, 1028, 512, 82, 0), (2048, 2048, 1024, 0, 0)])
 def test_postprocess_matches_oracle_on_given_logits(models, H, W, S, hp, wp):
     rng = np.random.default_rng(H + W)
     logits = (rng.standard_normal((1, 3, S, S)) * 3).astype(np.float32)
