@@ -452,18 +452,20 @@ __global__ void __launch_bounds__(128) postprocess4_kernel(const PostDesc* __res
 //   3. 128-bit streaming stores of the mask plane; the best plane goes last and also emits the RGBA pixels.
 // Same summation order as the per-pixel kernels (taps left to right, rows top to bottom; zero-weight taps add +0).
 // Shared column c lives at c + (c >> 5): adjacent threads read columns 4*scale apart, the skew spreads them over banks.
-constexpr int kPostTileRows = 16;
+constexpr int kPostTileRows = 32;          // most output rows per tile (the host picks 32 or 16 by shared-memory size)
 constexpr int kPostTileW = 512;
 __host__ __device__ __forceinline__ int post_skew(int c) { return c + (c >> 5); }
 
 template <int K>
 __global__ void __launch_bounds__(128, 6) postprocess_tile_kernel(const PostDesc* __restrict__ descs, const float* __restrict__ mask_logits,
                                                                const float* __restrict__ iou_logits, float* __restrict__ ious,
-                                                               int* __restrict__ best_idx, int S, int rows_max, int pitch) {
+                                                               int* __restrict__ best_idx, int S, int tile_out_rows, int rows_max,
+                                                               int pitch) {
   extern __shared__ float s_sig[];                 // [rows_max][pitch]
+  __shared__ float4 s_rowtab[kPostTileRows];       // per output row: (first input row relative to the region, 3 weights)
   const int b = blockIdx.z;
   const PostDesc d = descs[b];
-  const int oy0 = blockIdx.y * kPostTileRows;
+  const int oy0 = blockIdx.y * tile_out_rows;
   const int ox0 = blockIdx.x * kPostTileW;
   if (oy0 >= d.H || ox0 >= d.W) return;            // block-uniform
   float sc[K];
@@ -479,13 +481,19 @@ __global__ void __launch_bounds__(128, 6) postprocess_tile_kernel(const PostDesc
     for (int k = 0; k < K; ++k) ious[b * K + k] = sc[k];
     best_idx[b] = best;
   }
-  const int oy1 = min(oy0 + kPostTileRows, d.H);
+  const int oy1 = min(oy0 + tile_out_rows, d.H);
   const int ox1 = min(ox0 + kPostTileW, d.W);
   const int row0 = d.ystart[oy0] + d.pad_h;
   const int nrows = min(d.ystart[oy1 - 1] + d.pad_h + d.ky - 1, S - 1) - row0 + 1;
   const int col0 = d.xstart[ox0] + d.pad_w;
   const int ncols = min(d.xstart[ox1 - 1] + d.pad_w + d.kx - 1, S - 1) - col0 + 1;
   if (nrows > rows_max || post_skew(ncols - 1) >= pitch) __trap();     // the host sized the tile from the same tables
+  if (threadIdx.x < oy1 - oy0) {
+    const int oy = oy0 + threadIdx.x;
+    const float* yw = d.yw + static_cast<size_t>(oy) * d.ky;
+    s_rowtab[threadIdx.x] = make_float4(__int_as_float(d.ystart[oy] + d.pad_h - row0), yw[0], d.ky > 1 ? yw[1] : 0.0f,
+                                        d.ky > 2 ? yw[2] : 0.0f);
+  }
   // this thread's 4 output columns: shared-memory tap positions and weights (3 taps, zero-padded)
   const int ox = ox0 + threadIdx.x * 4;
   const bool active = ox < d.W;
@@ -501,7 +509,7 @@ __global__ void __launch_bounds__(128, 6) postprocess_tile_kernel(const PostDesc
     }
   }
   if (active) {                                     // source RGB rows of the tile towards L2 while the planes are processed
-    for (int r = oy0 + (threadIdx.x & 15); r < oy1; r += 16)
+    for (int r = oy0 + (threadIdx.x & 15); r < oy1; r += 16)     // 16 rows x 8 segments per pass
       for (int seg = threadIdx.x >> 4; seg * 128 < (ox1 - ox0) * 3; seg += 8)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(d.src + (static_cast<size_t>(r) * d.W + ox0) * 3 + seg * 128));
   }
@@ -542,7 +550,8 @@ __global__ void __launch_bounds__(128, 6) postprocess_tile_kernel(const PostDesc
     if (last) { n0 = __ldg(sp); n1 = __ldg(sp + 1); n2 = __ldg(sp + 2); }
 #pragma unroll 1
     for (int oy = oy0; oy < oy1; ++oy, op += d.W) {
-      const int ys = d.ystart[oy] + d.pad_h - row0;
+      const float4 rt = s_rowtab[oy - oy0];
+      const int ys = __float_as_int(rt.x);
 #pragma unroll 1
       while (cur < ys) {                           // block-uniform
 #pragma unroll
@@ -550,11 +559,9 @@ __global__ void __launch_bounds__(128, 6) postprocess_tile_kernel(const PostDesc
         hrow(cur + 3, h2);
         ++cur;
       }
-      const float* yw = d.yw + static_cast<size_t>(oy) * d.ky;
-      const float w0 = yw[0], w1 = d.ky > 1 ? yw[1] : 0.0f, w2 = d.ky > 2 ? yw[2] : 0.0f;
       float acc[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = (h0[i] * w0 + h1[i] * w1) + h2[i] * w2;
+      for (int i = 0; i < 4; ++i) acc[i] = (h0[i] * rt.y + h1[i] * rt.z) + h2[i] * rt.w;
       __stcs(reinterpret_cast<float4*>(op), make_float4(acc[0], acc[1], acc[2], acc[3]));
       if (last) {
         const uint32_t s0 = n0, s1 = n1, s2 = n2;                                  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
@@ -568,6 +575,167 @@ __global__ void __launch_bounds__(128, 6) postprocess_tile_kernel(const PostDesc
         o.z = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | a[2];
         o.w = (s2 >> 8) | a[3];
         __stcs(reinterpret_cast<uint4*>(d.rgba) + ((static_cast<size_t>(oy) * d.W + ox) >> 2), o);
+      }
+    }
+  }
+}
+
+// Identity path (source size == cropped mask size, e.g. 1024^2 sources at image_size 1024; widths and the left padding
+// multiples of 4): ATen's antialias table for scale 1 is exactly (first tap = i, weights 1, 0), so the resize is a copy
+// and all_masks = sigmoid(logits) * 1 * 1.  Pure streaming: thread = 4 pixels x kPostIdRows rows, 128-bit accesses.
+constexpr int kPostIdRows = 8;
+
+template <int K>
+__global__ void __launch_bounds__(128) postprocess_identity_kernel(const PostDesc* __restrict__ descs, const float* __restrict__ mask_logits,
+                                                                   const float* __restrict__ iou_logits, float* __restrict__ ious,
+                                                                   int* __restrict__ best_idx, int S) {
+  const int b = blockIdx.z;
+  const PostDesc d = descs[b];
+  const int oy0 = blockIdx.y * kPostIdRows;
+  const int ox = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (oy0 >= d.H) return;
+  float sc[K];
+  int best = 0;
+  float bestv = -1.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    sc[k] = sigmoidf_acc(iou_logits[b * K + k]);
+    if (sc[k] > bestv) { bestv = sc[k]; best = k; }      // strict >: first maximum wins, like numpy argmax
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) ious[b * K + k] = sc[k];
+    best_idx[b] = best;
+  }
+  if (ox >= d.W) return;
+  const int oy1 = min(oy0 + kPostIdRows, d.H);
+  const float* lp = mask_logits + static_cast<size_t>(b) * K * S * S + static_cast<size_t>(oy0 + d.pad_h) * S + d.pad_w + ox;
+  float* op = d.all_masks + static_cast<size_t>(oy0) * d.W + ox;
+  const uint32_t* sp = reinterpret_cast<const uint32_t*>(d.src + (static_cast<size_t>(oy0) * d.W + ox) * 3);
+  uint4* rp = reinterpret_cast<uint4*>(d.rgba) + ((static_cast<size_t>(oy0) * d.W + ox) >> 2);
+  const size_t plane_in = static_cast<size_t>(S) * S, plane_out = static_cast<size_t>(d.H) * d.W;
+#pragma unroll 2
+  for (int oy = oy0; oy < oy1; ++oy, lp += S, op += d.W, sp += d.W * 3 / 4, rp += d.W / 4) {
+    float4 v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = __ldcs(reinterpret_cast<const float4*>(lp + k * plane_in));
+    const uint32_t s0 = __ldcs(sp), s1 = __ldcs(sp + 1), s2 = __ldcs(sp + 2);     // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+    float4 al = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float4 m = make_float4(sigmoidf_fast(v[k].x), sigmoidf_fast(v[k].y), sigmoidf_fast(v[k].z), sigmoidf_fast(v[k].w));
+      __stcs(reinterpret_cast<float4*>(op + k * plane_out), m);
+      if (k == best) al = m;
+    }
+    uint4 o;
+    o.x = (s0 & 0x00FFFFFFu) | (static_cast<uint32_t>(static_cast<int>(al.x * 255.0f)) << 24);   // truncation, predictor.py:130
+    o.y = (s0 >> 24) | ((s1 & 0x0000FFFFu) << 8) | (static_cast<uint32_t>(static_cast<int>(al.y * 255.0f)) << 24);
+    o.z = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | (static_cast<uint32_t>(static_cast<int>(al.z * 255.0f)) << 24);
+    o.w = (s2 >> 8) | (static_cast<uint32_t>(static_cast<int>(al.w * 255.0f)) << 24);
+    __stcs(rp, o);
+  }
+}
+
+// Exact 2x path (source = 2 x cropped mask, e.g. 2048^2 sources at image_size 1024): ATen's antialias table for scale 1/2
+// is the plain bilinear one - weights (.25, .75) / (.75, .25), a single tap of weight 1 at the borders (= the clamped
+// form below up to one rounding).  Thread = input columns (2j, 2j+1) -> output columns 4j..4j+3, walking down
+// kPostUpRows input rows with the horizontally filtered rows above / at / below in registers: one new input row (one
+// 8-byte + two 4-byte loads per plane, the neighbours hit in L1) per two output rows, no shared memory, no divergence.
+constexpr int kPostUpRows = 16;
+
+template <int K>
+__global__ void __launch_bounds__(128) postprocess_up2_kernel(const PostDesc* __restrict__ descs, const float* __restrict__ mask_logits,
+                                                              const float* __restrict__ iou_logits, float* __restrict__ ious,
+                                                              int* __restrict__ best_idx, int S) {
+  const int b = blockIdx.z;
+  const PostDesc d = descs[b];
+  const int in_h = d.H >> 1, in_w = d.W >> 1;
+  const int iy0 = blockIdx.y * kPostUpRows;
+  const int j2 = (blockIdx.x * 128 + threadIdx.x) * 2;         // first of this thread's two input columns
+  if (iy0 >= in_h) return;
+  float sc[K];
+  int best = 0;
+  float bestv = -1.0f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    sc[k] = sigmoidf_acc(iou_logits[b * K + k]);
+    if (sc[k] > bestv) { bestv = sc[k]; best = k; }      // strict >: first maximum wins, like numpy argmax
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) ious[b * K + k] = sc[k];
+    best_idx[b] = best;
+  }
+  if (j2 >= in_w) return;
+  const int iy1 = min(iy0 + kPostUpRows, in_h);
+  const size_t plane_in = static_cast<size_t>(S) * S, plane_out = static_cast<size_t>(d.H) * d.W;
+  const int jl = max(j2 - 1, 0), jr = min(j2 + 2, in_w - 1);
+  const int ox = j2 * 2;
+  // One plane at a time (the best one last: it also writes the RGBA pixels) keeps the thread at ~50 registers, and the
+  // logits of the NEXT input row are requested before the current rows are filtered and stored (the source / output
+  // pointers may alias as far as the compiler knows, so loads are never moved above the stores for us).
+#pragma unroll 1
+  for (int kk = 0; kk < K; ++kk) {
+    const int k = (best + 1 + kk) % K;
+    const bool last = kk == K - 1;
+    const float* lp = mask_logits + (static_cast<size_t>(b) * K + k) * plane_in + static_cast<size_t>(d.pad_h) * S + d.pad_w;
+    float* op = d.all_masks + k * plane_out + static_cast<size_t>(2 * iy0) * d.W + ox;
+    float raw[4];                                    // logits (left neighbour, 2j, 2j+1, right neighbour) of the row in flight
+    auto request = [&](int r) {
+      const float* rp = lp + static_cast<size_t>(min(max(r, 0), in_h - 1)) * S;
+      const float2 m = __ldg(reinterpret_cast<const float2*>(rp + j2));
+      raw[0] = __ldg(rp + jl); raw[1] = m.x; raw[2] = m.y; raw[3] = __ldg(rp + jr);
+    };
+    auto filter = [&](float (&h)[4]) {               // horizontally filtered row: output columns 4j .. 4j+3
+      const float l = sigmoidf_fast(raw[0]), a = sigmoidf_fast(raw[1]), c = sigmoidf_fast(raw[2]), r_ = sigmoidf_fast(raw[3]);
+      h[0] = l * 0.25f + a * 0.75f;
+      h[1] = a * 0.75f + c * 0.25f;
+      h[2] = a * 0.25f + c * 0.75f;
+      h[3] = c * 0.75f + r_ * 0.25f;
+    };
+    float h0[4], h1[4], h2[4];                       // filtered rows above / at / below the current input row
+    request(iy0 - 1);
+    filter(h0);
+    request(iy0);
+    filter(h1);
+    request(iy0 + 1);
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(d.src + (static_cast<size_t>(2 * iy0) * d.W + ox) * 3);
+    uint4* rp4 = reinterpret_cast<uint4*>(d.rgba) + ((static_cast<size_t>(2 * iy0) * d.W + ox) >> 2);
+    const int w3 = d.W * 3 / 4, w4 = d.W / 4;
+#pragma unroll 1
+    for (int i = iy0; i < iy1; ++i, op += 2 * d.W, sp += 2 * w3, rp4 += 2 * w4) {
+      uint32_t s[6] = {0, 0, 0, 0, 0, 0};            // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3 of output rows 2i and 2i+1
+      if (last) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { s[e] = __ldcs(sp + e); s[3 + e] = __ldcs(sp + w3 + e); }
+      }
+      filter(h2);                                     // row i+1 (requested one iteration ago)
+      request(i + 2);
+      float t[4], u[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        t[e] = h0[e] * 0.25f + h1[e] * 0.75f;        // output row 2i
+        u[e] = h1[e] * 0.75f + h2[e] * 0.25f;        // output row 2i+1
+        h0[e] = h1[e];
+        h1[e] = h2[e];
+      }
+      __stcs(reinterpret_cast<float4*>(op), make_float4(t[0], t[1], t[2], t[3]));
+      __stcs(reinterpret_cast<float4*>(op + d.W), make_float4(u[0], u[1], u[2], u[3]));
+      if (last) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const float* al = rr == 0 ? t : u;
+          uint32_t a[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) a[e] = static_cast<uint32_t>(static_cast<int>(al[e] * 255.0f)) << 24;   // truncation, predictor.py:130
+          const uint32_t s0 = s[3 * rr], s1 = s[3 * rr + 1], s2 = s[3 * rr + 2];
+          uint4 o;
+          o.x = (s0 & 0x00FFFFFFu) | a[0];
+          o.y = (s0 >> 24) | ((s1 & 0x0000FFFFu) << 8) | a[1];
+          o.z = (s1 >> 16) | ((s2 & 0x000000FFu) << 16) | a[2];
+          o.w = (s2 >> 8) | a[3];
+          __stcs(rp4 + rr * w4, o);
+        }
       }
     }
   }

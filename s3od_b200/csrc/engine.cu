@@ -828,10 +828,10 @@ int s3od_postprocess(s3od_ctx* c, const float* d_mask_logits, const float* d_iou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int maxH = 0, maxW = 0;
   bool mult4 = true;
-  // Tile kernel (up-sampling or identity, <= 3 taps per axis): the largest input region one 16 x 512 output tile reads.
+  // Tile kernel (up-sampling or identity, <= 3 taps per axis): the largest input region one R x 512 output tile reads.
   // ATen's first tap is trunc(scale * (i + 0.5) - support + 0.5) clamped at 0, so n outputs span <= scale * (n - 1) + 1 + k inputs.
-  bool tile_ok = true;
-  int tile_rows = 0, tile_cols = 0;
+  // R = 32 output rows when that region fits in 24 KB of shared memory (2x up-sampling: 20 x 260 floats), else 16.
+  bool tile_ok = true, identity = true, twice = true;
   for (int i = 0; i < batch; ++i) {
     const s3od_post& im = images[i];
     maxH = std::max(maxH, im.H);
@@ -840,15 +840,30 @@ int s3od_postprocess(s3od_ctx* c, const float* d_mask_logits, const float* d_iou
     const int in_h = c->S - 2 * im.pad_h, in_w = c->S - 2 * im.pad_w;
     if (im.H < 1 || im.W < 1 || in_h < 1 || in_w < 1) return fail(S3OD_ERR_ARG, "bad image geometry in s3od_postprocess");
     tile_ok = tile_ok && im.ky <= 3 && im.kx <= 3 && im.H >= in_h && im.W >= in_w;
-    const long long rows = (16LL * in_h + im.H - 1) / im.H + im.ky + 1;
-    const long long cols = (512LL * in_w + im.W - 1) / im.W + im.kx + 1;
-    tile_rows = std::max(tile_rows, static_cast<int>(std::min<long long>(rows, c->S)));
-    tile_cols = std::max(tile_cols, static_cast<int>(std::min<long long>(cols, c->S)));
+    // scale exactly 1: ATen's table is (first tap i, weights 1, 0), the resize is a copy of the cropped mask
+    identity = identity && im.H == in_h && im.W == in_w && im.pad_w % 4 == 0 && im.ky <= 2 && im.kx <= 2;
+    // scale exactly 1/2: ATen's table is the plain 2x bilinear one (taps .25 / .75, weight 1 at the borders)
+    twice = twice && im.H == 2 * in_h && im.W == 2 * in_w && im.pad_w % 2 == 0 && im.ky <= 3 && im.kx <= 3;
   }
-  if (!tile_ok) tile_rows = tile_cols = 0;
+  int tile_out_rows = 0, tile_rows = 0, tile_cols = 0;
+  for (int R : {32, 16}) {
+    if (!tile_ok) break;
+    tile_out_rows = R; tile_rows = 0; tile_cols = 0;
+    for (int i = 0; i < batch; ++i) {
+      const s3od_post& im = images[i];
+      const int in_h = c->S - 2 * im.pad_h, in_w = c->S - 2 * im.pad_w;
+      const long long rows = (static_cast<long long>(R) * in_h + im.H - 1) / im.H + im.ky + 1;
+      const long long cols = (512LL * in_w + im.W - 1) / im.W + im.kx + 1;
+      tile_rows = std::max(tile_rows, static_cast<int>(std::min<long long>(rows, c->S)));
+      tile_cols = std::max(tile_cols, static_cast<int>(std::min<long long>(cols, c->S)));
+    }
+    if (static_cast<size_t>(tile_rows) * (tile_cols + tile_cols / 32 + 1) * sizeof(float) <= 24 * 1024) break;
+  }
+  if (identity && mult4) tile_out_rows = -1;
+  else if (twice && mult4) tile_out_rows = -2;
   CK(cudaMemcpyAsync(c->d_post, images, sizeof(PostDesc) * batch, cudaMemcpyHostToDevice, st));
-  CK(launch_postprocess(c->d_post, d_mask_logits, d_iou_logits, d_ious, d_best_idx, c->S, c->K, batch, maxH, maxW, mult4, tile_rows,
-                        tile_cols, st));
+  CK(launch_postprocess(c->d_post, d_mask_logits, d_iou_logits, d_ious, d_best_idx, c->S, c->K, batch, maxH, maxW, mult4, tile_out_rows,
+                        tile_rows, tile_cols, st));
   c->launches += 1;
   return S3OD_OK;
 }

@@ -96,18 +96,36 @@ cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, cons
 }
 
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
-                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, int tile_rows, int tile_cols,
-                               cudaStream_t stream) {
+                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, int tile_out_rows, int tile_rows,
+                               int tile_cols, cudaStream_t stream) {
   if (K != 1 && K != 3) return cudaErrorInvalidValue;
-  if (all_w_mult4 && tile_rows > 0) {
-    // up-sampling / identity: shared-memory tile kernel (tile_rows x tile_cols = largest input region of one tile)
+  if (all_w_mult4 && tile_out_rows == -1) {
+    // every image keeps the size of its cropped mask: the resize is the identity
+    dim3 grid((maxW / 4 + 127) / 128, (maxH + kPostIdRows - 1) / kPostIdRows, B);
+    if (K == 3)
+      postprocess_identity_kernel<3><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+    else
+      postprocess_identity_kernel<1><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+  } else if (all_w_mult4 && tile_out_rows == -2) {
+    // every image is exactly twice its cropped mask: plain 2x bilinear
+    dim3 grid((maxW / 4 + 127) / 128, (maxH / 2 + kPostUpRows - 1) / kPostUpRows, B);
+    if (K == 3)
+      postprocess_up2_kernel<3><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+    else
+      postprocess_up2_kernel<1><<<grid, 128, 0, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S);
+  } else if (all_w_mult4 && tile_rows > 0) {
+    // up-sampling / identity: shared-memory tile kernel; tile_rows x tile_cols = largest input region of one
+    // tile_out_rows x kPostTileW output tile
+    if (tile_out_rows < 1 || tile_out_rows > kPostTileRows) return cudaErrorInvalidValue;
     const int pitch = post_skew(tile_cols - 1) + 1;
     const size_t smem = static_cast<size_t>(tile_rows) * pitch * sizeof(float);
-    dim3 grid((maxW + kPostTileW - 1) / kPostTileW, (maxH + kPostTileRows - 1) / kPostTileRows, B);
+    dim3 grid((maxW + kPostTileW - 1) / kPostTileW, (maxH + tile_out_rows - 1) / tile_out_rows, B);
     if (K == 3)
-      postprocess_tile_kernel<3><<<grid, 128, smem, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S, tile_rows, pitch);
+      postprocess_tile_kernel<3><<<grid, 128, smem, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S, tile_out_rows,
+                                                              tile_rows, pitch);
     else
-      postprocess_tile_kernel<1><<<grid, 128, smem, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S, tile_rows, pitch);
+      postprocess_tile_kernel<1><<<grid, 128, smem, stream>>>(descs, mask_logits, iou_logits, ious, best_idx, S, tile_out_rows,
+                                                              tile_rows, pitch);
   } else if (all_w_mult4) {
     dim3 grid((maxW / 4 + 127) / 128, maxH, B);
     if (K == 3)

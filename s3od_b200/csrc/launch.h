@@ -42,9 +42,11 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float
                               int num_sms, cudaStream_t stream);
 cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, const float* w1, const float* b1, const float* w2,
                             const float* b2, float* iou_logits, int K, int B, cudaStream_t stream);
+// tile_out_rows: -1 = identity kernel (no resize), -2 = exact 2x kernel, 16 / 32 = shared-memory tile kernel with tile_rows x tile_cols input
+// regions, 0 = per-pixel kernels
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,
-                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, int tile_rows, int tile_cols,
-                               cudaStream_t stream);
+                               int* best_idx, int S, int K, int B, int maxH, int maxW, bool all_w_mult4, int tile_out_rows, int tile_rows,
+                               int tile_cols, cudaStream_t stream);
 
 // saliency metrics (metrics.cuh)
 cudaError_t launch_sod_stats(const float* pred, const float* mask, int H, int W, const float* thresholds, void* stats, int num_sms,

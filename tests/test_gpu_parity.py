@@ -192,6 +192,8 @@ def test_preprocess_bit_exact(models, h, w, S):
                                          (300, 300, 128, 0, 0), (64, 64, 64, 0, 0),
                                          # shared-memory tile kernel: several 16 x 512 tiles, ragged edges, 2x / identity / odd ratios
                                          (1024, 1024, 512, 0, 0), (512, 512, 512, 0, 0), (520, 1040, 256, 64, 0),
+                                         (96, 128, 128, 16, 0), (128, 96, 128, 0, 16),         # identity kernel with padding
+                                         (192, 256, 128, 16, 0), (256, 192, 128, 0, 16), (1160, 1240, 1024, 222, 202),   # exact-2x kernel
                                          (1100, 600, 512, 0, 116), (700, 1028, 512, 82, 0), (2048, 2048, 1024, 0, 0)])
 def test_postprocess_matches_oracle_on_given_logits(models, H, W, S, hp, wp):
     rng = np.random.default_rng(H + W)
