@@ -83,6 +83,8 @@ class ClockSampler:
 
 
 def kernel_family(label: str) -> str:
+    if label in ("preprocess", "postprocess"):
+        return label
     if label.endswith("attention"):
         return "attention"
     if label.endswith((".ln1", ".ln2", "final_residual")):
@@ -176,7 +178,6 @@ def run_b200(args, rank, local_rank, world):
 
     if rank != 0:
         return None
-    peaks = load_peaks()
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     # ---- per-family device time (CUDA events on the launch stream, recorded inside the timed region)
@@ -185,6 +186,7 @@ def run_b200(args, rank, local_rank, world):
             f.write("label\tlaunches\timages\ttotal_ms\tms_per_launch\n")
             for label, n, imgs, ms in prof:
                 f.write(f"{label}\t{n}\t{imgs}\t{ms:.4f}\t{ms / max(n, 1):.4f}\n")
+    peaks = load_peaks()
     fam_ms, fam_n = {}, {}
     for label, n, imgs, ms in prof:
         f = kernel_family(label)
@@ -193,10 +195,20 @@ def run_b200(args, rank, local_rank, world):
     total_ms = sum(fam_ms.values())
     images = B * args.steps
     families = {}
+    K = arch.num_outputs
+    # algorithmic bytes per image of the two bandwidth kernels either side of the network
+    family_bytes = {"preprocess": src * src * 3 + 3 * S * S * 2,
+                    "postprocess": K * S * S * 4 + src * src * 3 + K * src * src * 4 + src * src * 4}
     for f, ms in sorted(fam_ms.items(), key=lambda kv: -kv[1]):
+        if ms <= 0.0:
+            continue
         ent = {"share": round(ms / total_ms, 4), "ms_per_image": round(ms / images, 5), "launches": fam_n[f]}
         if f in FAMILY_GFLOP and S == 1024 and args.model == "dinob":
             ent["tflops"] = round(FAMILY_GFLOP[f] * images / ms, 1)
+        if f in family_bytes:
+            gbs = family_bytes[f] * images / ms / 1e6
+            ent["hbm_gbs"] = round(gbs, 1)
+            ent["hbm_frac"] = round(gbs / peaks["hbm_gbs"], 4)
         families[f] = ent
     dom = max((f for f in fam_ms if f in FAMILY_GFLOP), key=lambda f: fam_ms[f])
     flops_known = S == 1024 and args.model == "dinob"

@@ -769,13 +769,33 @@ int s3od_finalize(s3od_ctx* c) {
 static_assert(sizeof(s3od_image) == sizeof(ImageDesc), "s3od_image must mirror ImageDesc");
 static_assert(sizeof(s3od_post) == sizeof(PostDesc), "s3od_post must mirror PostDesc");
 
+// CUDA-event pair around one launch outside the forward plan (op index plan.size() = preprocess, +1 = postprocess)
+static int profile_mark(s3od_ctx* c, int op, int nb, cudaStream_t st, bool begin) {
+  if (!c->profile) return S3OD_OK;
+  if (begin) {
+    while (c->ev_pool.size() < c->ev_used + 2) {
+      cudaEvent_t ev;
+      CK(cudaEventCreate(&ev));
+      c->ev_pool.push_back(ev);
+    }
+    c->ev_ops.emplace_back(op, nb);
+    CK(cudaEventRecord(c->ev_pool[c->ev_used], st));
+    c->ev_used += 2;
+  } else {
+    CK(cudaEventRecord(c->ev_pool[c->ev_used - 1], st));
+  }
+  return S3OD_OK;
+}
+
 int s3od_preprocess_u8(s3od_ctx* c, const s3od_image* images, int batch, s3od_stream stream) {
   if (c == nullptr || !c->finalized) return fail(S3OD_ERR_STATE, "context not finalized");
   if (images == nullptr || batch < 1 || batch > c->max_batch) return fail(S3OD_ERR_ARG, "bad batch for s3od_preprocess_u8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CK(cudaMemcpyAsync(c->d_img, images, sizeof(ImageDesc) * batch, cudaMemcpyHostToDevice, st));
+  if (profile_mark(c, static_cast<int>(c->plan.size()), batch, st, true) != S3OD_OK) return S3OD_ERR_CUDA;
   CK(launch_preprocess(c->d_img, wptr<bf16>(c, "pre.lut"), c->pre_affine ? c->pre_ab : nullptr, aptr<bf16>(c, "patches"), c->S, batch,
                        st));
+  if (profile_mark(c, static_cast<int>(c->plan.size()), batch, st, false) != S3OD_OK) return S3OD_ERR_CUDA;
   c->launches += 1;
   return S3OD_OK;
 }
@@ -862,8 +882,10 @@ int s3od_postprocess(s3od_ctx* c, const float* d_mask_logits, const float* d_iou
   if (identity && mult4) tile_out_rows = -1;
   else if (twice && mult4) tile_out_rows = -2;
   CK(cudaMemcpyAsync(c->d_post, images, sizeof(PostDesc) * batch, cudaMemcpyHostToDevice, st));
+  if (profile_mark(c, static_cast<int>(c->plan.size()) + 1, batch, st, true) != S3OD_OK) return S3OD_ERR_CUDA;
   CK(launch_postprocess(c->d_post, d_mask_logits, d_iou_logits, d_ious, d_best_idx, c->S, c->K, batch, maxH, maxW, mult4, tile_out_rows,
                         tile_rows, tile_cols, st));
+  if (profile_mark(c, static_cast<int>(c->plan.size()) + 1, batch, st, false) != S3OD_OK) return S3OD_ERR_CUDA;
   c->launches += 1;
   return S3OD_OK;
 }
@@ -897,8 +919,9 @@ int s3od_profile_enable(s3od_ctx* c, int on) {
 // Writes "label<TAB>launches<TAB>images<TAB>total_ms\n" per plan entry, for all forwards since the last enable/read.
 int s3od_profile_read(s3od_ctx* c, char* buf, size_t buf_bytes) {
   if (c == nullptr || buf == nullptr || buf_bytes == 0) return fail(S3OD_ERR_ARG, "bad argument to s3od_profile_read");
-  std::vector<double> ms(c->plan.size(), 0.0);
-  std::vector<long long> cnt(c->plan.size(), 0), imgs(c->plan.size(), 0);
+  const size_t nops = c->plan.size() + 2;          // + preprocess, postprocess
+  std::vector<double> ms(nops, 0.0);
+  std::vector<long long> cnt(nops, 0), imgs(nops, 0);
   if (c->ev_used > 0) CK(cudaEventSynchronize(c->ev_pool[c->ev_used - 1]));
   for (size_t i = 0; i < c->ev_ops.size(); ++i) {
     float t = 0.0f;
@@ -908,9 +931,10 @@ int s3od_profile_read(s3od_ctx* c, char* buf, size_t buf_bytes) {
     imgs[c->ev_ops[i].first] += c->ev_ops[i].second;
   }
   std::string out;
-  for (size_t i = 0; i < c->plan.size(); ++i) {
+  for (size_t i = 0; i < nops; ++i) {
     char line[256];
-    snprintf(line, sizeof(line), "%s\t%lld\t%lld\t%.6f\n", c->plan[i].first.c_str(), cnt[i], imgs[i], ms[i]);
+    const char* label = i < c->plan.size() ? c->plan[i].first.c_str() : (i == c->plan.size() ? "preprocess" : "postprocess");
+    snprintf(line, sizeof(line), "%s\t%lld\t%lld\t%.6f\n", label, cnt[i], imgs[i], ms[i]);
     out += line;
   }
   c->ev_used = 0;

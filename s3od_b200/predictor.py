@@ -28,6 +28,27 @@ class RemovalResult:
     rgba_image: Image.Image
 
 
+def chunk_schedule(n: int, step: int) -> List[tuple]:
+    """[(start, end)] of the device chunks of an n-image batch: full micro-batches, the last one halved down to 4 images.
+    The device-to-host copy of a chunk overlaps the compute of the next one, so only the LAST chunk's copy is exposed;
+    ending on small chunks keeps that tail short (67 MB of results per 2048^2 image)."""
+    sizes = [step] * (n // step)
+    if n % step:
+        sizes.append(n % step)
+    if sizes:
+        last = sizes.pop()
+        while last > 4:
+            half = last // 2
+            sizes.append(half)
+            last -= half
+        sizes.append(last)
+    bounds, s0 = [], 0
+    for sz in sizes:
+        bounds.append((s0, s0 + sz))
+        s0 += sz
+    return bounds
+
+
 class BackgroundRemoval:
     DEFAULT_MODEL_ID = "okupyn/s3od"
     DEFAULT_CHECKPOINT_NAME = "s3od.pt"
@@ -100,17 +121,26 @@ class BackgroundRemoval:
         main = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(dev)
-        side = self._copy_stream
+            self._upload_stream = torch.cuda.Stream(dev)
+        side, up = self._copy_stream, self._upload_stream
         pending = []
         step = max(1, min(model.max_batch, model.micro_batch))
         if getattr(self, "_slot_free", None) is None:
             self._slot_free = [None, None]                      # event: the slot's device buffers have been copied out
-        for ci, s0 in enumerate(range(0, len(arrays), step)):
-            chunk = arrays[s0:s0 + step]
+        bounds = chunk_schedule(len(arrays), step)
+        # host -> device copies of every chunk on their own stream, ahead of the compute that consumes them
+        uploads = []
+        with torch.cuda.stream(up):
+            for s0, s1 in bounds:
+                d_imgs = [torch.from_numpy(a).to(dev, non_blocking=True) for a in arrays[s0:s1]]
+                uploads.append((d_imgs, up.record_event()))
+        for ci, (d_imgs, uploaded) in enumerate(uploads):
             slot = ci & 1                                       # two sets of reusable device output buffers
             if self._slot_free[slot] is not None:
                 main.wait_event(self._slot_free[slot])
-            d_imgs = [torch.from_numpy(a).to(dev, non_blocking=True) for a in chunk]
+            main.wait_event(uploaded)
+            for t in d_imgs:
+                t.record_stream(main)
             _, outs, ious, best = model.run_u8(d_imgs, slot=slot)
             done = torch.cuda.Event()
             done.record(main)

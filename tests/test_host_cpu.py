@@ -177,3 +177,18 @@ def test_sharder_two_ranks_gloo():
         assert p.exitcode == 0
     assert res[0][1:3] == (0, 19) and res[1][1:3] == (19, 37)
     assert all(r[3] == 11.0 and r[4] == 37.0 for r in res)               # max over ranks, total units
+
+
+def test_chunk_schedule_covers_the_batch_and_ends_small():
+    """remove_background_batch: full micro-batches, then the last one halved down to <= 4 images (short copy-out tail)."""
+    from s3od_b200.predictor import chunk_schedule
+    assert chunk_schedule(32, 16) == [(0, 16), (16, 24), (24, 28), (28, 32)]
+    assert chunk_schedule(1, 16) == [(0, 1)]
+    assert chunk_schedule(0, 16) == []
+    for n in range(1, 70):
+        for step in (1, 3, 8, 16):
+            b = chunk_schedule(n, step)
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+            assert all(0 < e - s0 <= step for s0, e in b)
+            assert b[-1][1] - b[-1][0] <= 4
