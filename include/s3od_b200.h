@@ -128,6 +128,11 @@ int s3od_vis_composite(const uint8_t* d_image, const float* d_mask, uint8_t* d_o
 int s3od_vis_mask_grid(const uint8_t* d_image, const float* d_masks, int num_masks, uint8_t* d_out, int h, int w, s3od_stream stream);
 int s3od_mask_pair_counts(const float* d_masks, int num_masks, int h, int w, unsigned long long* d_counts, s3od_stream stream);
 
+/* ---- SODPredictor.predict tail (synth_sod/src/synth_sod/model_training/predictor.py:461-470):
+ *     out[i] = in[i] > threshold ? 1.0f : 0.0f  over n device floats (binary_mask / all_masks of PredictionResult);
+ *     the soft masks come from s3od_postprocess.  Buffers 16-byte aligned. */
+int s3od_threshold_f32(const float* d_in, float* d_out, size_t n, float threshold, s3od_stream stream);
+
 /* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
 /* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */
 int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream);

@@ -16,9 +16,9 @@ namespace s3od {
 // patch-embed convolution (HF:71-81) is a plain GEMM.  The 3x256 normalisation LUT holds bf16(float32(reference value)).
 // predictor.py:79-94;  cv2.resize INTER_LINEAR arithmetic restated in oracle/prepost.py.
 // ------------------------------------------------------------------------------------------------------------------
-S3OD_DEVICE int resized_px(const ImageDesc& d, int y, int x, int c) {
-  if (d.mode == 0) return d.src[(static_cast<size_t>(y) * d.w + x) * 3 + c];
-  if (d.mode == 1) {
+S3OD_DEVICE int resized_px(const ImageDesc& d, int mode, int y, int x, int c) {
+  if (mode == 0) return d.src[(static_cast<size_t>(y) * d.w + x) * 3 + c];
+  if (mode == 1) {
     const uint8_t* r0 = d.src + (static_cast<size_t>(2 * y) * d.w + 2 * x) * 3 + c;
     const uint8_t* r1 = r0 + static_cast<size_t>(d.w) * 3;
     return (r0[0] + r0[3] + r1[0] + r1[3] + 2) >> 2;
@@ -42,8 +42,10 @@ constexpr int kPrePatchBytes = 1536 + 32;     // +32: the 16-byte pieces of the 
 // random bank conflicts per thread); the host only selects it after checking that it reproduces all 768 table entries.
 struct PreAffine { float a[3], b[3]; };
 
-template <bool AFFINE>
-__global__ void __launch_bounds__(256) preprocess_kernel(const ImageDesc* __restrict__ descs, const __nv_bfloat16* __restrict__ lut,
+// MODE = 0 / 1: every image of the batch is in copy / exact-2x mode (the generic table path is compiled out, which keeps
+// the kernel at <= 48 registers = 5 blocks per SM; it was latency-bound at 3); MODE = 2: per-image mode from the descriptor.
+template <bool AFFINE, int MODE>
+__global__ void __launch_bounds__(256, MODE == 2 ? 3 : 5) preprocess_kernel(const ImageDesc* __restrict__ descs, const __nv_bfloat16* __restrict__ lut,
                                                          PreAffine aff, __nv_bfloat16* __restrict__ patches, int S) {
   __shared__ __nv_bfloat16 s_lut[AFFINE ? 8 : 768];
   __shared__ __align__(16) uint8_t s_out[8 * kPrePatchBytes];
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const ImageDesc* __rest
   }
   const int b = blockIdx.z;
   const ImageDesc d = descs[b];
+  const int mode = MODE == 2 ? d.mode : MODE;
   const int g = S >> 4;
   const int py = blockIdx.y, px0 = blockIdx.x * 8;
   const int row = threadIdx.x >> 4, x8 = threadIdx.x & 15;
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const ImageDesc* __rest
     uint8_t px[8][3];
     // fast paths: all 8 pixels inside the resized image and the source row segment is 8- / 16-byte aligned
     const bool inside = row_in && rx0 >= 0 && rx0 + 8 <= d.new_w;
-    if (inside && d.mode == 0 && ((d.w * 3) & 7) == 0 && (rx0 & 7) == 0) {
+    if (inside && mode == 0 && ((d.w * 3) & 7) == 0 && (rx0 & 7) == 0) {
       // 8 pixels = 24 contiguous bytes
       const uint2* sp = reinterpret_cast<const uint2*>(d.src + (static_cast<size_t>(ry) * d.w + rx0) * 3);
       uint2 v[3] = {__ldg(sp), __ldg(sp + 1), __ldg(sp + 2)};
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const ImageDesc* __rest
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int c = 0; c < 3; ++c) px[i][c] = bytes[i * 3 + c];
-    } else if (inside && d.mode == 1 && ((d.w * 3) & 15) == 0 && (rx0 & 7) == 0) {
+    } else if (inside && mode == 1 && ((d.w * 3) & 15) == 0 && (rx0 & 7) == 0) {
       // exact 2x: (a + b + c + d + 2) >> 2 over 2 source rows x 16 source pixels = 2 x 48 contiguous bytes
       const uint4* r0 = reinterpret_cast<const uint4*>(d.src + (static_cast<size_t>(2 * ry) * d.w + 2 * rx0) * 3);
       const uint4* r1 = reinterpret_cast<const uint4*>(d.src + (static_cast<size_t>(2 * ry + 1) * d.w + 2 * rx0) * 3);
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const ImageDesc* __rest
         const int rx = rx0 + i;
         const bool in = row_in && rx >= 0 && rx < d.new_w;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) px[i][c] = in ? static_cast<uint8_t>(resized_px(d, ry, rx, c)) : 0;
+        for (int c = 0; c < 3; ++c) px[i][c] = in ? static_cast<uint8_t>(resized_px(d, mode, ry, rx, c)) : 0;
       }
     }
     uint8_t* so = s_out + (x8 >> 1) * kPrePatchBytes + row * 32 + (x8 & 1) * 16;

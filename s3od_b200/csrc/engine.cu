@@ -793,8 +793,12 @@ int s3od_preprocess_u8(s3od_ctx* c, const s3od_image* images, int batch, s3od_st
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CK(cudaMemcpyAsync(c->d_img, images, sizeof(ImageDesc) * batch, cudaMemcpyHostToDevice, st));
   if (profile_mark(c, static_cast<int>(c->plan.size()), batch, st, true) != S3OD_OK) return S3OD_ERR_CUDA;
+  int common_mode = images[0].mode;
+  for (int i = 1; i < batch; ++i)
+    if (images[i].mode != common_mode) common_mode = 2;
+  if (common_mode < 0 || common_mode > 2) return fail(S3OD_ERR_ARG, "bad resize mode in s3od_preprocess_u8");
   CK(launch_preprocess(c->d_img, wptr<bf16>(c, "pre.lut"), c->pre_affine ? c->pre_ab : nullptr, aptr<bf16>(c, "patches"), c->S, batch,
-                       st));
+                       common_mode, st));
   if (profile_mark(c, static_cast<int>(c->plan.size()), batch, st, false) != S3OD_OK) return S3OD_ERR_CUDA;
   c->launches += 1;
   return S3OD_OK;
@@ -1094,6 +1098,17 @@ size_t s3od_metrics_stats_bytes(void) { return sod_stats_bytes(); }
 size_t s3od_metrics_region_bytes(void) { return sod_region_bytes(); }
 
 // ---- visualisation: device-resident composites of visualizer.py and the pair counts behind is_ambiguous
+int s3od_threshold_f32(const float* d_in, float* d_out, size_t n, float threshold, s3od_stream stream) {
+  if ((d_in == nullptr || d_out == nullptr) && n > 0) return fail(S3OD_ERR_ARG, "bad argument for s3od_threshold_f32");
+  if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15)
+    return fail(S3OD_ERR_ARG, "s3od_threshold_f32 needs 16-byte aligned buffers");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(launch_threshold(d_in, d_out, n, threshold, sms, static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
 int s3od_vis_composite(const uint8_t* d_image, const float* d_mask, uint8_t* d_out, int h, int w, int bg_r, int bg_g, int bg_b,
                        s3od_stream stream) {
   if (d_image == nullptr || d_mask == nullptr || d_out == nullptr || h < 0 || w < 0) return fail(S3OD_ERR_ARG, "bad argument for s3od_vis_composite");

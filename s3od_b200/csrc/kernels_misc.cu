@@ -3,6 +3,8 @@
 #include "elementwise.cuh"
 #include "visualize.cuh"
 #include "metrics.cuh"
+#include <algorithm>
+
 #include "launch.h"
 
 #include <cstdlib>
@@ -47,17 +49,25 @@ cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, const float* affine, __nv_bfloat16* patches, int S,
-                              int B, cudaStream_t stream) {
-  const int g = S / 16;
-  const dim3 grid((g + 7) / 8, g, B);
+template <int MODE>
+static void launch_preprocess_mode(dim3 grid, const ImageDesc* descs, const __nv_bfloat16* lut, const float* affine,
+                                   __nv_bfloat16* patches, int S, cudaStream_t stream) {
   if (affine != nullptr) {
     PreAffine aff;
     for (int c = 0; c < 3; ++c) { aff.a[c] = affine[c]; aff.b[c] = affine[3 + c]; }
-    preprocess_kernel<true><<<grid, 256, 0, stream>>>(descs, lut, aff, patches, S);
+    preprocess_kernel<true, MODE><<<grid, 256, 0, stream>>>(descs, lut, aff, patches, S);
   } else {
-    preprocess_kernel<false><<<grid, 256, 0, stream>>>(descs, lut, PreAffine{}, patches, S);
+    preprocess_kernel<false, MODE><<<grid, 256, 0, stream>>>(descs, lut, PreAffine{}, patches, S);
   }
+}
+
+cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, const float* affine, __nv_bfloat16* patches, int S,
+                              int B, int common_mode, cudaStream_t stream) {
+  const int g = S / 16;
+  const dim3 grid((g + 7) / 8, g, B);
+  if (common_mode == 0) launch_preprocess_mode<0>(grid, descs, lut, affine, patches, S, stream);
+  else if (common_mode == 1) launch_preprocess_mode<1>(grid, descs, lut, affine, patches, S, stream);
+  else launch_preprocess_mode<2>(grid, descs, lut, affine, patches, S, stream);
   return cudaGetLastError();
 }
 
@@ -142,6 +152,14 @@ cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, 
   return cudaGetLastError();
 }
 
+
+cudaError_t launch_threshold(const float* in, float* out, size_t n, float thr, int num_sms, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  size_t blocks = (n / 4 + 255) / 256;
+  blocks = std::max<size_t>(1, std::min<size_t>(blocks, static_cast<size_t>(16) * num_sms));
+  threshold_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(in, out, n, thr);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_sod_stats(const float* pred, const float* mask, int H, int W, const float* thresholds, void* stats, int num_sms,
                              cudaStream_t stream) {

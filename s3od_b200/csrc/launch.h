@@ -34,8 +34,9 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
 cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,
                              int ntok, int D, float eps, cudaStream_t stream);
 // affine = host pointer to {a0, a1, a2, b0, b1, b2} (normalisation as fma(v, a, b)), or nullptr for the table look-up
+// common_mode = the resize mode shared by every image of the batch (0 copy, 1 exact 2x), or 2 = read it per image
 cudaError_t launch_preprocess(const ImageDesc* descs, const __nv_bfloat16* lut, const float* affine, __nv_bfloat16* patches, int S,
-                              int B, cudaStream_t stream);
+                              int B, int common_mode, cudaStream_t stream);
 cudaError_t launch_pack_input(const float* x, __nv_bfloat16* patches, int S, int B, cudaStream_t stream);
 cudaError_t launch_fill_prefix(float* x, const float* prefix, int ntok, int D, int B, cudaStream_t stream);
 cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float* pool, int pool_blocks, int B, int h, int w,
@@ -49,6 +50,7 @@ cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, 
                                int tile_cols, cudaStream_t stream);
 
 // saliency metrics (metrics.cuh)
+cudaError_t launch_threshold(const float* in, float* out, size_t n, float thr, int num_sms, cudaStream_t stream);
 cudaError_t launch_sod_stats(const float* pred, const float* mask, int H, int W, const float* thresholds, void* stats, int num_sms,
                              cudaStream_t stream);
 cudaError_t launch_sod_region(const float* pred, const float* mask, int H, int W, int X, int Y, void* region, int num_sms,

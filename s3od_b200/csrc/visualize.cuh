@@ -116,4 +116,19 @@ __global__ void __launch_bounds__(256) mask_pair_counts_kernel(const float* __re
   }
 }
 
+// SODPredictor.predict tail (synth_sod/model_training/predictor.py:461-470): binary = (soft > threshold) as float32.
+// Thread = 4 values, grid-stride; n need not be a multiple of 4.
+__global__ void __launch_bounds__(256) threshold_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, float thr) {
+  const size_t n4 = n >> 2;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(in) + i);
+    __stcs(reinterpret_cast<float4*>(out) + i,
+           make_float4(v.x > thr ? 1.0f : 0.0f, v.y > thr ? 1.0f : 0.0f, v.z > thr ? 1.0f : 0.0f, v.w > thr ? 1.0f : 0.0f));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const size_t i = (n4 << 2) + threadIdx.x;
+    out[i] = in[i] > thr ? 1.0f : 0.0f;
+  }
+}
+
 }  // namespace s3od

@@ -74,6 +74,7 @@ def load_library() -> ctypes.CDLL:
     lib.s3od_metrics_region.argtypes = [vp, vp, ci, ci, ci, ci, vp, ctypes.c_size_t, vp]
     lib.s3od_metrics_stats_bytes.restype = ctypes.c_size_t
     lib.s3od_metrics_region_bytes.restype = ctypes.c_size_t
+    lib.s3od_threshold_f32.argtypes = [vp, vp, ctypes.c_size_t, cf, vp]
     lib.s3od_vis_composite.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
     lib.s3od_vis_mask_grid.argtypes = [vp, vp, ci, vp, ci, ci, vp]
     lib.s3od_mask_pair_counts.argtypes = [vp, ci, ci, ci, vp, vp]
@@ -99,7 +100,7 @@ class B200DPTSegmentation:
     """Device model: packed weights + launch plan inside the CUDA library."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int = 1024, device: str = "cuda:0",
-                 max_batch: int = 1, micro_batch: Optional[int] = None):
+                 max_batch: int = 1, micro_batch: Optional[int] = None, normalisation: str = "s3od"):
         if not torch.cuda.is_available():
             raise RuntimeError("s3od_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = load_library()
@@ -118,7 +119,7 @@ class B200DPTSegmentation:
         with torch.cuda.device(self.dev_index):
             _check(self.lib, self.lib.s3od_create(ctypes.byref(self._ctx), self.dev_index, arch_id, self.K, self.image_size,
                                                   self.max_batch, self.micro_batch), "s3od_create")
-            for name, t in pack_weights(state_dict, arch, self.image_size).items():
+            for name, t in pack_weights(state_dict, arch, self.image_size, normalisation).items():
                 t = t.contiguous()
                 _check(self.lib, self.lib.s3od_set_tensor(self._ctx, name.encode(), t.data_ptr(), t.numel() * t.element_size()),
                        f"s3od_set_tensor({name})")
@@ -185,14 +186,17 @@ class B200DPTSegmentation:
         check_padding(pad, S)
         return pad
 
-    def preprocess(self, d_images: Sequence[torch.Tensor]) -> List[dict]:
-        """_preprocess (predictor.py:79-94) for uint8 (H,W,3) tensors already on the device; stages the model input."""
+    def preprocess(self, d_images: Sequence[torch.Tensor], placements: Optional[Sequence[dict]] = None) -> List[dict]:
+        """_preprocess (predictor.py:79-94) for uint8 (H,W,3) tensors already on the device; stages the model input.
+        `placements` (same keys as pad_info: resized_size, height_pad = top, width_pad = left) overrides the reference
+        letterbox geometry - SODPredictor's albumentations front end rounds and pads differently; pixels that fall outside
+        the image_size x image_size canvas are dropped."""
         B = len(d_images)
         descs = (S3odImage * B)()
         pads = []
         for i, img in enumerate(d_images):
             h, w = int(img.shape[0]), int(img.shape[1])
-            pad = self.geometry(h, w)
+            pad = self.geometry(h, w) if placements is None else placements[i]
             new_h, new_w = pad["resized_size"]
             mode = geometry.resize_mode(h, w, new_h, new_w)
             xt = yt = None
@@ -263,6 +267,15 @@ class B200DPTSegmentation:
             label, n, imgs, ms = line.split("\t")
             rows.append((label, int(n), int(imgs), float(ms)))
         return rows
+
+    def threshold(self, soft: torch.Tensor, threshold: float) -> torch.Tensor:
+        """(soft > threshold) as float32 on the device (SODPredictor.predict, synth_sod/.../predictor.py:461-470)."""
+        soft = soft.contiguous()
+        out = torch.empty_like(soft)
+        with torch.cuda.device(self.dev_index):
+            _check(self.lib, self.lib.s3od_threshold_f32(soft.data_ptr(), out.data_ptr(), soft.numel(), float(threshold),
+                                                         _stream_ptr(self.device)), "s3od_threshold_f32")
+        return out
 
     def preprocess_mode(self) -> int:
         """1 = normalisation as one FMA (verified against the table by the library), 0 = table look-up."""

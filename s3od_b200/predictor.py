@@ -8,6 +8,7 @@ the odd-padding inputs the reference cannot paste).  Additive surfac
 Everything between the uint8 source image and the result arrays runs in the CUDA library: letterbox resize + normalise,
 the DINOv3 ViT + DPT head forward, sigmoid / crop / antialiased resize / argmax / RGBA composite.
 """
+import threading
 from dataclasses import dataclass
 from pathlib import Path
 from typing import List, Optional, Sequence, Union
@@ -72,6 +73,9 @@ class BackgroundRemoval:
         self.model.eval()
         self.mean = np.array([0.485, 0.456, 0.406])
         self.std = np.array([0.229, 0.224, 0.225])
+        # one shared instance may be called from several threads (the reference's Gradio demo does, demo/app.py:18-25): the
+        # context's workspace and output slots serve one call at a time
+        self._lock = threading.Lock()
 
     @classmethod
     def from_pretrained(cls, model_id: str, **kwargs):
@@ -114,6 +118,10 @@ class BackgroundRemoval:
         Images go through the device in chunks of the model's micro-batch; the device-to-host copies of a chunk's
         results run on a side stream into pinned memory while the next chunk computes."""
         arrays = [np.ascontiguousarray(self._to_uint8(im)) for im in images]
+        with self._lock:
+            return self._run_batch(arrays)
+
+    def _run_batch(self, arrays: List[np.ndarray]) -> List[RemovalResult]:
         model = self.model
         dev = model.device
         for a in arrays:                                        # raise before touching the GPU, like the reference's paste

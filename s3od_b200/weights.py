@@ -95,7 +95,28 @@ def convt_rows_weights(wt: torch.Tensor) -> torch.Tensor:
     return torch.cat(blocks, dim=0)
 
 
-def pack_weights(sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int) -> Dict[str, torch.Tensor]:
+def albumentations_lut() -> torch.Tensor:
+    """bf16[3*256] of `A.Normalize(mean, std)` on uint8 input, the front end of the training-side SODPredictor
+    (synth_sod/.../predictor.py:355): float32 throughout - `img.astype(f32)`, `img -= mean * 255`, `img *= 1 / (std * 255)`
+    with mean / std float32 arrays.  albumentations is not installed here, so this arithmetic is restated from its
+    published functional `normalize` (parity unpinned, see oracle/sod_predictor.py)."""
+    f32 = np.float32
+    mean = np.array([0.485, 0.456, 0.406], dtype=f32) * f32(255.0)
+    den = np.reciprocal(np.array([0.229, 0.224, 0.225], dtype=f32) * f32(255.0), dtype=f32)
+    v = np.arange(256, dtype=np.uint8).astype(f32)
+    lut = ((v[None, :] - mean[:, None]).astype(f32) * den[:, None]).astype(f32)
+    return torch.from_numpy(lut).reshape(-1).to(torch.bfloat16).contiguous()
+
+
+def albumentations_affine() -> torch.Tensor:
+    """fp32[6] hint for the table above: (v - m) * d ~= fma(v, d, -m * d); only used if it reproduces the table."""
+    f32 = np.float32
+    mean = np.array([0.485, 0.456, 0.406], dtype=f32) * f32(255.0)
+    den = np.reciprocal(np.array([0.229, 0.224, 0.225], dtype=f32) * f32(255.0), dtype=f32)
+    return torch.from_numpy(np.concatenate([den, (-mean.astype(np.float64) * den.astype(np.float64)).astype(f32)])).contiguous()
+
+
+def pack_weights(sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int, normalisation: str = "s3od") -> Dict[str, torch.Tensor]:
     D, I, K = arch.hidden, arch.mlp, arch.num_outputs
     out: Dict[str, torch.Tensor] = {}
     e = "encoder.embeddings."
@@ -104,8 +125,14 @@ def pack_weights(sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int) -
     out["prefix"] = _f32(torch.cat([sd[e + "cls_token"].reshape(1, D), sd[e + "register_tokens"].reshape(-1, D)], 0))
     g = image_size // arch.patch
     out["rope.cos"], out["rope.sin"] = rope_tables(g, g, arch.head_dim, arch.rope_theta)
-    out["pre.lut"] = normalisation_lut()
-    out["pre.affine"] = normalisation_affine()      # optional fast form; the library verifies it against pre.lut
+    if normalisation == "s3od":                     # BackgroundRemoval._preprocess (src/s3od/predictor.py:91)
+        out["pre.lut"] = normalisation_lut()
+        out["pre.affine"] = normalisation_affine()  # optional fast form; the library verifies it against pre.lut
+    elif normalisation == "albumentations":         # SODPredictor's A.Normalize (synth_sod/.../predictor.py:355)
+        out["pre.lut"] = albumentations_lut()
+        out["pre.affine"] = albumentations_affine()
+    else:
+        raise ValueError(f"unknown normalisation {normalisation!r}")
 
     pre = _enc_prefix(sd)
     for l in range(arch.layers_needed):                                               # layer 12 / final norm are dead (F3)

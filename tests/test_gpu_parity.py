@@ -270,6 +270,28 @@ def test_batch_api_matches_single_calls(predictors):
         np.testing.assert_array_equal(np.array(rs.rgba_image), np.array(rb.rgba_image))
 
 
+def test_shared_instance_from_several_threads(predictors):
+    """The reference's demo calls one shared predictor from worker threads (demo/app.py:18-25): calls are serialised."""
+    import threading
+    br = predictors(64, max_batch=4, micro_batch=2)
+    imgs = [synth_image((64, 128, 96)[i % 3], 64, seed=80 + i) for i in range(6)]
+    want = [br.remove_background(im) for im in imgs]
+    got = [None] * len(imgs)
+
+    def work(i):
+        for _ in range(3):
+            got[i] = br.remove_background(imgs[i])
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(imgs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for w, g in zip(want, got):
+        np.testing.assert_array_equal(w.all_masks, g.all_masks)
+        np.testing.assert_array_equal(w.all_ious, g.all_ious)
+        np.testing.assert_array_equal(np.array(w.rgba_image), np.array(g.rgba_image))
+
+
 def test_full_size_against_reference_golden(predictors, golden_dir):
     """BASELINE.json config 0/1 shape: image_size 1024, one 1024x1024 image; sub-sampled reference outputs."""
     g = np.load(os.path.join(golden_dir, "full_s1024.npz"))
