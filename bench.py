@@ -217,7 +217,7 @@ def run_b200(args, rank, local_rank, world):
     # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (same command, same micro-batch)
     traffic = None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01b_traffic.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01d_traffic.json")) as f:
             t = json.load(f).get(dom)
         if t and t["micro_batch"] == model.micro_batch and t["model"] == args.model and t["image_size"] == S:
             traffic = t["dram_bytes_per_launch"]
@@ -304,7 +304,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE.json configs[1])")
     ap.add_argument("--image-size", type=int, default=1024)
     ap.add_argument("--source", type=int, default=1024, help="source image side (2048 = configs[2] shape)")
-    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--model", default="dinob", choices=["dinob", "dinol"], help="dinol = ViT-L backbone, one mask (BASELINE.json configs[4])")
     ap.add_argument("--dump-profile", default=None, help="write the per-kernel CUDA-event table (label, launches, images, ms) here")
