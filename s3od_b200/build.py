@@ -38,11 +38,12 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
         return LIB_PATH
     nvcc = _nvcc()
+    extra = os.environ.get("S3OD_NVCC_FLAGS", "").split()       # experiments only (e.g. -DS3OD_ATTN_POLY_EVERY=4)
     objs = [os.path.join(LIB_DIR, s.replace(".cu", ".o")) for s in SOURCES]
 
     def compile_one(args):
         src, obj = args
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

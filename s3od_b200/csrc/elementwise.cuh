@@ -228,10 +228,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
 // grid = (blocks_per_image, B), block = 256 threads = (C/8) channel groups x (256 / (C/8)) input columns; a block walks
 // work units (8-column tile, kUpsRows-row strip) grid-stride.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kUpsRows = 32;
+#ifndef S3OD_UPS_ROWS
+#define S3OD_UPS_ROWS 32
+#endif
+#ifndef S3OD_UPS_MINBLOCKS
+#define S3OD_UPS_MINBLOCKS 2
+#endif
+#ifndef S3OD_UPS_STREAM
+#define S3OD_UPS_STREAM 0
+#endif
+constexpr int kUpsRows = S3OD_UPS_ROWS;
 
 template <int C>
-__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256, S3OD_UPS_MINBLOCKS) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                          float* __restrict__ pool, int h, int w) {
   constexpr int CG = C / 8;                 // channel groups (threads along channels)
   constexpr int PP = 256 / CG;              // input columns per block
@@ -295,10 +304,17 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __
       }
       __nv_bfloat16* o0 = ob + (static_cast<size_t>(2 * iy) * OW + 2 * ix) * C;
       __nv_bfloat16* o1 = o0 + static_cast<size_t>(OW) * C;
+#if S3OD_UPS_STREAM
+      __stcs(reinterpret_cast<uint4*>(o0), make_uint4(o00[0], o00[1], o00[2], o00[3]));
+      __stcs(reinterpret_cast<uint4*>(o0 + C), make_uint4(o01[0], o01[1], o01[2], o01[3]));
+      __stcs(reinterpret_cast<uint4*>(o1), make_uint4(o10[0], o10[1], o10[2], o10[3]));
+      __stcs(reinterpret_cast<uint4*>(o1 + C), make_uint4(o11[0], o11[1], o11[2], o11[3]));
+#else
       *reinterpret_cast<uint4*>(o0) = make_uint4(o00[0], o00[1], o00[2], o00[3]);
       *reinterpret_cast<uint4*>(o0 + C) = make_uint4(o01[0], o01[1], o01[2], o01[3]);
       *reinterpret_cast<uint4*>(o1) = make_uint4(o10[0], o10[1], o10[2], o10[3]);
       *reinterpret_cast<uint4*>(o1 + C) = make_uint4(o11[0], o11[1], o11[2], o11[3]);
+#endif
     };
     float La[8], Ra[8], Lb[8], Rb[8], Lc[8], Rc[8];
     hrow(max(y0 - 1, 0), La, Ra);
