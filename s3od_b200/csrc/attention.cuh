@@ -180,17 +180,26 @@ S3OD_DEVICE void row_max2(const uint32_t (&r)[kAttnRegs], int nvq, float& mxa, f
   mxb = fmaxf(b0, b1);
 }
 
-// exp2 of repetitions [I0, I1) against the two row references -> packed bf16 pairs w[2i], w[2i+1]; adds to the row sums
+// exp2 of repetitions [I0, I1) against the two row references -> packed bf16 pairs w[2i], w[2i+1]; adds to the row sums.
+// nma2 / nmb2 = (-m_ref, -m_ref) of the thread's two rows; sa2 / sb2 = two partial row sums each (packed fp32 pairs: the
+// subtraction and the accumulation of two scores are ONE instruction each - 12 instead of 16 issue slots per 4 scores).
 template <int I0, int I1, bool kMasked>
-S3OD_DEVICE void softmax_reps(const uint32_t (&r)[kAttnRegs], float ma, float mb, int nvq, uint32_t (&w)[kAttnRegs / 2], float& sa,
-                              float& sb) {
+S3OD_DEVICE void softmax_reps(const uint32_t (&r)[kAttnRegs], uint64_t nma2, uint64_t nmb2, int nvq, uint32_t (&w)[kAttnRegs / 2],
+                              uint64_t& sa2, uint64_t& sb2) {
 #pragma unroll
   for (int i = I0; i < I1; ++i) {
-    const float ma_ = (S3OD_ATTN_LAB & 64) ? 0.0f : ma, mb_ = (S3OD_ATTN_LAB & 64) ? 0.0f : mb;     // lab: no subtraction
-    float e0 = exp2_sel(__uint_as_float(r[4 * i + 0]) - ma_, 4 * i + 0);
-    float e1 = exp2_sel(__uint_as_float(r[4 * i + 1]) - ma_, 4 * i + 1);
-    float e2 = exp2_sel(__uint_as_float(r[4 * i + 2]) - mb_, 4 * i + 2);
-    float e3 = exp2_sel(__uint_as_float(r[4 * i + 3]) - mb_, 4 * i + 3);
+    float x0, x1, x2, x3;
+    if (S3OD_ATTN_LAB & 64) {                           // lab: no subtraction
+      x0 = __uint_as_float(r[4 * i + 0]); x1 = __uint_as_float(r[4 * i + 1]);
+      x2 = __uint_as_float(r[4 * i + 2]); x3 = __uint_as_float(r[4 * i + 3]);
+    } else {
+      f2_unpack(f2_add(f2_pack(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1])), nma2), x0, x1);
+      f2_unpack(f2_add(f2_pack(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), nmb2), x2, x3);
+    }
+    float e0 = exp2_sel(x0, 4 * i + 0);
+    float e1 = exp2_sel(x1, 4 * i + 1);
+    float e2 = exp2_sel(x2, 4 * i + 2);
+    float e3 = exp2_sel(x3, 4 * i + 3);
     if (kMasked) {
       const bool v0 = 8 * i < nvq, v1 = 8 * i + 1 < nvq;
       e0 = v0 ? e0 : 0.0f;
@@ -198,12 +207,9 @@ S3OD_DEVICE void softmax_reps(const uint32_t (&r)[kAttnRegs], float ma, float mb
       e2 = v0 ? e2 : 0.0f;
       e3 = v1 ? e3 : 0.0f;
     }
-    if (!(S3OD_ATTN_LAB & 32)) {                        // lab: no row sums
-      sa += e0 + e1;
-      sb += e2 + e3;
-    } else if (i == 0) {
-      sa += e0;
-      sb += e2;
+    if (!(S3OD_ATTN_LAB & 32) || i == 0) {              // lab: no row sums
+      sa2 = f2_add(sa2, f2_pack(e0, e1));
+      sb2 = f2_add(sb2, f2_pack(e2, e3));
     }
     w[2 * i] = pack_bf16x2(e0, e1);
     w[2 * i + 1] = pack_bf16x2(e2, e3);
@@ -451,12 +457,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       if (warp == 0) S3OD_STAMP(2);
 
       // ---- P = exp2(S - m_ref) as packed bf16 into tensor memory, row sums
-      softmax_reps<0, 4, kMasked>(ra, ma, mb, nvq, w, la, lb);
+      const uint64_t nma2 = f2_pack(-ma, -ma), nmb2 = f2_pack(-mb, -mb);
+      uint64_t sa2 = f2_pack(la, 0.0f), sb2 = f2_pack(lb, 0.0f);
+      softmax_reps<0, 4, kMasked>(ra, nma2, nmb2, nvq, w, sa2, sb2);
       tmem_st_16x128_x4<0>(p_addr, w);
-      softmax_reps<4, 8, kMasked>(ra, ma, mb, nvq, w, la, lb);
+      softmax_reps<4, 8, kMasked>(ra, nma2, nmb2, nvq, w, sa2, sb2);
       tmem_st_16x128_x4<8>(p_addr + 16, w);
-      softmax_reps<8, 12, kMasked>(ra, ma, mb, nvq, w, la, lb);
+      softmax_reps<8, 12, kMasked>(ra, nma2, nmb2, nvq, w, sa2, sb2);
       tmem_st_16x128_x4<16>(p_addr + 32, w);
+      {
+        float s0, s1;
+        f2_unpack(sa2, s0, s1);
+        la = s0 + s1;
+        f2_unpack(sb2, s0, s1);
+        lb = s0 + s1;
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[j & 1]);

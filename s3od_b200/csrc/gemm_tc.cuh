@@ -479,9 +479,13 @@ struct EpiGelu {
     for (int c = 0; c < NCOLS; c += 32) {
       float v[32];
       tmem_ld_f32x32(taddr + c, v);
-      add_vec32(e.bias + n0 + c, v);
+      const float4* bs = reinterpret_cast<const float4*>(e.bias + n0 + c);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      for (int q = 0; q < 8; ++q) {                   // bias + GELU on packed fp32 pairs
+        const float4 bq = __ldg(bs + q);
+        f2_unpack(gelu_erf2(f2_add(f2_pack(v[4 * q + 0], v[4 * q + 1]), f2_pack(bq.x, bq.y))), v[4 * q + 0], v[4 * q + 1]);
+        f2_unpack(gelu_erf2(f2_add(f2_pack(v[4 * q + 2], v[4 * q + 3]), f2_pack(bq.z, bq.w))), v[4 * q + 2], v[4 * q + 3]);
+      }
       uint32_t w[16];
       pack_bf16x32(v, w);
       stg.write(w);
