@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -794,9 +795,20 @@ int s3od_preprocess_u8(s3od_ctx* c, const s3od_image* images, int batch, s3od_st
   CK(cudaMemcpyAsync(c->d_img, images, sizeof(ImageDesc) * batch, cudaMemcpyHostToDevice, st));
   if (profile_mark(c, static_cast<int>(c->plan.size()), batch, st, true) != S3OD_OK) return S3OD_ERR_CUDA;
   int common_mode = images[0].mode;
-  for (int i = 1; i < batch; ++i)
-    if (images[i].mode != common_mode) common_mode = 2;
-  if (common_mode < 0 || common_mode > 2) return fail(S3OD_ERR_ARG, "bad resize mode in s3od_preprocess_u8");
+  for (int i = 0; i < batch; ++i) {
+    const s3od_image& im = images[i];
+    if (im.mode != common_mode) common_mode = 2;
+    // the vector paths read the source with 8- / 16-byte loads relative to d_src
+    if (im.d_src == nullptr || (reinterpret_cast<uintptr_t>(im.d_src) & 15) != 0)
+      return fail(S3OD_ERR_ARG, "s3od_preprocess_u8: d_src must be a 16-byte aligned device pointer");
+    if (im.mode < 0 || im.mode > 2 || im.h < 1 || im.w < 1 || im.new_h < 1 || im.new_w < 1 || im.pad_h < 0 || im.pad_w < 0)
+      return fail(S3OD_ERR_ARG, "s3od_preprocess_u8: bad image geometry / resize mode");
+    if (im.mode == 0 && (im.new_h != im.h || im.new_w != im.w)) return fail(S3OD_ERR_ARG, "s3od_preprocess_u8: mode 0 needs new size == size");
+    if (im.mode == 1 && (2 * im.new_h != im.h || 2 * im.new_w != im.w))
+      return fail(S3OD_ERR_ARG, "s3od_preprocess_u8: mode 1 needs size == 2 x new size");
+    if (im.mode == 2 && (im.d_xtab == nullptr || im.d_ytab == nullptr))
+      return fail(S3OD_ERR_ARG, "s3od_preprocess_u8: mode 2 needs the coefficient tables");
+  }
   CK(launch_preprocess(c->d_img, wptr<bf16>(c, "pre.lut"), c->pre_affine ? c->pre_ab : nullptr, aptr<bf16>(c, "patches"), c->S, batch,
                        common_mode, st));
   if (profile_mark(c, static_cast<int>(c->plan.size()), batch, st, false) != S3OD_OK) return S3OD_ERR_CUDA;
@@ -849,6 +861,7 @@ int s3od_postprocess(s3od_ctx* c, const float* d_mask_logits, const float* d_iou
   if (images == nullptr || batch < 1 || batch > c->max_batch || d_mask_logits == nullptr || d_iou_logits == nullptr ||
       d_ious == nullptr || d_best_idx == nullptr)
     return fail(S3OD_ERR_ARG, "bad argument to s3od_postprocess");
+  if ((reinterpret_cast<uintptr_t>(d_mask_logits) & 15) != 0) return fail(S3OD_ERR_ARG, "s3od_postprocess: d_mask_logits must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int maxH = 0, maxW = 0;
   bool mult4 = true;
@@ -862,7 +875,15 @@ int s3od_postprocess(s3od_ctx* c, const float* d_mask_logits, const float* d_iou
     maxW = std::max(maxW, im.W);
     mult4 = mult4 && (im.W % 4 == 0);
     const int in_h = c->S - 2 * im.pad_h, in_w = c->S - 2 * im.pad_w;
-    if (im.H < 1 || im.W < 1 || in_h < 1 || in_w < 1) return fail(S3OD_ERR_ARG, "bad image geometry in s3od_postprocess");
+    if (im.H < 1 || im.W < 1 || in_h < 1 || in_w < 1 || im.pad_h < 0 || im.pad_w < 0 || im.ky < 1 || im.kx < 1)
+      return fail(S3OD_ERR_ARG, "bad image geometry in s3od_postprocess");
+    if (im.d_src == nullptr || im.d_all_masks == nullptr || im.d_rgba == nullptr || im.d_ystart == nullptr || im.d_yw == nullptr ||
+        im.d_xstart == nullptr || im.d_xw == nullptr)
+      return fail(S3OD_ERR_ARG, "null pointer in s3od_postprocess image descriptor");
+    // 128-bit stores of the mask planes / RGBA pixels and 32-bit loads of the RGB source
+    if (((reinterpret_cast<uintptr_t>(im.d_all_masks) | reinterpret_cast<uintptr_t>(im.d_rgba)) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(im.d_src) & 3) != 0)
+      return fail(S3OD_ERR_ARG, "s3od_postprocess: d_all_masks / d_rgba must be 16-byte aligned, d_src 4-byte aligned");
     tile_ok = tile_ok && im.ky <= 3 && im.kx <= 3 && im.H >= in_h && im.W >= in_w;
     // scale exactly 1: ATen's table is (first tap i, weights 1, 0), the resize is a copy of the cropped mask
     identity = identity && im.H == in_h && im.W == in_w && im.pad_w % 4 == 0 && im.ky <= 2 && im.kx <= 2;

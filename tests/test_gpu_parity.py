@@ -270,6 +270,23 @@ def test_batch_api_matches_single_calls(predictors):
         np.testing.assert_array_equal(np.array(rs.rgba_image), np.array(rb.rgba_image))
 
 
+def test_c_abi_rejects_misaligned_buffers(models):
+    """The vector paths of the pre / post-process kernels need aligned buffers: the C ABI refuses anything else (ValueError)."""
+    m = models(64)
+    raw = torch.zeros(64 * 64 * 3 + 1, dtype=torch.uint8, device="cuda")
+    skewed = raw[1:].view(64, 64, 3)                                   # contiguous, data_ptr % 16 == 1
+    with pytest.raises(ValueError):
+        m.preprocess([skewed])
+    logits = torch.zeros(1, 3, 64, 64, device="cuda")
+    pad = dict(height_pad=0, width_pad=0, original_size=(64, 64), resized_size=(64, 64))
+    with pytest.raises(ValueError):
+        m.postprocess(logits, torch.zeros(1, 3, device="cuda"), [skewed], [pad])
+    good = raw[:64 * 64 * 3].view(64, 64, 3)
+    m.preprocess([good])
+    m.postprocess(logits, torch.zeros(1, 3, device="cuda"), [good], [pad])
+    torch.cuda.synchronize()
+
+
 def test_shared_instance_from_several_threads(predictors):
     """The reference's demo calls one shared predictor from worker threads (demo/app.py:18-25): calls are serialised."""
     import threading

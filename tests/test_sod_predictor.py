@@ -95,18 +95,22 @@ def test_predict_matches_oracle(tmp_path, vitb_sd, h, w, S, lightning):
 
 @pytest.mark.gpu
 def test_single_output_model_returns_no_all_masks(tmp_path):
+    """num_outputs == 1 branch (predictor.py:451-456); the shapes take the K = 1 instantiations of the tile, identity, exact-2x
+    and per-pixel post-process kernels."""
     from dataclasses import replace
     arch = replace(VITB, num_outputs=1)
     sd = synth_state_dict(arch, 3)
-    img = synth_image(80, 64, seed=5)
-    ref = osp.predict(sd, img, arch, 64, 0.4)
     p = tmp_path / "one.pt"
     torch.save({"state_dict": sd}, p)
     pred = SODPredictor(str(p), image_size=64, device="cuda:0")
-    got = pred.predict(img, 0.4)
-    assert got.all_masks is None and got.all_ious is None and not got.has_multiple_masks
-    assert np.abs(got.soft_mask - ref["soft_mask"]).max() <= 4e-2
-    np.testing.assert_array_equal(got.binary_mask, (got.soft_mask > 0.4).astype(np.float32))
+    for h, w in [(80, 64), (64, 64), (128, 128), (40, 30), (50, 70)]:
+        img = synth_image(h, w, seed=5 + h)
+        ref = osp.predict(sd, img, arch, 64, 0.4)
+        got = pred.predict(img, 0.4)
+        assert got.all_masks is None and got.all_ious is None and not got.has_multiple_masks
+        assert got.soft_mask.shape == (h, w)
+        assert np.abs(got.soft_mask - ref["soft_mask"]).max() <= 4e-2
+        np.testing.assert_array_equal(got.binary_mask, (got.soft_mask > 0.4).astype(np.float32))
     pred.model.close()
 
 
