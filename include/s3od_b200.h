@@ -103,7 +103,7 @@ const char* s3od_version(void);
 /* ---- saliency metrics on the device: the reductions of EvaluationMetrics.step
  * (synth_sod/model_training/metrics.py:213-421).  d_pred, d_mask: (h, w) fp32.
  * s3od_metrics_stats fills (layout of struct SodStats, csrc/metrics.cuh; all 8-byte fields):
- *     double abs_err, sum_p, sum_y, fg_p, fg_p2, bg_q, bg_q2;  uint64 n_fg, sum_mx, sum_my;  uint64 hist_cnt[256];  double hist_y[256]
+ *     double abs_err, sum_p, sum_y, fg_p, fg_p2, bg_q, bg_q2;  uint64 n_fg, sum_mx, sum_my;  uint64 hist_cnt[256];  double hist_y[256];  uint64 em_all[256], em_fg[256] (E-measure histograms of uint8(pred * 255), metrics.py:80-110)
  *   hist bin = number of the 255 thresholds (d_thresholds, ascending) that are <= pred: replaces the 255-pass `_eval_pr`
  *   (metrics.py:316-327); the fg / bg moments feed `_S_object` (:329-344), n_fg / sum_mx / sum_my the centroid (:358-378).
  * s3od_metrics_region fills struct SodRegion { double sp[4], sm[4], spp[4], smm[4], spm[4]; }: moments of pred and of the

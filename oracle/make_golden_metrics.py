@@ -2,7 +2,8 @@
 
 Run in the build container only:   python -m oracle.make_golden_metrics
 Loads /root/reference/synth_sod/src/synth_sod/model_training/metrics.py (unmodified) by path and records, per case, the
-values EvaluationMetrics.step appends to its lists (mae, max_f, avg_f, s_score)."""
+values EvaluationMetrics.step appends to its lists (mae, max_f, avg_f, s_score) and the 256 changeable E-measure values
+of EMeasure.step (metrics.py:23-33)."""
 import importlib.util
 import os
 
@@ -41,10 +42,15 @@ def main():
         names.append(name)
         rec[name + "_pred"], rec[name + "_mask"] = pred.numpy(), mask.numpy()
         rec[name + "_vals"] = np.array([em.metrics["mae"][0], em.metrics["max_f"][0], em.metrics["avg_f"][0], em.metrics["s_score"][0]], np.float64)
+        rec[name + "_ems"] = np.asarray(em.emeasure.metrics["changeable_ems"][0], np.float64)
         em2 = ref.EvaluationMetrics(device=None, sm_only=True)
         em2.step(pred.clone(), mask.clone())
         assert abs(em2.metrics["s_score"][0] - em.metrics["s_score"][0]) < 1e-7
         print(name, rec[name + "_vals"])
+    full = ref.EvaluationMetrics(device=None)
+    for name, pred, mask in cases():
+        full.step(pred.clone(), mask.clone())
+    rec["em_all_cases"] = np.float64(full.compute_metrics()["Em"])
     rec["names"] = np.array(names)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "metrics.npz"), **rec)
 

@@ -16,6 +16,9 @@ struct SodStats {                       // written by sod_stats_kernel (zero-ini
   unsigned long long n_fg, sum_mx, sum_my;   // |m|, sum m * x, sum m * y   (centroid, metrics.py:358-378)
   unsigned long long hist_cnt[256];     // pixels per bin
   double hist_y[256];                   // sum of y per bin
+  // E-measure (metrics.py:80-110, cal_em_with_cumsumhistogram): histograms of uint8(p * 255) over all pixels and over m == 1
+  unsigned long long em_all[256];
+  unsigned long long em_fg[256];
 };
 
 struct SodRegion {                      // per quadrant (LT, RT, LB, RB): moments of p and m for _ssim (metrics.py:405-421)
@@ -38,10 +41,13 @@ __global__ void __launch_bounds__(256) sod_stats_kernel(const float* __restrict_
   __shared__ float th[256];
   __shared__ unsigned int h_cnt[256];
   __shared__ float h_y[256];
+  __shared__ unsigned int e_all[256], e_fg[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     th[i] = i < 255 ? thresholds[i] : 3.0e38f;
     h_cnt[i] = 0;
     h_y[i] = 0.0f;
+    e_all[i] = 0;
+    e_fg[i] = 0;
   }
   __syncthreads();
   double a_err = 0, s_p = 0, s_y = 0, fp = 0, fp2 = 0, bq = 0, bq2 = 0;
@@ -60,7 +66,10 @@ __global__ void __launch_bounds__(256) sod_stats_kernel(const float* __restrict_
     }
     atomicAdd(&h_cnt[lo], 1u);
     if (y != 0.0f) atomicAdd(&h_y[lo], y);
+    const int eb = min(max(static_cast<int>(p * 255.0f), 0), 255);      // (pred * 255).astype(uint8) for p in [0, 1]
+    atomicAdd(&e_all[eb], 1u);
     if (y >= 0.5f) {
+      atomicAdd(&e_fg[eb], 1u);
       const float pf = p;
       fp += pf;
       fp2 += static_cast<double>(pf) * pf;
@@ -85,6 +94,8 @@ __global__ void __launch_bounds__(256) sod_stats_kernel(const float* __restrict_
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     if (h_cnt[i] != 0) atomicAdd(&out->hist_cnt[i], static_cast<unsigned long long>(h_cnt[i]));
     if (h_y[i] != 0.0f) atomicAdd(&out->hist_y[i], static_cast<double>(h_y[i]));
+    if (e_all[i] != 0) atomicAdd(&out->em_all[i], static_cast<unsigned long long>(e_all[i]));
+    if (e_fg[i] != 0) atomicAdd(&out->em_fg[i], static_cast<unsigned long long>(e_fg[i]));
   }
 }
 

@@ -5,9 +5,11 @@ instead of the reference's ~770 small torch kernels per image.
 
 Same surface: `EvaluationMetrics(device, sm_only=False)`, `step(pred, mask)`, `compute_metrics()`, `reset()`.
 Differences, on purpose: `step` does not binarise the caller's `mask` in place (the reference does, metrics.py:269-270);
-the E-measure and weighted F-measure, which the reference computes with numpy / scipy on the CPU after copying the
-tensors to the host (metrics.py:282-286), are not part of this path, so `compute_metrics()` returns MAE, MaxF, AvgF, Sm
-(or Sm alone with `sm_only=True`).  Values agree with the reference to float32 rounding (sums are accumulated in
+the E-measure (metrics.py:14-137: its cumulative-histogram form) is evaluated from two 256-bin histograms the same
+device pass produces instead of numpy on a host copy; the weighted F-measure (scipy distance transform + 7x7 Gaussian on
+the CPU in the reference, metrics.py:140-210) is not part of this path, so `compute_metrics()` returns MAE, MaxF, AvgF, Sm,
+Em (or Sm alone with `sm_only=True`) and no wFm.  The ground truth of the E-measure is `mask >= 0.5`, which for masks in
+[0, 1] is what the reference's in-place binarisation followed by `gt > 0` amounts to.  Values agree with the reference to float32 rounding (sums are accumulated in
 double here, in float32 there).  There is no CPU fallback.
 """
 import ctypes
@@ -23,7 +25,8 @@ class _Stats(ctypes.Structure):
     _fields_ = [("abs_err", ctypes.c_double), ("sum_p", ctypes.c_double), ("sum_y", ctypes.c_double),
                 ("fg_p", ctypes.c_double), ("fg_p2", ctypes.c_double), ("bg_q", ctypes.c_double), ("bg_q2", ctypes.c_double),
                 ("n_fg", ctypes.c_uint64), ("sum_mx", ctypes.c_uint64), ("sum_my", ctypes.c_uint64),
-                ("hist_cnt", ctypes.c_uint64 * 256), ("hist_y", ctypes.c_double * 256)]
+                ("hist_cnt", ctypes.c_uint64 * 256), ("hist_y", ctypes.c_double * 256),
+                ("em_all", ctypes.c_uint64 * 256), ("em_fg", ctypes.c_uint64 * 256)]
 
 
 class _Region(ctypes.Structure):
@@ -41,6 +44,7 @@ class EvaluationMetrics:
             raise RuntimeError("s3od_b200.metrics.EvaluationMetrics runs on CUDA devices only; there is no CPU fallback")
         self.sm_only = sm_only
         self.metrics: Dict[str, List[float]] = {"mae": [], "max_f": [], "avg_f": [], "s_score": []}
+        self.changeable_ems: List[np.ndarray] = []                     # EMeasure.metrics['changeable_ems'] (metrics.py:18-21)
         self._lib = load_library()
         assert self._lib.s3od_metrics_stats_bytes() == ctypes.sizeof(_Stats)
         assert self._lib.s3od_metrics_region_bytes() == ctypes.sizeof(_Region)
@@ -110,6 +114,37 @@ class EvaluationMetrics:
         Q = 0.5 * s_obj + 0.5 * (w1 * q[0] + w2 * q[1] + w3 * q[2] + w4 * q[3])
         return max(Q, 0.0) if Q == Q else Q
 
+    @staticmethod
+    def _changeable_em(st: _Stats, gt_size: int) -> np.ndarray:
+        """EMeasure.cal_em_with_cumsumhistogram + generate_parts_numel_combinations (metrics.py:80-132) on the device
+        histograms; same float64 numpy arithmetic, the counts are exact integers."""
+        eps = np.spacing(1)
+        all_hist = np.array(st.em_all, dtype=np.int64)
+        fg_fg_hist = np.array(st.em_fg, dtype=np.int64)
+        fg_bg_hist = all_hist - fg_fg_hist
+        gt_fg_numel = int(fg_fg_hist.sum())
+        fg_fg = np.cumsum(np.flip(fg_fg_hist), axis=0)
+        fg_bg = np.cumsum(np.flip(fg_bg_hist), axis=0)
+        fg__ = fg_fg + fg_bg
+        bg__ = gt_size - fg__
+        if gt_fg_numel == 0:
+            enhanced = bg__
+        elif gt_fg_numel == gt_size:
+            enhanced = fg__
+        else:
+            bg_fg = gt_fg_numel - fg_fg
+            bg_bg = bg__ - bg_fg
+            parts = [fg_fg, fg_bg, bg_fg, bg_bg]
+            mean_pred, mean_gt = fg__ / gt_size, gt_fg_numel / gt_size
+            dp_fg, dp_bg, dg_fg, dg_bg = 1 - mean_pred, 0 - mean_pred, 1 - mean_gt, 0 - mean_gt
+            combos = [(dp_fg, dg_fg), (dp_fg, dg_bg), (dp_bg, dg_fg), (dp_bg, dg_bg)]
+            res = np.empty((4, 256), dtype=np.float64)
+            for i, (numel, (a, b)) in enumerate(zip(parts, combos)):
+                align = 2 * (a * b) / (a ** 2 + b ** 2 + eps)
+                res[i] = (align + 1) ** 2 / 4 * numel
+            enhanced = res.sum(axis=0)
+        return enhanced / (gt_size - 1 + eps)
+
     def step(self, pred: torch.Tensor, mask: torch.Tensor) -> None:
         pred = pred.to(self.device, torch.float32).contiguous()
         mask = mask.to(self.device, torch.float32).contiguous()
@@ -131,6 +166,7 @@ class EvaluationMetrics:
         prec, recall = tp / (sel + 1e-20), tp / (total_y + 1e-20)
         f_score = (1 + 0.3) * prec * recall / (0.3 * prec + recall)  # metrics.py:250-252
         f_score[f_score != f_score] = 0
+        self.changeable_ems.append(self._changeable_em(st, n))
         self.metrics["mae"].append(st.abs_err / n)
         self.metrics["max_f"].append(f_score.max().item())
         self.metrics["avg_f"].append(f_score.mean().item())
@@ -140,8 +176,10 @@ class EvaluationMetrics:
         if self.sm_only:
             return {"Sm": np.mean(self.metrics["s_score"])}
         return {"MAE": np.mean(self.metrics["mae"]), "MaxF": np.mean(self.metrics["max_f"]), "AvgF": np.mean(self.metrics["avg_f"]),
-                "Sm": np.mean(self.metrics["s_score"])}
+                "Sm": np.mean(self.metrics["s_score"]),
+                "Em": np.mean(np.array(self.changeable_ems, dtype=np.float64), axis=0).mean()}          # metrics.py:134-137
 
     def reset(self) -> None:
         for v in self.metrics.values():
             v.clear()
+        self.changeable_ems.clear()

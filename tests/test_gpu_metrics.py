@@ -28,8 +28,11 @@ def test_metrics_match_reference_golden(golden_dir):
         got = np.array([em.metrics[k][i] for k in ("mae", "max_f", "avg_f", "s_score")])
         assert np.abs(got - g[name + "_vals"]).max() <= TOL, (name, got, g[name + "_vals"])
         assert abs(sm.metrics["s_score"][i] - g[name + "_vals"][3]) <= TOL
+        # E-measure: integer histograms + the reference's float64 formulas -> equal to rounding
+        np.testing.assert_allclose(em.changeable_ems[i], g[name + "_ems"], rtol=1e-12, atol=1e-12)
     out = em.compute_metrics()
-    assert set(out) == {"MAE", "MaxF", "AvgF", "Sm"} and set(sm.compute_metrics()) == {"Sm"}
+    assert set(out) == {"MAE", "MaxF", "AvgF", "Sm", "Em"} and set(sm.compute_metrics()) == {"Sm"}
+    assert abs(out["Em"] - float(g["em_all_cases"])) <= 1e-12
     vals = np.stack([g[n + "_vals"] for n in g["names"]])
     assert abs(out["MAE"] - vals[:, 0].mean()) <= TOL and abs(out["Sm"] - vals[:, 3].mean()) <= TOL
     em.reset()
