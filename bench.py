@@ -199,6 +199,13 @@ def run_b200(args, rank, local_rank, world):
     # algorithmic bytes per image of the two bandwidth kernels either side of the network
     family_bytes = {"preprocess": src * src * 3 + 3 * S * S * 2,
                     "postprocess": K * S * S * 4 + src * src * 3 + K * src * src * 4 + src * src * 4}
+    if args.model == "dinob":
+        ntok, g = (S // 16) ** 2 + 5, S // 16
+        # residual add + LayerNorm: x fp32 read + write, dx bf16 read, y bf16 write = 12 B per element, 2 per layer, 11 layers
+        # (the first has no dx; the four tap copies add 2 B per patch element)
+        family_bytes["layernorm"] = ntok * 768 * (22 * 12 - 2) + 4 * (ntok - 5) * 768 * 2
+        # bilinear x2 of the four fusion levels, 256 channels bf16: read 1 + write 4 per input pixel (+ the tiny IoU head / prefix kernels)
+        family_bytes["head_bandwidth"] = sum((g * 2 ** l // 2) ** 2 for l in range(4)) * 256 * 2 * 5
     for f, ms in sorted(fam_ms.items(), key=lambda kv: -kv[1]):
         if ms <= 0.0:
             continue
