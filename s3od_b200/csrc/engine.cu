@@ -373,9 +373,21 @@ bool add_conv3x3(s3od_ctx* c, const std::string& label, const bf16* in, int Hs, 
   return add_conv<BN, EpiConv, EW>(c, label, ta, geom_3x3(Hs, Ws, cin), wt, cout, 0, 9 * cin, cout, ep);
 }
 
+#ifndef S3OD_FLAT_TILES
+#define S3OD_FLAT_TILES 1
+#endif
+constexpr bool kFlatTiles = S3OD_FLAT_TILES != 0;
+
 bool build_plan(s3od_ctx* c) {
   const int mb = c->mb, g = c->g, P = c->P, ntok = c->ntok, D = c->D, H = c->H, I = c->I, K = c->K, S = c->S;
   const size_t MT = static_cast<size_t>(mb) * ntok;
+  // flat tiling: the epilogue sees ONE "image" of nb * ntok rows (RowInfo.b = 0, RowInfo.t = global row)
+  std::function<void(EpiResidual::Params&, int, int, float*, float*)> flat_residual;
+  std::function<void(EpiGelu::Params&, int, int, float*, float*)> flat_gelu;
+  if (kFlatTiles) {
+    flat_residual = [ntok](EpiResidual::Params& e, int nb, int, float*, float*) { e.ntok = nb * ntok; };
+    flat_gelu = [ntok](EpiGelu::Params& e, int nb, int, float*, float*) { e.ntok = nb * ntok; };
+  }
   // ---- activations
   bool ok = true;
   ok = ok && alloc_act(c, "patches", static_cast<size_t>(c->max_batch) * P * 768 * 2);
@@ -472,18 +484,23 @@ bool build_plan(s3od_ctx* c) {
     });
     {
       EpiResidual::Params e{dx, wptr<float>(c, pre + "o.b"), wptr<float>(c, pre + "ls1"), ntok, D};
-      if (!add_linear<256, EpiResidual, 8>(c, pre + "o_proj", actx, MT, ntok, D, wptr<bf16>(c, pre + "o.w"), D, e, false, true)) return false;
+      // flat M tiling (S3OD_FLAT_TILES): dx is a plain [nb * ntok, D] matrix, so the tiles may straddle images - per-image
+      // tiling spends one tile in 33 on the 5-row remainder of every image (ntok = 4101 = 32 * 128 + 5)
+      if (!add_linear<256, EpiResidual, 8>(c, pre + "o_proj", actx, MT, ntok, D, wptr<bf16>(c, pre + "o.w"), D, e, false, !kFlatTiles,
+                                           flat_residual)) return false;
     }
     c->plan.emplace_back(pre + "ln2", [=](int nb, int, float*, float*, cudaStream_t st) {
       return launch_layernorm(x, dx, ln2w, ln2b, xn, nullptr, nb * ntok, ntok, D, 1e-5f, st);
     });
     {
       EpiGelu::Params e{hmid, wptr<float>(c, pre + "up.b"), I, ntok};
-      if (!add_linear<256, EpiGelu, 8>(c, pre + "up_proj", xn, MT, ntok, D, wptr<bf16>(c, pre + "up.w"), I, e, false, true)) return false;
+      if (!add_linear<256, EpiGelu, 8>(c, pre + "up_proj", xn, MT, ntok, D, wptr<bf16>(c, pre + "up.w"), I, e, false, !kFlatTiles,
+                                       flat_gelu)) return false;
     }
     {
       EpiResidual::Params e{dx, wptr<float>(c, pre + "down.b"), wptr<float>(c, pre + "ls2"), ntok, D};
-      if (!add_linear<256, EpiResidual, 8>(c, pre + "down_proj", hmid, MT, ntok, I, wptr<bf16>(c, pre + "down.w"), D, e, false, true)) return false;
+      if (!add_linear<256, EpiResidual, 8>(c, pre + "down_proj", hmid, MT, ntok, I, wptr<bf16>(c, pre + "down.w"), D, e, false, !kFlatTiles,
+                                           flat_residual)) return false;
     }
   }
 
