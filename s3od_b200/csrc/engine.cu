@@ -373,6 +373,9 @@ bool add_conv3x3(s3od_ctx* c, const std::string& label, const bf16* in, int Hs, 
   return add_conv<BN, EpiConv, EW>(c, label, ta, geom_3x3(Hs, Ws, cin), wt, cout, 0, 9 * cin, cout, ep);
 }
 
+#ifndef S3OD_POOL_MIN
+#define S3OD_POOL_MIN 128
+#endif
 #ifndef S3OD_FLAT_TILES
 #define S3OD_FLAT_TILES 1
 #endif
@@ -420,7 +423,11 @@ bool build_plan(s3od_ctx* c) {
   ok = ok && alloc_act(c, "mh1", static_cast<size_t>(mb) * R0 * R0 * 128 * 2);
   ok = ok && alloc_act(c, "feat0", static_cast<size_t>(mb) * S * S * 64 * 2);
   ok = ok && alloc_act(c, "feat", static_cast<size_t>(mb) * S * S * 64 * 2);
-  c->pool_blocks = std::max(1, std::min(8 * c->num_sms / std::max(1, mb) + 1, ((R0 / 2 + 7) / 8) * ((R0 / 2 + 31) / 32)));
+  // blocks per image of the pooled (last) up-sampling level: enough for 8 blocks per SM at a full micro-batch, and at least
+  // S3OD_POOL_MIN per image so that the small tail chunks of the batch API (4 images) still fill the GPU; never more than
+  // the work units of one image
+  c->pool_blocks = std::max(1, std::min(std::max(8 * c->num_sms / std::max(1, mb) + 1, S3OD_POOL_MIN),
+                                        ((R0 / 2 + 7) / 8) * ((R0 / 2 + 31) / 32)));
   ok = ok && alloc_act(c, "pool", static_cast<size_t>(mb) * c->pool_blocks * 256 * 4);
   if (!ok) return false;
 
