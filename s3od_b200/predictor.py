@@ -32,7 +32,8 @@ class RemovalResult:
 def chunk_schedule(n: int, step: int) -> List[tuple]:
     """[(start, end)] of the device chunks of an n-image batch: full micro-batches, the last one halved down to 4 images.
     The device-to-host copy of a chunk overlaps the compute of the next one, so only the LAST chunk's copy is exposed;
-    ending on small chunks keeps that tail short (67 MB of results per 2048^2 image)."""
+    ending on small chunks keeps that tail short (67 MB of results per 2048^2 image).  One of the small chunks leads, so
+    that the exposed upload in front of the first compute is short too."""
     sizes = [step] * (n // step)
     if n % step:
         sizes.append(n % step)
@@ -43,6 +44,10 @@ def chunk_schedule(n: int, step: int) -> List[tuple]:
             sizes.append(half)
             last -= half
         sizes.append(last)
+        # the compute of the first chunk cannot start before its images are on the device: lead with a small chunk
+        # (16, 8, 4, 4 -> 8, 16, 4, 4) so that only its short upload is exposed
+        if len(sizes) >= 3 and sizes[-3] < sizes[0]:
+            sizes.insert(0, sizes.pop(-3))
     bounds, s0 = [], 0
     for sz in sizes:
         bounds.append((s0, s0 + sz))
@@ -134,7 +139,7 @@ class BackgroundRemoval:
         pending = []
         step = max(1, min(model.max_batch, model.micro_batch))
         if getattr(self, "_slot_free", None) is None:
-            self._slot_free = [None, None]                      # event: the slot's device buffers have been copied out
+            self._slot_free = [None, None, None]                # event: the slot's device buffers have been copied out
         bounds = chunk_schedule(len(arrays), step)
         # host -> device copies of every chunk on their own stream, ahead of the compute that consumes them
         uploads = []
@@ -143,7 +148,7 @@ class BackgroundRemoval:
                 d_imgs = [torch.from_numpy(a).to(dev, non_blocking=True) for a in arrays[s0:s1]]
                 uploads.append((d_imgs, up.record_event()))
         for ci, (d_imgs, uploaded) in enumerate(uploads):
-            slot = ci & 1                                       # two sets of reusable device output buffers
+            slot = ci % 3                                       # three sets of reusable device output buffers
             if self._slot_free[slot] is not None:
                 main.wait_event(self._slot_free[slot])
             main.wait_event(uploaded)

@@ -182,7 +182,9 @@ def test_sharder_two_ranks_gloo():
 def test_chunk_schedule_covers_the_batch_and_ends_small():
     """remove_background_batch: full micro-batches, then the last one halved down to <= 4 images (short copy-out tail)."""
     from s3od_b200.predictor import chunk_schedule
-    assert chunk_schedule(32, 16) == [(0, 16), (16, 24), (24, 28), (28, 32)]
+    assert chunk_schedule(32, 16) == [(0, 8), (8, 24), (24, 28), (28, 32)]
+    assert chunk_schedule(64, 32) == [(0, 8), (8, 40), (40, 56), (56, 60), (60, 64)]
+    assert chunk_schedule(16, 16) == [(0, 8), (8, 12), (12, 16)]
     assert chunk_schedule(1, 16) == [(0, 1)]
     assert chunk_schedule(0, 16) == []
     for n in range(1, 70):
