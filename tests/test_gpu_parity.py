@@ -270,6 +270,21 @@ def test_batch_api_matches_single_calls(predictors):
         np.testing.assert_array_equal(np.array(rs.rgba_image), np.array(rb.rgba_image))
 
 
+def test_batch_api_chunk_schedule_with_rotating_slots(predictors):
+    """16 images at micro-batch 16 run as chunks of 8, 4, 4 (lead + tails) over three rotating output slots; a second call
+    reuses the slots while the first results are still referenced."""
+    br = predictors(64, max_batch=16, micro_batch=16)
+    imgs = [synth_image((64, 128, 96)[i % 3], 64, seed=100 + i) for i in range(16)]
+    first = br.remove_background_batch(imgs)
+    second = br.remove_background_batch(imgs[::-1])
+    for i in (0, 5, 9, 13, 15):
+        single = br.remove_background(imgs[i])
+        for got in (first[i], second[15 - i]):
+            np.testing.assert_array_equal(single.all_masks, got.all_masks)
+            np.testing.assert_array_equal(single.all_ious, got.all_ious)
+            np.testing.assert_array_equal(np.array(single.rgba_image), np.array(got.rgba_image))
+
+
 def test_c_abi_rejects_misaligned_buffers(models):
     """The vector paths of the pre / post-process kernels need aligned buffers: the C ABI refuses anything else (ValueError)."""
     m = models(64)
