@@ -43,7 +43,10 @@ constexpr int kAttnThreads = 608;                 // 2 streams x 8 softmax warps
 // kAttnTile = 128 query rows per CTA; kAttnKvTile = 96 keys per step (types.h): S (96) + two P buffers (2 x 48) + O (64)
 // = the 256 TMEM columns a CTA may hold at 2 CTAs/SM.
 static_assert(kAttnKvTile == 96 && kAttnTile == 128, "attention kernel is written for 128 x 96 steps");
-constexpr int kAttnStages = 4;                    // K / V ring depth
+#ifndef S3OD_ATTN_STAGES
+#define S3OD_ATTN_STAGES 4
+#endif
+constexpr int kAttnStages = S3OD_ATTN_STAGES;     // K / V ring depth (3 / 4 / 6 measure the same: the ring never runs dry)
 constexpr int kAttnQBytes = 128 * 128;            // 128 rows x 64 bf16
 constexpr int kAttnKBytes = kAttnKvTile * 128;
 constexpr int kAttnVBytes = kAttnKvTile * 128;    // 96 kv rows x 64 d
