@@ -620,9 +620,29 @@ bool build_plan(s3od_ctx* c) {
   }
   // ---- mask head (model.py:455-467)
   bf16 *p1 = aptr<bf16>(c, "p1"), *mh1 = aptr<bf16>(c, "mh1"), *feat0 = aptr<bf16>(c, "feat0"), *feat = aptr<bf16>(c, "feat");
-  if (!add_conv3x3<128, 8>(c, "head.mh.c1", p1, R0, R0, 256, "head.mh.c1.w", 128,
-                           conv_epi(mh1, nullptr, wptr<float>(c, "head.mh.c1.b"), nullptr, nullptr, 0, 128, R0, R0)))
+  // 256 -> 128 channels: operand-swapped kernel (conv_swap.cuh) when the tile grid pairs up; S3OD_SWAP128=0 keeps the 128-wide
+  // pair GEMM (A/B switch)
+  const ConvGeom g_c1 = geom_3x3(R0, R0, 256);
+  const char* swap_env = getenv("S3OD_SWAP128");
+  if ((swap_env == nullptr || swap_env[0] != '0') && (g_c1.tiles_h * g_c1.tiles_w) % 2 == 0) {
+    ConvSwapParams sp{};
+    if (!tmap_nhwc(&sp.tma_x, p1, mb, R0, R0, 256)) return false;
+    if (!tmap_matrix(&sp.tma_w, wptr<bf16>(c, "head.mh.c1.w"), 128, 9 * 256, 128)) return false;
+    sp.geom = g_c1;
+    sp.num_k_blocks = 9 * 256 / 64;
+    sp.out = mh1;
+    sp.bias = wptr<float>(c, "head.mh.c1.b");
+    sp.relu = 0;
+    const int sms = c->num_sms, per_img = g_c1.tiles_h * g_c1.tiles_w;
+    c->plan.emplace_back("head.mh.c1", [=](int nb, int, float*, float*, cudaStream_t st) mutable -> cudaError_t {
+      ConvSwapParams q = sp;
+      q.m_tiles = nb * per_img;
+      return launch_conv_swap128(q, sms, st);
+    });
+  } else if (!add_conv3x3<128, 8>(c, "head.mh.c1", p1, R0, R0, 256, "head.mh.c1.w", 128,
+                                  conv_epi(mh1, nullptr, wptr<float>(c, "head.mh.c1.b"), nullptr, nullptr, 0, 128, R0, R0))) {
     return false;
+  }
   const bool rows_ok = (S % kRowPx == 0) && getenv("S3OD_NO_ROWCONV") == nullptr;
   if (rows_ok && R0 % kRowPx == 0) {
     // ConvTranspose2d k4 s2 p1 + ReLU on the row-streaming kernel, one launch per output-column phase

@@ -11,6 +11,20 @@ S3OD_INSTANTIATE_CONV_ROWS(64, EpiConv)
 S3OD_INSTANTIATE_CONV_ROWS(96, EpiMask)
 S3OD_INSTANTIATE_CONV_ROWS(32, EpiMask)
 
+cudaError_t launch_conv_swap128(const ConvSwapParams& p, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_swap128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSwapCfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int items = p.m_tiles / 2;
+  if (items <= 0) return cudaSuccess;
+  const int grid = items < num_sms ? items : num_sms;
+  conv_swap128_kernel<0><<<grid, 128 + 32 * 8, ConvSwapCfg::kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {

@@ -2,6 +2,7 @@
 #pragma once
 #include "gemm_tc.cuh"
 #include "conv_rows.cuh"
+#include "conv_swap.cuh"
 #include "types.h"
 
 #include <cstdlib>
@@ -27,6 +28,7 @@ template <int NOUT, class Epi>
 cudaError_t launch_conv_rows(const RowConvParams<Epi>& p, int num_sms, cudaStream_t stream);
 
 cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_conv_swap128(const ConvSwapParams& p, int num_sms, cudaStream_t stream);
 
 extern long long* g_attn_trace;
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream);
