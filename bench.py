@@ -26,7 +26,12 @@ from s3od_b200.synth import save_checkpoint, synth_noise_image, synth_state_dict
 
 METRIC = "images/sec (dinob, device-timed)"
 UNIT = "images/s"
-GFLOP_PER_IMAGE = 2276.8            # algorithmic FLOPs of the needed layers, dinob @ 1024^2
+# algorithmic FLOPs of the needed layers, dinob @ 1024^2 = 2276.8 GF as written; the plan runs the four
+# fusion-block out_convs (1x1) BEFORE the 2x interpolation (engine.cu, "out_conv commuted"), which removes 34.2 GF of them
+# ("if used, subtract 34.2 GF") - the work actually executed is what the roofline is computed from.
+OUT_CONV_COMMUTE_GFLOP = 34.2
+GFLOP_PER_IMAGE = 2276.8 - OUT_CONV_COMMUTE_GFLOP          # 2242.6
+GFLOP_PER_IMAGE_VITL = 4958.1 - OUT_CONV_COMMUTE_GFLOP     # ViT-L @ 1024^2, one mask
 
 
 def load_peaks():
@@ -36,6 +41,21 @@ def load_peaks():
             p = json.load(f)
         return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"], source="measured")
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+def newest_traffic(kernel: str, micro_batch: int, model: str, image_size: int):
+    """dram bytes per launch of `kernel` from the NEWEST committed ncu --set full summary (profiles/r*_traffic.json, highest
+    round tag first) whose capture matches this run's micro-batch / model / image size; (None, None) if there is none."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                t = json.load(f).get(kernel)
+            if t and t["micro_batch"] == micro_batch and t["model"] == model and t["image_size"] == image_size:
+                return t["dram_bytes_per_launch"], os.path.basename(path)
+        except (OSError, ValueError, KeyError, TypeError):
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -102,9 +122,195 @@ def kernel_family(label: str) -> str:
 FAMILY_GFLOP = {
     "attention": 11 * 51.67,
     "encoder_gemm": 4.83 + 11 * (19.35 + 38.70),
-    "head_conv": 17.7 + 36.5 + 140.1 + 2.95 + 21.47 + 85.90 + 343.60 + 154.62,
+    "head_conv": 17.7 + 36.5 + 140.1 + 2.95 + 21.47 + 85.90 + 343.60 + 154.62 - OUT_CONV_COMMUTE_GFLOP,
     "head_conv_smallN": 68.72 + 77.31 + 116.17,
 }
+
+
+def config_dict(args):
+    """The workload both arms (--impl b200 / reference) are quoted on: BASELINE.json configs[1] unless overridden."""
+    B, S, src = args.batch, args.image_size, args.source
+    return {"workload": f"{args.model} inference, batch {B} synthetic {src}x{src} uint8 images per GPU, image_size {S} "
+                        "(preprocess + backbone + mask decoder + IoU head + postprocess), seeded random weights",
+            "batch_per_gpu": B, "image_size": S, "source": src, "micro_batch": min(args.micro_batch, B),
+            "cache": "inputs + activations per step exceed the 126 MB L2 by >10x (no flush needed)"}
+
+
+def make_images(B, src, first_seed, dev):
+    """Seeded synthetic uint8 images (reference fixture style, tests/conftest.py:39-54): ordinary PAGEABLE numpy arrays for
+    the public API - what /root/reference/src/s3od/predictor.py:96-106 receives - and device copies for the device-timed leg."""
+    np_imgs = [synth_noise_image(src, src, seed=first_seed + i) for i in range(B)]
+    d_imgs = [torch.from_numpy(a).to(dev) for a in np_imgs]
+    return np_imgs, d_imgs
+
+
+def time_device(model, d_imgs, steps, warmup, dev, sampler=None, profile=False):
+    """`steps` passes of preprocess -> forward -> postprocess over the device-resident batch, CUDA events on the launch stream."""
+    for _ in range(warmup):
+        model.run_u8(d_imgs, slot=0)                 # reusable output buffers: no allocator traffic in the timed loop
+    torch.cuda.synchronize(dev)
+    if profile:
+        model.profile_enable(True)
+    sharder.barrier()
+    torch.cuda.synchronize(dev)
+    if sampler is not None:
+        sampler.start()
+    launches0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = model.run_u8(d_imgs, slot=0)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sharder.barrier()
+    ms_local = e0.elapsed_time(e1)
+    launches = model.launch_count() - launches0
+    prof = model.profile_read() if profile else None
+    if profile:
+        model.profile_enable(False)
+    clocks = sampler.stop() if sampler is not None else None
+    return sharder.max_over_ranks(ms_local, device=dev), launches, prof, clocks, out
+
+
+def time_e2e(br, np_imgs, steps, warmup, dev):
+    """The same metric through the public API: pageable host uint8 in (pinned on ingest through the predictor's staging ring),
+    host results out; H2D and D2H inside the timed region, wall clock around the calls."""
+    res = None
+    for _ in range(warmup):
+        res = br.remove_background_batch(np_imgs)      # same binding pattern as the timed loop (two result sets alive)
+    sharder.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = br.remove_background_batch(np_imgs)
+        _ = float(res[0].all_ious.sum())               # host read of the step's result
+    torch.cuda.synchronize(dev)
+    t_local = time.perf_counter() - t0
+    return sharder.max_over_ranks(t_local, device=dev), res
+
+
+def verify_batch_against_single(model, d_imgs, out_batch, picks):
+    """After the timed loop: images `picks` of the benchmarked batch are run ALONE (batch 1) on the same context and must give
+    the same bits - mask logits, all_masks, RGBA (the IoU logits' pooled mean is a two-stage sum: equal to 2e-5)."""
+    out, outs, ious, best = out_batch
+    keep = {i: (out["pred_masks"][i].clone(), out["pred_iou"][i].clone(), outs[i][0].clone(), outs[i][1].clone(), int(best[i]))
+            for i in picks}
+    ok = True
+    for i in picks:
+        o1, outs1, _, best1 = model.run_u8([d_imgs[i]], slot=1)
+        lm, li, am, rg, bi = keep[i]
+        ok = ok and bool(torch.equal(o1["pred_masks"][0], lm)) and bool(torch.equal(outs1[0][0], am)) and bool(torch.equal(outs1[0][1], rg))
+        ok = ok and float((o1["pred_iou"][0] - li).abs().max()) <= 2e-5 and int(best1[0]) == bi
+    return ok
+
+
+def latency_batch1(br, model, np_img, d_img, dev, iters=20):
+    """The reference API is one image per call: device-timed and end-to-end latency of a single image."""
+    for _ in range(3):
+        model.run_u8([d_img], slot=1)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        model.run_u8([d_img], slot=1)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    dev_ms = e0.elapsed_time(e1) / iters
+    for _ in range(2):
+        br.remove_background(np_img)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        r = br.remove_background(np_img)
+        _ = float(r.all_ious.sum())
+    return dev_ms, (time.perf_counter() - t0) / iters * 1e3
+
+
+def gpu_baseline(S, batch, dev):
+    """SURVEY 8(d) last row: the reference's own GPU path on the SAME B200 - the oracle restatement of DPTSegmentation.forward
+    run by PyTorch (cuBLAS / cuDNN / SDPA flash, channels_last, cudnn.benchmark) in fp32 (TF32 off), under
+    torch.autocast(bfloat16) and with bf16 weights; model forward only (no pre / post-process), CUDA-event timed.
+    This - not the CPU number - is the bar the hand-written kernels have to beat."""
+    from oracle import model as om
+    sd = synth_state_dict(VITB, 0)
+    cl = torch.channels_last
+    sd_dev = {k: (v.to(dev).contiguous(memory_format=cl) if v.dim() == 4 else v.to(dev)) for k, v in sd.items()}
+    x = torch.randn(batch, 3, S, S, device=dev)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    res = {"batch": batch, "sdpa": True, "channels_last": True, "cudnn_benchmark": True, "unit": UNIT,
+           "what": "oracle restatement of DPTSegmentation.forward (model.py:99-106) run by torch on this GPU, model forward only"}
+
+    def run(tag, tf32, autocast, weights):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        xx = x.to(weights.get("_dtype", torch.float32))
+        try:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                for _ in range(2):
+                    om.forward(weights, xx, VITB, sdpa=True) if weights is sd_dev else _forward_lowp(om, weights, xx)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                n = 3
+                for _ in range(n):
+                    om.forward(weights, xx, VITB, sdpa=True) if weights is sd_dev else _forward_lowp(om, weights, xx)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            res[tag] = round(n * batch / (e0.elapsed_time(e1) / 1e3), 2)
+        except Exception as e:  # noqa: BLE001 - a baseline that cannot run is reported, not fatal
+            res[tag] = None
+            res[tag + "_error"] = repr(e)[:200]
+
+    try:
+        run("fp32", False, False, sd_dev)
+        run("tf32", True, False, sd_dev)
+        run("bf16_autocast", False, True, sd_dev)
+        sd_bf = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v) for k, v in sd_dev.items()}
+        sd_bf["_dtype"] = torch.bfloat16
+        run("bf16_weights", False, True, sd_bf)          # + autocast: the fp32 RoPE tables / LayerNorm outputs meet bf16 operands
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
+    return res
+
+
+def _forward_lowp(om, sd_bf, x):
+    """The oracle arithmetic with bf16 weights and activations (`model.to(torch.bfloat16)` in reference terms)."""
+    sd = {k: v for k, v in sd_bf.items() if k != "_dtype"}
+    x = x.to(torch.bfloat16)
+    taps = om.encoder_taps(sd, x, VITB, None, True)
+    return om.head_forward(sd, taps, x.shape[-2] // 16, x.shape[-1] // 16, VITB)
+
+
+def extra_leg(model_name, S, src, B, micro_batch, local_rank, rank, world, dev, steps, e2e_steps, br=None):
+    """Short device-timed + end-to-end measurement of another BASELINE.json configuration (reported under `extra`, the headline
+    stays configs[1]): cfg3 = 2048^2 sources with full-resolution mask up-sampling + RGBA composite, cfg5 = ViT-L / one mask."""
+    from s3od_b200 import BackgroundRemoval
+    arch = VITL if model_name == "dinol" else VITB
+    own = br is None
+    if own:
+        ckpt = os.path.join("/tmp", f"s3od_synth_{model_name}_seed0_{os.getpid()}.pt")
+        save_checkpoint(ckpt, arch, 0)
+        br = BackgroundRemoval(model_id=ckpt, image_size=S, device=f"cuda:{local_rank}", max_batch=B, micro_batch=micro_batch,
+                               encoder_name="dinov3_large" if model_name == "dinol" else "dinov3_base", num_outputs=arch.num_outputs)
+        os.remove(ckpt)
+    b0, _ = sharder.shard_range(B * world, rank, world)
+    np_imgs, d_imgs = make_images(B, src, 10_000 + b0, dev)
+    ms, launches, _, _, out = time_device(br.model, d_imgs, steps, 3, dev)
+    del out
+    t_e2e, res = time_e2e(br, np_imgs, e2e_steps, 1, dev)
+    del res, d_imgs
+    K = arch.num_outputs
+    ent = {"workload": f"{model_name} inference bf16, batch {B} synthetic {src}x{src} uint8 images per GPU, image_size {S}",
+           "value": round(world * B * steps / (ms / 1e3), 2), "unit": UNIT, "steps": steps, "ms_per_step": round(ms / steps, 3),
+           "e2e": {"value": round(world * B * e2e_steps / t_e2e, 2), "unit": UNIT, "steps": e2e_steps,
+                   "h2d_bytes_per_step": B * src * src * 3, "d2h_bytes_per_step": B * (K * src * src * 4 + src * src * 4 + K * 4 + 4)},
+           "gpu_launches": int(launches), "n_gpus": world}
+    if S == 1024:
+        gf = GFLOP_PER_IMAGE_VITL if model_name == "dinol" else GFLOP_PER_IMAGE
+        ent["whole_step_tflops_per_gpu"] = round(gf * ent["value"] / world / 1e3, 1)
+    if own:
+        br.close()
+    return ent
 
 
 def run_b200(args, rank, local_rank, world):
@@ -119,62 +325,35 @@ def run_b200(args, rank, local_rank, world):
                            encoder_name="dinov3_large" if args.model == "dinol" else "dinov3_base", num_outputs=arch.num_outputs)
     os.remove(ckpt)
     model = br.model
-    # seeded synthetic uint8 images (reference fixture style), distinct per rank / slot; resident in HBM for `value`
+    # distinct images per rank / slot; device copies resident in HBM for `value`, pageable host arrays for `e2e`
     b0, _ = sharder.shard_range(B * world, rank, world)
-    host_imgs = []
-    for i in range(B):
-        t = torch.empty((src, src, 3), dtype=torch.uint8, pin_memory=True)
-        t.numpy()[...] = synth_noise_image(src, src, seed=b0 + i)
-        host_imgs.append(t)
-    d_imgs = [t.to(dev) for t in host_imgs]
-    np_imgs = [t.numpy() for t in host_imgs]          # numpy views of pinned memory for the public API
+    np_imgs, d_imgs = make_images(B, src, b0, dev)
 
-    def step_device():
-        return model.run_u8(d_imgs, slot=0)          # reusable output buffers: no allocator traffic in the timed loop
-
-    for _ in range(args.warmup):
-        step_device()
-    torch.cuda.synchronize(dev)
-    model.profile_enable(True)
-    sampler = ClockSampler(local_rank)
-    sharder.barrier()
-    torch.cuda.synchronize(dev)
-    if rank == 0:
-        sampler.start()
-    launches0 = model.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step_device()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    sharder.barrier()
-    ms_local = e0.elapsed_time(e1)
-    launches = model.launch_count() - launches0
-    prof = model.profile_read()
-    model.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = sharder.max_over_ranks(ms_local, device=dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, launches, prof, clocks, out = time_device(model, d_imgs, args.steps, args.warmup, dev, sampler, profile=True)
+    # ---- the benchmarked batch is checked, not only timed: two of its images alone give the same bits
+    verified = {"batch_vs_single_bitwise": verify_batch_against_single(model, d_imgs, out, sorted({0, B - 1}))}
     del out
 
-    # ---- end to end through the public API: pinned host uint8 in, host results out (H2D + D2H inside the timed region)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    res = None
-    for _ in range(args.warmup):
-        res = br.remove_background_batch(np_imgs)      # same binding pattern as the timed loop (two result sets alive)
-    sharder.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = br.remove_background_batch(np_imgs)
-        loss_like = float(res[0].all_ious.sum())       # host read of the step's result
-    torch.cuda.synchronize(dev)
-    t_e2e_local = time.perf_counter() - t0
-    t_e2e = sharder.max_over_ranks(t_e2e_local, device=dev)
+    # ---- end to end through the public API (H2D + D2H inside the timed region)
+    e2e_steps = max(1, args.e2e_steps)
+    t_e2e, res = time_e2e(br, np_imgs, e2e_steps, args.warmup, dev)
     h2d = B * src * src * 3
     K = arch.num_outputs
     d2h = B * (K * src * src * 4 + src * src * 4 + K * 4 + 4)
+    api_first = [(res[i].all_masks.copy(), int(res[i].all_ious.argmax()), res[i].all_ious.copy()) for i in range(min(2, B))]
     del res
+    lat_dev_ms, lat_e2e_ms = latency_batch1(br, model, np_imgs[0], d_imgs[0], dev)
+
+    extra = {}
+    if args.extras and args.model == "dinob" and S == 1024 and src == 1024:
+        # BASELINE.json configs[2] shape on the same context, configs[4] on its own ViT-L context (after this one is freed)
+        extra["cfg3_source2048"] = extra_leg("dinob", S, 2048, B, args.micro_batch, local_rank, rank, world, dev, 5, 3, br=br)
+    del d_imgs
+    br.close()
+    torch.cuda.empty_cache()
+    if args.extras and args.model == "dinob" and S == 1024 and src == 1024:
+        extra["cfg5_dinol"] = extra_leg("dinol", S, 1024, B, args.micro_batch, local_rank, rank, world, dev, 3, 2)
 
     if rank != 0:
         return None
@@ -219,21 +398,14 @@ def run_b200(args, rank, local_rank, world):
         families[f] = ent
     dom = max((f for f in fam_ms if f in FAMILY_GFLOP), key=lambda f: fam_ms[f])
     flops_known = S == 1024 and args.model == "dinob"
-    gflop_img = GFLOP_PER_IMAGE if args.model == "dinob" else 4958.1     # ViT-L, one mask
+    gflop_img = GFLOP_PER_IMAGE if args.model == "dinob" else GFLOP_PER_IMAGE_VITL
     achieved = FAMILY_GFLOP[dom] * images / fam_ms[dom] if flops_known else None
     # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (same command, same micro-batch)
-    traffic = None
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01d_traffic.json")) as f:
-            t = json.load(f).get(dom)
-        if t and t["micro_batch"] == model.micro_batch and t["model"] == args.model and t["image_size"] == S:
-            traffic = t["dram_bytes_per_launch"]
-    except (OSError, ValueError, KeyError):
-        traffic = None
+    traffic, traffic_src = newest_traffic(dom, model.micro_batch, args.model, S)
     roofline = {"kernel": dom, "bound": "tensor", "achieved": round(achieved, 1) if achieved else None,
                 "peak": peaks["tflops_sustained"], "peak_source": peaks["source"] + " (sustained: timed inside a long step)",
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4) if achieved else None,
-                "traffic": traffic, "avg_launch_ms": round(fam_ms[dom] / fam_n[dom], 4),
+                "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": round(fam_ms[dom] / fam_n[dom], 4),
                 "whole_step_tflops": round(gflop_img * value / world / 1e3, 1) if S == 1024 else None,
                 "whole_step_frac": round(gflop_img * value / world / 1e3 / peaks["tflops_sustained"], 4) if S == 1024 else None}
     if dom == "attention" and achieved and clocks and clocks.get("sm_mhz"):
@@ -247,17 +419,22 @@ def run_b200(args, rank, local_rank, world):
         "metric": METRIC.replace("dinob", args.model), "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"{args.model} inference bf16, batch {B} synthetic {src}x{src} uint8 images per GPU, image_size {S} "
-                               "(preprocess + backbone + mask decoder + IoU head + postprocess), seeded random weights",
-                   "batch_per_gpu": B, "image_size": S, "source": src, "micro_batch": model.micro_batch,
-                   "cache": "inputs + activations per step exceed the 126 MB L2 by >10x (no flush needed)"},
+        "config": config_dict(args),
         "clocks": clocks,
         "e2e": {"value": round(world * B * e2e_steps / t_e2e, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "BackgroundRemoval.remove_background_batch (pinned host uint8 in, host results out)"},
+                "steps": e2e_steps, "api": "BackgroundRemoval.remove_background_batch (pageable host uint8 arrays in, pinned on "
+                                           "ingest through a staging ring; host results out)"},
         "gpu_launches": int(launches),
+        "latency_b1_ms": round(lat_dev_ms, 3),
+        "latency_b1": {"device_ms": round(lat_dev_ms, 3), "e2e_ms": round(lat_e2e_ms, 3), "images_per_s_device": round(1e3 / lat_dev_ms, 1),
+                       "api": "BackgroundRemoval.remove_background (one image per call, the reference API's shape)"},
+        "verified": verified,
         "roofline": roofline,
         "kernels": families,
     }
+    if extra:
+        line["extra"] = extra
+    line["_api_first"] = api_first
     return line
 
 
@@ -268,16 +445,35 @@ def cpu_baseline(sample_images: int, S: int, src: int):
     torch.set_num_threads(os.cpu_count() or 1)
     remove_background(sd, synth_noise_image(64, 64, seed=0), VITB, 64)          # thread-pool / allocator warm-up, tiny
     t0 = time.perf_counter()
+    outs = []
     for i in range(sample_images):
-        remove_background(sd, synth_noise_image(src, src, seed=i), VITB, S)
+        outs.append(remove_background(sd, synth_noise_image(src, src, seed=i), VITB, S))
     dt = time.perf_counter() - t0
     return {"value": round(sample_images / dt, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{sample_images} image(s) {src}x{src}, image_size {S}, full remove_background on the CPU oracle "
-                      f"(torch {torch.__version__} fp32), {dt:.1f} s"}
+                      f"(torch {torch.__version__} fp32), {dt:.1f} s"}, outs
+
+
+def check_against_oracle(api_first, oracle_outs):
+    """The images the CPU baseline just processed are images 0.. of rank 0's benchmarked batch: compare the public-API results
+    of the timed e2e loop with the oracle's (tolerances of tests/test_gpu_parity.py)."""
+    n = min(len(api_first), len(oracle_outs))
+    if n == 0:
+        return None
+    mx = mean = 0.0
+    idx_ok = True
+    for (am, best, ious), ref in zip(api_first[:n], oracle_outs[:n]):
+        d = np.abs(am - ref["all_masks"])
+        mx, mean = max(mx, float(d.max())), max(mean, float(d.mean()))
+        idx_ok = idx_ok and best == int(ref["best_idx"]) and float(np.abs(ious - ref["all_ious"]).max()) <= 1e-2
+    return {"images": n, "all_masks_max_abs": round(mx, 5), "all_masks_mean_abs": round(mean, 6), "best_idx_and_ious_match": idx_ok,
+            "ok": bool(mx <= 5e-2 and mean <= 6e-3 and idx_ok)}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference path's CPU implementation (oracle port; /root/reference cannot travel)."""
+    """--impl reference: the reference path's own CPU implementation on the host cores (the oracle port: the reference is
+    Python under /root/reference and cannot travel to the GPU box), all host threads, same config / metric / unit as the
+    b200 arm; one step = a 1-image sample of the batch (about 3 s of CPU work)."""
     if rank != 0:
         return None
     from oracle.pipeline import remove_background
@@ -285,8 +481,8 @@ def run_reference(args, rank, world):
     torch.set_num_threads(os.cpu_count() or 1)
     S, src = args.image_size, args.source
     imgs = [synth_noise_image(src, src, seed=i) for i in range(2)]
-    for _ in range(min(args.warmup, 1)):
-        remove_background(sd, imgs[0], VITB, S)
+    for i in range(args.warmup):
+        remove_background(sd, imgs[i % 2], VITB, S)
     t0 = time.perf_counter()
     for i in range(args.steps):
         remove_background(sd, imgs[i % 2], VITB, S)       # one step = a 1-image sample of the batch
@@ -294,10 +490,8 @@ def run_reference(args, rank, world):
     v = round(args.steps / dt, 4)
     sample = f"1 image {src}x{src} per step (bounded sample of the batch-{args.batch} workload), oracle port of the reference CPU path"
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"dinob inference, batch {args.batch} synthetic {src}x{src} uint8 images per GPU, image_size {S}",
-                       "batch_per_gpu": args.batch, "image_size": S, "source": src},
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
@@ -312,11 +506,16 @@ def main():
     ap.add_argument("--image-size", type=int, default=1024)
     ap.add_argument("--source", type=int, default=1024, help="source image side (2048 = configs[2] shape)")
     ap.add_argument("--micro-batch", type=int, default=32)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the short cfg3 (2048^2 sources) / cfg5 (ViT-L) legs")
+    ap.add_argument("--no-gpu-baseline", dest="gpu_baseline", action="store_false", help="skip the PyTorch-on-this-GPU baseline leg")
+    ap.add_argument("--gpu-baseline-batch", type=int, default=8)
     ap.add_argument("--model", default="dinob", choices=["dinob", "dinol"], help="dinol = ViT-L backbone, one mask (BASELINE.json configs[4])")
     ap.add_argument("--dump-profile", default=None, help="write the per-kernel CUDA-event table (label, launches, images, ms) here")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images timed on the CPU oracle (0 = skip)")
     args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -329,8 +528,18 @@ def main():
     rank, local_rank, world = sharder.init_from_env("nccl")
     line = run_b200(args, rank, local_rank, world)
     if rank == 0:
+        api_first = line.pop("_api_first")
+        if world == 1 and args.gpu_baseline and args.model == "dinob":
+            line["gpu_baseline"] = gpu_baseline(args.image_size, args.gpu_baseline_batch, torch.device("cuda", local_rank))
+            ours = line["value"]
+            best = max((line["gpu_baseline"].get(k) or 0.0) for k in ("fp32", "tf32", "bf16_autocast", "bf16_weights"))
+            line["gpu_baseline"]["speedup_over_best_torch"] = round(ours / best, 2) if best > 0 else None
+            line["gpu_baseline"]["note"] = ("PRIMARY baseline: same GPU, same arithmetic, PyTorch library kernels; the CPU figure "
+                                            "below is the reference's CPU path and is secondary")
         if world == 1 and args.cpu_sample > 0:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_sample, args.image_size, args.source)
+            line["cpu_baseline"], oracle_outs = cpu_baseline(args.cpu_sample, args.image_size, args.source)
+            line["cpu_baseline"]["note"] = "secondary (reported, not the bar): CPU path of the reference on the host cores"
+            line["verified"]["e2e_vs_cpu_oracle"] = check_against_oracle(api_first, oracle_outs)
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()

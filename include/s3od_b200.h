@@ -153,10 +153,6 @@ int s3od_op_conv3x3_rows(const void* d_in, const void* d_w, const float* d_bias,
 int s3od_op_convt_rows(const void* d_in, const void* d_wr, const float* d_bias, void* d_out, int batch, int h, int w, int relu,
                        s3od_stream stream);
 
-/* debug aid: per-step clock64() stamps of one attention CTA.  Library builds compile the stamps out (they sit in the
-   softmax loop); tools/lab/attn_lab.cu builds the kernel with S3OD_ATTN_TRACE_BUILD and reads them directly. */
-int s3od_debug_attn_trace(long long* host_out /* [64][8] */);
-
 #ifdef __cplusplus
 }
 #endif

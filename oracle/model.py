@@ -55,7 +55,7 @@ def embed(sd, x):
     return torch.cat([sd[e + "cls_token"].expand(B, -1, -1), sd[e + "register_tokens"].expand(B, -1, -1), t], dim=1)
 
 
-def attention(sd, p, xn, cos, sin, heads, stages=None):
+def attention(sd, p, xn, cos, sin, heads, stages=None, sdpa=False):
     B, N, D = xn.shape
     hd = D // heads
     q = F.linear(xn, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"])
@@ -70,19 +70,25 @@ def attention(sd, p, xn, cos, sin, heads, stages=None):
     k = torch.cat((k[:, :, :npre], kp * cos + _rot_half(kp) * sin), dim=2)
     if stages is not None:
         stages["q_rope"], stages["k_rope"], stages["v"] = q, k, v
-    s = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
-    o = torch.matmul(torch.softmax(s, dim=-1), v)
+    if sdpa:
+        # the reference's own dispatch (HF:316-329 with attn_implementation "sdpa"): flash / memory-efficient kernels on a GPU.
+        # Used by the same-GPU PyTorch baseline of bench.py and by the error-envelope test; the default below is the plain
+        # matmul-softmax form the CPU golden checks were pinned with.
+        o = F.scaled_dot_product_attention(q, k, v, scale=hd ** -0.5)
+    else:
+        s = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5)
+        o = torch.matmul(torch.softmax(s, dim=-1), v)
     o = o.transpose(1, 2).reshape(B, N, D)
     if stages is not None:
         stages["attn_ctx"] = o
     return F.linear(o, sd[p + "o_proj.weight"], sd[p + "o_proj.bias"])
 
 
-def encoder_layer(sd, p, x, cos, sin, heads, eps, stages=None):
+def encoder_layer(sd, p, x, cos, sin, heads, eps, stages=None, sdpa=False):
     xn = F.layer_norm(x, (x.shape[-1],), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
     if stages is not None:
         stages["ln1"] = xn
-    x = x + attention(sd, p + "attention.", xn, cos, sin, heads, stages) * sd[p + "layer_scale1.lambda1"]
+    x = x + attention(sd, p + "attention.", xn, cos, sin, heads, stages, sdpa) * sd[p + "layer_scale1.lambda1"]
     if stages is not None:
         stages["x_attn"] = x
     xn = F.layer_norm(x, (x.shape[-1],), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
@@ -93,7 +99,7 @@ def encoder_layer(sd, p, x, cos, sin, heads, eps, stages=None):
     return x + y * sd[p + "layer_scale2.lambda1"]
 
 
-def encoder_taps(sd, x, arch, stages=None) -> List[torch.Tensor]:
+def encoder_taps(sd, x, arch, stages=None, sdpa=False) -> List[torch.Tensor]:
     """hidden_states[taps][:, 5:]  - un-normed residual streams (model.py:72-84)."""
     gh, gw = x.shape[-2] // arch.patch, x.shape[-1] // arch.patch
     cos, sin = rope_tables(gh, gw, arch.head_dim, arch.rope_theta)
@@ -105,7 +111,7 @@ def encoder_taps(sd, x, arch, stages=None) -> List[torch.Tensor]:
     taps = []
     for i in range(arch.layers_needed):
         st = stages if (stages is not None and i == 0) else None
-        h = encoder_layer(sd, f"{pre}{i}.", h, cos, sin, arch.heads, arch.ln_eps, st)
+        h = encoder_layer(sd, f"{pre}{i}.", h, cos, sin, arch.heads, arch.ln_eps, st, sdpa)
         if stages is not None and i == 0:
             stages["layer0"] = h
         if (i + 1) in arch.taps:
@@ -177,10 +183,10 @@ def head_forward(sd, taps, gh, gw, arch, stages=None) -> Dict[str, torch.Tensor]
 
 
 @torch.no_grad()
-def forward(sd, x, arch, stages=None) -> Dict[str, torch.Tensor]:
-    """DPTSegmentation.forward (model.py:99-106) on fp32 CPU tensors."""
+def forward(sd, x, arch, stages=None, sdpa=False) -> Dict[str, torch.Tensor]:
+    """DPTSegmentation.forward (model.py:99-106) on fp32 tensors (CPU, or a GPU for the same-device baseline)."""
     x = x.float()
-    taps = encoder_taps(sd, x, arch, stages)
+    taps = encoder_taps(sd, x, arch, stages, sdpa)
     if stages is not None:
         for i, t in enumerate(taps):
             stages[f"tap{i}"] = t

@@ -36,7 +36,9 @@ def _newest_source_mtime():
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
+        print(f"s3od_b200.build: {LIB_PATH} is newer than every source under csrc/ and include/ - reused (force=True / --force recompiles)")
         return LIB_PATH
+    print(f"s3od_b200.build: compiling {len(SOURCES)} translation units for sm_100a with nvcc ({'forced' if force else 'sources changed'})")
     nvcc = _nvcc()
     extra = os.environ.get("S3OD_NVCC_FLAGS", "").split()       # experiments only (e.g. -DS3OD_ATTN_POLY_EVERY=4)
     objs = [os.path.join(LIB_DIR, s.replace(".cu", ".o")) for s in SOURCES]

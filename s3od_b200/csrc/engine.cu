@@ -380,6 +380,14 @@ bool add_conv3x3(s3od_ctx* c, const std::string& label, const bf16* in, int Hs, 
 #define S3OD_FLAT_TILES 1
 #endif
 constexpr bool kFlatTiles = S3OD_FLAT_TILES != 0;
+#ifndef S3OD_SWAP128
+#define S3OD_SWAP128 1
+#endif
+#ifndef S3OD_ROWCONV
+#define S3OD_ROWCONV 1
+#endif
+constexpr bool kSwap128 = S3OD_SWAP128 != 0;      // compile-time A/B switches (tools/build_variants.sh); never read from the environment
+constexpr bool kRowConv = S3OD_ROWCONV != 0;
 
 bool build_plan(s3od_ctx* c) {
   const int mb = c->mb, g = c->g, P = c->P, ntok = c->ntok, D = c->D, H = c->H, I = c->I, K = c->K, S = c->S;
@@ -620,11 +628,10 @@ bool build_plan(s3od_ctx* c) {
   }
   // ---- mask head (model.py:455-467)
   bf16 *p1 = aptr<bf16>(c, "p1"), *mh1 = aptr<bf16>(c, "mh1"), *feat0 = aptr<bf16>(c, "feat0"), *feat = aptr<bf16>(c, "feat");
-  // 256 -> 128 channels: operand-swapped kernel (conv_swap.cuh) when the tile grid pairs up; S3OD_SWAP128=0 keeps the 128-wide
-  // pair GEMM (A/B switch)
+  // 256 -> 128 channels: operand-swapped kernel (conv_swap.cuh) when the tile grid pairs up, else the 128-wide pair GEMM
+  // (-DS3OD_SWAP128=0 builds the library without the swapped kernel: A/B measurements only)
   const ConvGeom g_c1 = geom_3x3(R0, R0, 256);
-  const char* swap_env = getenv("S3OD_SWAP128");
-  if ((swap_env == nullptr || swap_env[0] != '0') && (g_c1.tiles_h * g_c1.tiles_w) % 2 == 0) {
+  if (kSwap128 && (g_c1.tiles_h * g_c1.tiles_w) % 2 == 0) {
     ConvSwapParams sp{};
     if (!tmap_nhwc(&sp.tma_x, p1, mb, R0, R0, 256)) return false;
     if (!tmap_matrix(&sp.tma_w, wptr<bf16>(c, "head.mh.c1.w"), 128, 9 * 256, 128)) return false;
@@ -643,7 +650,7 @@ bool build_plan(s3od_ctx* c) {
                                   conv_epi(mh1, nullptr, wptr<float>(c, "head.mh.c1.b"), nullptr, nullptr, 0, 128, R0, R0))) {
     return false;
   }
-  const bool rows_ok = (S % kRowPx == 0) && getenv("S3OD_NO_ROWCONV") == nullptr;
+  const bool rows_ok = kRowConv && (S % kRowPx == 0);
   if (rows_ok && R0 % kRowPx == 0) {
     // ConvTranspose2d k4 s2 p1 + ReLU on the row-streaming kernel, one launch per output-column phase
     ConvTRowParams p{};
@@ -699,30 +706,48 @@ bool build_plan(s3od_ctx* c) {
   return true;
 }
 
-std::vector<std::string> required_tensors(const s3od_ctx* c) {
-  std::vector<std::string> r = {"patch.w", "patch.b", "prefix", "pre.lut"};
+// Every tensor the plan reads, with the exact byte size the architecture implies (D / I / heads / out_channels / K): the
+// launch plan builds TMA maps and pointers from these dimensions alone, so a checkpoint of another architecture must be
+// refused here - the reference's strict load_state_dict raises in the same situation (predictor.py:76).
+std::vector<std::pair<std::string, size_t>> required_tensors(const s3od_ctx* c) {
+  const size_t D = c->D, I = c->I, K = c->K, F = 256;
+  std::vector<std::pair<std::string, size_t>> r = {
+      {"patch.w", D * 768 * 2}, {"patch.b", D * 4}, {"prefix", 5 * D * 4}, {"pre.lut", 768 * 2}};
   for (int l = 0; l < c->L; ++l) {
     const std::string p = "enc." + std::to_string(l) + ".";
-    for (const char* s : {"ln1.w", "ln1.b", "qkv.w", "qkv.b", "o.w", "o.b", "ls1", "ln2.w", "ln2.b", "up.w", "up.b", "down.w", "down.b", "ls2"})
-      r.push_back(p + s);
+    r.push_back({p + "ln1.w", D * 4}); r.push_back({p + "ln1.b", D * 4});
+    r.push_back({p + "qkv.w", 3 * D * D * 2}); r.push_back({p + "qkv.b", 3 * D * 4});
+    r.push_back({p + "o.w", D * D * 2}); r.push_back({p + "o.b", D * 4}); r.push_back({p + "ls1", D * 4});
+    r.push_back({p + "ln2.w", D * 4}); r.push_back({p + "ln2.b", D * 4});
+    r.push_back({p + "up.w", I * D * 2}); r.push_back({p + "up.b", I * 4});
+    r.push_back({p + "down.w", D * I * 2}); r.push_back({p + "down.b", D * 4}); r.push_back({p + "ls2", D * 4});
   }
   for (int j = 0; j < 4; ++j) {
-    r.push_back("head.proj" + std::to_string(j) + ".w");
-    r.push_back("head.proj" + std::to_string(j) + ".b");
-    r.push_back("head.rn" + std::to_string(j + 1) + ".w");
+    const size_t oc = c->oc[j];
+    r.push_back({"head.proj" + std::to_string(j) + ".w", oc * D * 2});
+    r.push_back({"head.proj" + std::to_string(j) + ".b", oc * 4});
+    r.push_back({"head.rn" + std::to_string(j + 1) + ".w", F * 9 * oc * 2});
   }
-  for (const char* s : {"head.rs0.w", "head.rs0.b", "head.rs1.w", "head.rs1.b", "head.rs3.w", "head.rs3.b", "head.mh.c1.w", "head.mh.c1.b",
-                        "head.mh.up.w", "head.mh.up.wr", "head.mh.up.b", "head.mh.c2.w", "head.mh.c2.b", "head.mh.heads.w", "head.mh.heads.b",
-                        "head.mh.heads.w2", "head.mh.heads.b2", "head.cls.w1", "head.cls.b1", "head.cls.w2", "head.cls.b2"})
-    r.push_back(s);
+  const size_t oc0 = c->oc[0], oc1 = c->oc[1], oc3 = c->oc[3];
+  r.push_back({"head.rs0.w", 16 * oc0 * oc0 * 2}); r.push_back({"head.rs0.b", oc0 * 4});
+  r.push_back({"head.rs1.w", 4 * oc1 * oc1 * 2}); r.push_back({"head.rs1.b", oc1 * 4});
+  r.push_back({"head.rs3.w", oc3 * 9 * oc3 * 2}); r.push_back({"head.rs3.b", oc3 * 4});
+  r.push_back({"head.mh.c1.w", 128 * 9 * F * 2}); r.push_back({"head.mh.c1.b", 128 * 4});
+  r.push_back({"head.mh.up.w", 4 * 64 * 4 * 128 * 2}); r.push_back({"head.mh.up.wr", 16 * 64 * 128 * 2});
+  r.push_back({"head.mh.up.b", 64 * 4});
+  r.push_back({"head.mh.c2.w", 64 * 9 * 64 * 2}); r.push_back({"head.mh.c2.b", 64 * 4});
+  r.push_back({"head.mh.heads.w", 32 * K * 9 * 64 * 2}); r.push_back({"head.mh.heads.b", 32 * K * 4});
+  r.push_back({"head.mh.heads.w2", K * 32 * 4}); r.push_back({"head.mh.heads.b2", K * 4});
+  r.push_back({"head.cls.w1", 64 * F * 4}); r.push_back({"head.cls.b1", 64 * 4});
+  r.push_back({"head.cls.w2", K * 64 * 4}); r.push_back({"head.cls.b2", K * 4});
   for (int k = 1; k <= 4; ++k) {
     const std::string p = "head.ref" + std::to_string(k) + ".";
-    r.push_back(p + "out.w");
-    r.push_back(p + "out.b");
+    r.push_back({p + "out.w", F * F * 2});
+    r.push_back({p + "out.b", F * 4});
     for (int u = (k == 4 ? 2 : 1); u <= 2; ++u)
       for (int cc = 1; cc <= 2; ++cc) {
-        r.push_back(p + "rcu" + std::to_string(u) + ".c" + std::to_string(cc) + ".w");
-        r.push_back(p + "rcu" + std::to_string(u) + ".c" + std::to_string(cc) + ".b");
+        r.push_back({p + "rcu" + std::to_string(u) + ".c" + std::to_string(cc) + ".w", F * 9 * F * 2});
+        r.push_back({p + "rcu" + std::to_string(u) + ".c" + std::to_string(cc) + ".b", F * 4});
       }
   }
   return r;
@@ -782,8 +807,13 @@ int s3od_finalize(s3od_ctx* c) {
   if (c == nullptr) return fail(S3OD_ERR_ARG, "null ctx");
   if (c->finalized) return S3OD_OK;
   CK(cudaSetDevice(c->device));
-  for (const std::string& n : required_tensors(c))
-    if (c->w.find(n) == c->w.end()) return fail(S3OD_ERR_MISSING, "missing tensor: " + n);
+  for (const auto& req : required_tensors(c)) {
+    auto it = c->w.find(req.first);
+    if (it == c->w.end()) return fail(S3OD_ERR_MISSING, "missing tensor: " + req.first);
+    if (it->second.bytes != req.second)
+      return fail(S3OD_ERR_ARG, "size mismatch for " + req.first + ": got " + std::to_string(it->second.bytes) + " bytes, this architecture needs " +
+                                    std::to_string(req.second) + " (checkpoint of another model?)");
+  }
   CK(cudaMalloc(reinterpret_cast<void**>(&c->d_img), sizeof(ImageDesc) * c->max_batch));
   CK(cudaMalloc(reinterpret_cast<void**>(&c->d_post), sizeof(PostDesc) * c->max_batch));
   // Optional "pre.affine" = {a[3], b[3]} fp32: the preprocess kernel evaluates bf16(fma(v, a, b)) instead of the table
@@ -1072,13 +1102,6 @@ int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d
   ap.out = static_cast<bf16*>(d_out);
   ap.ntok = ntok; ap.heads = heads; ap.kv_tiles = (ntok + kAttnKvTile - 1) / kAttnKvTile;
   CK(launch_attention(ap, (ntok + kAttnTile - 1) / kAttnTile, static_cast<int>(BH), static_cast<cudaStream_t>(stream)));
-  return S3OD_OK;
-}
-
-// debug: copies the 64 x 8 clock64() stamps written by the traced attention CTA (S3OD_ATTN_TRACE=1) to the host
-int s3od_debug_attn_trace(long long* host_out) {
-  if (g_attn_trace == nullptr || host_out == nullptr) return fail(S3OD_ERR_STATE, "attention tracing is off (set S3OD_ATTN_TRACE=1)");
-  CK(cudaMemcpy(host_out, g_attn_trace, 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
   return S3OD_OK;
 }
 

@@ -11,8 +11,6 @@
 
 namespace s3od {
 
-long long* g_attn_trace = nullptr;
-
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
@@ -21,16 +19,8 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
     configured = true;
   }
   AttnParams q = p;
-  static long long* trace_buf = nullptr;      // S3OD_ATTN_TRACE=1: clock64() stamps of one CTA, read back with s3od_debug_attn_trace
-  static const bool want_trace = getenv("S3OD_ATTN_TRACE") != nullptr;
-  if (want_trace && trace_buf == nullptr) {
-    cudaMalloc(&trace_buf, 64 * 8 * sizeof(long long));
-    cudaMemset(trace_buf, 0, 64 * 8 * sizeof(long long));
-  }
-  q.trace = trace_buf;
-  static const char* tb = getenv("S3OD_ATTN_TRACE_BH");
-  q.trace_bh = tb != nullptr ? atoi(tb) : 0;
-  g_attn_trace = trace_buf;
+  q.trace = nullptr;            // per-step clock64() stamps exist only in the tools/lab build (S3OD_ATTN_TRACE_BUILD)
+  q.trace_bh = 0;
   q.bh_total = bh;
   attention_kernel<<<((q_tiles + 1) / 2) * bh, kAttnThreads, kAttnSmemBytes, stream>>>(q);   // two query tiles per CTA, 1-D grid
   return cudaGetLastError();

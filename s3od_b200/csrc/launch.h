@@ -5,19 +5,15 @@
 #include "conv_swap.cuh"
 #include "types.h"
 
-#include <cstdlib>
-
 namespace s3od {
 
-// BN = 256 / 128 tiles run on the CTA-pair kernel (gemm_tc2.cuh); S3OD_PAIR=0 selects the one-CTA kernel (A/B measurements).
+// BN = 256 / 128 tiles run on the CTA-pair kernel (gemm_tc2.cuh); -DS3OD_PAIR=0 builds the library on the one-CTA kernel
+// instead (A/B measurements; compile-time, never read from the environment).
 // The B tensor map's box must match: each CTA of a pair fetches a 128-row half of the 256-row tile.
-inline bool use_pair_kernel() {
-  static const bool on = [] {
-    const char* e = getenv("S3OD_PAIR");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
-}
+#ifndef S3OD_PAIR
+#define S3OD_PAIR 1
+#endif
+constexpr bool use_pair_kernel() { return S3OD_PAIR != 0; }
 template <int BN>
 inline int b_box_rows() { return ((BN == 256 || BN == 128) && use_pair_kernel()) ? BN / 2 : BN; }
 
@@ -30,7 +26,6 @@ cudaError_t launch_conv_rows(const RowConvParams<Epi>& p, int num_sms, cudaStrea
 cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv_swap128(const ConvSwapParams& p, int num_sms, cudaStream_t stream);
 
-extern long long* g_attn_trace;
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream);
 // x += dx (optional), tap = bf16(x) on patch rows (optional), y = LayerNorm(x) (optional)
 cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,

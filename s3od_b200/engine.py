@@ -8,6 +8,7 @@ module raises.
 """
 import ctypes
 import os
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -124,8 +125,20 @@ class B200DPTSegmentation:
                 _check(self.lib, self.lib.s3od_set_tensor(self._ctx, name.encode(), t.data_ptr(), t.numel() * t.element_size()),
                        f"s3od_set_tensor({name})")
             _check(self.lib, self.lib.s3od_finalize(self._ctx), "s3od_finalize")
-        self._tab_cache: Dict[Tuple, Tuple] = {}
-        self._buf_cache: Dict[Tuple, torch.Tensor] = {}
+        # Host-side caches are BOUNDED (a long-lived predictor fed images of every size - the reference's Gradio demo - must
+        # not grow without limit; the reference frees everything after each call):
+        #   _tab_cache   resize / antialias coefficient tables per geometry, least-recently-used, at most `max_tables`;
+        #   _fixed       per-slot buffers whose shape only depends on (max_batch, K, S);
+        #   _arena       ONE flat byte buffer per output slot, sized to the largest request so far (+25 % on growth) and
+        #                carved into the per-image (K,H,W) fp32 / (H,W,4) u8 views of each call.
+        self.max_tables = 64
+        self._tab_cache: "OrderedDict[Tuple, Tuple]" = OrderedDict()
+        self._fixed: Dict[Tuple, torch.Tensor] = {}
+        self._arena: Dict[int, torch.Tensor] = {}
+        self._arena_off: Dict[int, int] = {}
+        # streams other than the launch stream that read slot buffers (the predictor's copy-out stream): a retired arena is
+        # handed back to the allocator only after their queued work
+        self.aux_streams: List[torch.cuda.Stream] = []
 
     # -- nn.Module-ish surface used by BackgroundRemoval ----------------------------------------------------------
     def to(self, device):
@@ -152,16 +165,37 @@ class B200DPTSegmentation:
             return self._forward_staged(B)
 
     def _buffer(self, slot, name: str, shape, dtype) -> torch.Tensor:
-        """Reusable device buffer.  slot=None allocates a fresh tensor; an integer slot returns the same storage on every
-        call with that (slot, name, shape) - the steady-state hot path then makes no allocator calls at all."""
+        """Reusable device buffer of a batch-independent shape.  slot=None allocates a fresh tensor; an integer slot returns
+        the same storage on every call - the steady-state hot path then makes no allocator calls at all."""
         if slot is None:
             return torch.empty(shape, dtype=dtype, device=self.device)
         key = (slot, name, tuple(shape), dtype)
-        t = self._buf_cache.get(key)
+        t = self._fixed.get(key)
         if t is None:
             t = torch.empty(shape, dtype=dtype, device=self.device)
-            self._buf_cache[key] = t
+            self._fixed[key] = t
         return t
+
+    def _arena_reserve(self, slot: int, nbytes: int) -> None:
+        """Start carving slot `slot`'s arena for a call that needs `nbytes` in total; grows (and retires the old buffer) if short."""
+        cur = self._arena.get(slot)
+        if cur is None or cur.numel() < nbytes:
+            new = torch.empty(max(nbytes, (cur.numel() * 5 // 4) if cur is not None else 0), dtype=torch.uint8, device=self.device)
+            if cur is not None:
+                for st in self.aux_streams:
+                    cur.record_stream(st)
+            self._arena[slot] = new
+        self._arena_off[slot] = 0
+
+    def _arena_take(self, slot: int, shape, dtype) -> torch.Tensor:
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        off = self._arena_off[slot]
+        self._arena_off[slot] = off + ((n + 255) & ~255)
+        return self._arena[slot][off:off + n].view(dtype).view(shape)
+
+    def cache_bytes(self) -> int:
+        """Device bytes held by the reusable output buffers (bounded: 3 slots x the largest call so far)."""
+        return sum(t.numel() * t.element_size() for t in self._fixed.values()) + sum(t.numel() for t in self._arena.values())
 
     def _forward_staged(self, B: int, slot=None) -> Dict[str, torch.Tensor]:
         S, K = self.image_size, self.K
@@ -177,6 +211,10 @@ class B200DPTSegmentation:
         if t is None:
             t = builder()
             self._tab_cache[key] = t
+            while len(self._tab_cache) > self.max_tables:       # LRU; evicted tables were allocated on the launch stream, so
+                self._tab_cache.popitem(last=False)             # the allocator reuses them in stream order
+        else:
+            self._tab_cache.move_to_end(key)
         return t
 
     def geometry(self, h: int, w: int):
@@ -220,14 +258,21 @@ class B200DPTSegmentation:
         S, K = self.image_size, self.K
         descs = (S3odPost * B)()
         outs = []
+        if slot is not None:
+            self._arena_reserve(slot, sum(((K * p["original_size"][0] * p["original_size"][1] * 4 + 255) & ~255) +
+                                          ((p["original_size"][0] * p["original_size"][1] * 4 + 255) & ~255) for p in pads))
         for i, (img, pad) in enumerate(zip(d_images, pads)):
             H, W = pad["original_size"]
             hp, wp = pad["height_pad"], pad["width_pad"]
             ch, cw = S - 2 * hp, S - 2 * wp
             ys, yw, xs, xw = self._tables(("aa", ch, cw, H, W), lambda: tuple(
                 torch.from_numpy(a).to(self.device) for a in (geometry.aa_tables(ch, H) + geometry.aa_tables(cw, W))))
-            all_masks = self._buffer(slot, f"all_masks{i}", (K, H, W), torch.float32)
-            rgba = self._buffer(slot, f"rgba{i}", (H, W, 4), torch.uint8)
+            if slot is None:
+                all_masks = torch.empty((K, H, W), dtype=torch.float32, device=self.device)
+                rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=self.device)
+            else:
+                all_masks = self._arena_take(slot, (K, H, W), torch.float32)
+                rgba = self._arena_take(slot, (H, W, 4), torch.uint8)
             descs[i] = S3odPost(img.data_ptr(), all_masks.data_ptr(), rgba.data_ptr(), H, W, hp, wp, yw.shape[1], xw.shape[1],
                                 ys.data_ptr(), yw.data_ptr(), xs.data_ptr(), xw.data_ptr())
             outs.append((all_masks, rgba))

@@ -37,3 +37,10 @@ def check_padding(pad_info: Dict[str, Any], image_size: int) -> None:
     if hp == 0 and wp > 0 and image_size - 2 * wp != new_w:
         raise ValueError(f"could not broadcast input array from shape ({new_h},{new_w},3) into shape "
                          f"({image_size},{image_size - 2 * wp},3)")
+    if hp == 0 and wp == 0 and (new_h != image_size or new_w != image_size):
+        # One pixel short on the short side (e.g. a 1025 x 1024 source): both pads are 0, so the reference takes
+        # `padded = resized` (predictor.py:88-89) and runs the network on a NON-square (S-1) x S input - a 63 x 64 patch grid
+        # and a 1008-row mask.  The launch plan here is built for the square S x S canvas only; rather than return a mask
+        # that differs from the reference's, refuse the geometry explicitly.
+        raise ValueError(f"unsupported geometry: the resized image is {new_h}x{new_w} with zero padding, which the reference "
+                         f"feeds to the network as a non-square input; s3od_b200 only runs the square {image_size}x{image_size} canvas")

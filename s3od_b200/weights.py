@@ -116,7 +116,87 @@ def albumentations_affine() -> torch.Tensor:
     return torch.from_numpy(np.concatenate([den, (-mean.astype(np.float64) * den.astype(np.float64)).astype(f32)])).contiguous()
 
 
+def expected_shapes(arch: ArchSpec, prefix: str = "encoder.model.layer.") -> Dict[str, tuple]:
+    """Key -> shape of the reference checkpoint for `arch` (SURVEY 8b weight contract; what `DPTSegmentation(...)` builds at
+    /root/reference/src/s3od/predictor.py:67-74).  `num_batches_tracked` buffers are listed with shape ()."""
+    D, I, F, K, ps = arch.hidden, arch.mlp, arch.features, arch.num_outputs, arch.patch
+    oc, inter = arch.out_channels, arch.inter_features
+    sh: Dict[str, tuple] = {}
+    e = "encoder.embeddings."
+    sh[e + "cls_token"] = (1, 1, D)
+    sh[e + "mask_token"] = (1, 1, D)
+    sh[e + "register_tokens"] = (1, arch.n_prefix - 1, D)
+    sh[e + "patch_embeddings.weight"] = (D, 3, ps, ps)
+    sh[e + "patch_embeddings.bias"] = (D,)
+    for i in range(arch.layers):
+        p = f"{prefix}{i}."
+        for n in ("norm1", "norm2"):
+            sh[p + n + ".weight"] = sh[p + n + ".bias"] = (D,)
+        for n in ("q_proj", "v_proj", "o_proj"):
+            sh[p + f"attention.{n}.weight"] = (D, D)
+            sh[p + f"attention.{n}.bias"] = (D,)
+        sh[p + "attention.k_proj.weight"] = (D, D)
+        sh[p + "layer_scale1.lambda1"] = sh[p + "layer_scale2.lambda1"] = (D,)
+        sh[p + "mlp.up_proj.weight"], sh[p + "mlp.up_proj.bias"] = (I, D), (I,)
+        sh[p + "mlp.down_proj.weight"], sh[p + "mlp.down_proj.bias"] = (D, I), (D,)
+    sh["encoder.norm.weight"] = sh["encoder.norm.bias"] = (D,)
+    h = "seg_head."
+    for j, c in enumerate(oc):
+        sh[h + f"projects.{j}.weight"], sh[h + f"projects.{j}.bias"] = (c, D, 1, 1), (c,)
+        sh[h + f"scratch.layer{j + 1}_rn.weight"] = (F, c, 3, 3)
+    sh[h + "resize_layers.0.weight"], sh[h + "resize_layers.0.bias"] = (oc[0], oc[0], 4, 4), (oc[0],)
+    sh[h + "resize_layers.1.weight"], sh[h + "resize_layers.1.bias"] = (oc[1], oc[1], 2, 2), (oc[1],)
+    sh[h + "resize_layers.3.weight"], sh[h + "resize_layers.3.bias"] = (oc[3], oc[3], 3, 3), (oc[3],)
+    for r in range(1, 5):
+        p = h + f"scratch.refinenet{r}."
+        sh[p + "out_conv.weight"], sh[p + "out_conv.bias"] = (F, F, 1, 1), (F,)
+        for u in (1, 2):
+            for cidx in (1, 2):
+                q = p + f"resConfUnit{u}."
+                sh[q + f"conv{cidx}.weight"], sh[q + f"conv{cidx}.bias"] = (F, F, 3, 3), (F,)
+                for n in ("weight", "bias", "running_mean", "running_var"):
+                    sh[q + f"bn{cidx}.{n}"] = (F,)
+                sh[q + f"bn{cidx}.num_batches_tracked"] = ()
+    m = h + "mask_head."
+    sh[m + "output_conv1.weight"], sh[m + "output_conv1.bias"] = (F // 2, F, 3, 3), (F // 2,)
+    sh[m + "upsample_2x.0.weight"], sh[m + "upsample_2x.0.bias"] = (F // 2, 2 * inter, 4, 4), (2 * inter,)
+    sh[m + "upsample_2x.2.weight"], sh[m + "upsample_2x.2.bias"] = (2 * inter, 2 * inter, 3, 3), (2 * inter,)
+    for k in range(K):
+        sh[m + f"mask_heads.{k}.0.weight"], sh[m + f"mask_heads.{k}.0.bias"] = (inter, 2 * inter, 3, 3), (inter,)
+        sh[m + f"mask_heads.{k}.2.weight"], sh[m + f"mask_heads.{k}.2.bias"] = (1, inter, 1, 1), (1,)
+    c = h + "classifier_head."
+    sh[c + "2.weight"], sh[c + "2.bias"] = (64, F), (64,)
+    sh[c + "4.weight"], sh[c + "4.bias"] = (K, 64), (K,)
+    return sh
+
+
+# present in some exports, never in the parameter set the path reads: the non-persistent RoPE buffer (SURVEY 8b) and k_proj.bias
+# tensors of checkpoints written with key_bias=true (config.json:12 says false; a present bias is honoured below)
+_OPTIONAL_SUFFIXES = ("rope_embeddings.inv_freq", "attention.k_proj.bias", "num_batches_tracked")
+
+
+def validate_state_dict(sd: Dict[str, torch.Tensor], arch: ArchSpec) -> None:
+    """Strict ingest, like `model.load_state_dict(state_dict)` at /root/reference/src/s3od/predictor.py:76: missing keys,
+    unexpected keys and size mismatches raise RuntimeError (the type torch raises there) before anything reaches the GPU."""
+    want = expected_shapes(arch, _enc_prefix(sd))
+    missing = [k for k in want if k not in sd and not k.endswith(_OPTIONAL_SUFFIXES)]
+    unexpected = [k for k in sd if k not in want and not k.endswith(_OPTIONAL_SUFFIXES)]
+    mismatched = [f"{k}: checkpoint {tuple(sd[k].shape)} vs model {want[k]}" for k in want
+                  if k in sd and torch.is_tensor(sd[k]) and tuple(sd[k].shape) != want[k]]
+    if missing or unexpected or mismatched:
+        parts = []
+        if missing:
+            parts.append("Missing key(s) in state_dict: " + ", ".join(repr(k) for k in missing[:8]) + (" ..." if len(missing) > 8 else ""))
+        if unexpected:
+            parts.append("Unexpected key(s) in state_dict: " + ", ".join(repr(k) for k in unexpected[:8]) + (" ..." if len(unexpected) > 8 else ""))
+        if mismatched:
+            parts.append("size mismatch for " + "; ".join(mismatched[:8]) + (" ..." if len(mismatched) > 8 else ""))
+        raise RuntimeError(f"Error(s) in loading state_dict for DPTSegmentation ({arch.name}, num_outputs={arch.num_outputs}):\n\t"
+                           + "\n\t".join(parts))
+
+
 def pack_weights(sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int, normalisation: str = "s3od") -> Dict[str, torch.Tensor]:
+    validate_state_dict(sd, arch)
     D, I, K = arch.hidden, arch.mlp, arch.num_outputs
     out: Dict[str, torch.Tensor] = {}
     e = "encoder.embeddings."

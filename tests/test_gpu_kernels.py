@@ -36,6 +36,29 @@ def test_gemm_tcgen05(lib, M, N, K):
     assert float((c.double() - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) * max(1.0, K / 768)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_gemm_pair_accumulator_handoff_stress(lib, seed):
+    """TMEM write-after-read stress for the CTA-pair GEMM's RELAXED remote "accumulator free" arrival (gemm_tc2.cuh): K = 64 is
+    ONE k-block, so every main loop is as short as it can be while the epilogue (fp32 stores of a 256 x 256 tile) is at its
+    longest - 10 240 CTA tiles (1280 M tiles x 8 N tiles) through two accumulator stages per CTA.  An MMA that overwrote an
+    accumulator before the epilogue warps had read it would show up as a wrong block; the result is compared element by element
+    with fp64 (bf16 products are exact in fp32, K = 64 sums differ by accumulation order only)."""
+    M, N, K = 128 * 1280, 2048, 64
+    g = torch.Generator(device="cuda").manual_seed(100 + seed)
+    # every tile gets its own magnitude, so a stale / prematurely overwritten accumulator cannot pass as a neighbour's values
+    a = (torch.randn(M, K, device="cuda", generator=g) * (1.0 + (torch.arange(M, device="cuda") // 128 % 7).float()[:, None])).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) * (1.0 + (torch.arange(N, device="cuda") // 256 % 5).float()[:, None])).bfloat16()
+    c = torch.full((M, N), float("nan"), device="cuda")
+    for _ in range(2):                       # the second pass runs with every accumulator stage already used once
+        assert lib.s3od_op_gemm_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, _st()) == 0
+    torch.cuda.synchronize()
+    worst = 0.0
+    for r0 in range(0, M, 16384):            # fp64 reference in row blocks (2048 x 16384 doubles at a time)
+        ref = a[r0:r0 + 16384].double() @ b.double().t()
+        worst = max(worst, float((c[r0:r0 + 16384].double() - ref).abs().max()) / float(ref.abs().max()))
+    assert worst <= 2e-5, worst
+
+
 def test_gemm_rejects_bad_shape(lib):
     a = torch.zeros(8, 64, device="cuda", dtype=torch.bfloat16)
     c = torch.zeros(8, 100, device="cuda")

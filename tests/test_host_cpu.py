@@ -194,3 +194,44 @@ def test_chunk_schedule_covers_the_batch_and_ends_small():
             assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
             assert all(0 < e - s0 <= step for s0, e in b)
             assert b[-1][1] - b[-1][0] <= 4
+
+
+def test_strict_checkpoint_ingest_like_load_state_dict(vitb_sd):
+    """predictor.py:76 loads strictly: a checkpoint of another architecture, a missing or an unexpected key raises
+    RuntimeError before anything is packed (no silent garbage masks / out-of-bounds reads)."""
+    from s3od_b200.arch import VITB, VITL
+    from s3od_b200.weights import expected_shapes, pack_weights, validate_state_dict
+    assert len(expected_shapes(VITB)) == 371 == len(vitb_sd)                       # SURVEY 8b: 355 fp32 + 16 int64 entries
+    validate_state_dict(vitb_sd, VITB)
+    with pytest.raises(RuntimeError, match="Missing key"):
+        pack_weights(vitb_sd, VITL, 64)                                            # ViT-B weights, ViT-L model
+    bad = dict(vitb_sd)
+    bad.pop("seg_head.classifier_head.4.bias")
+    with pytest.raises(RuntimeError, match="Missing key"):
+        validate_state_dict(bad, VITB)
+    bad = dict(vitb_sd)
+    bad["seg_head.extra.weight"] = torch.zeros(3)
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        validate_state_dict(bad, VITB)
+    bad = dict(vitb_sd)
+    bad["seg_head.scratch.layer1_rn.weight"] = torch.zeros(128, 256, 3, 3)         # features != 256
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        validate_state_dict(bad, VITB)
+    from dataclasses import replace
+    with pytest.raises(RuntimeError, match="size mismatch|Missing key"):
+        validate_state_dict(vitb_sd, replace(VITB, num_outputs=1))
+    # the older transformers layout (encoder.layer.N.*, SURVEY F4) is the same checkpoint under other names
+    old = {k.replace("encoder.model.layer.", "encoder.layer."): v for k, v in vitb_sd.items()}
+    validate_state_dict(old, VITB)
+
+
+def test_zero_pad_non_square_geometry_is_refused():
+    """A source one pixel off square (1025 x 1024) resizes to 1024 x 1023 with BOTH pads 0: the reference then feeds the
+    network a non-square input (predictor.py:88-89).  The square launch plan cannot reproduce that, so it raises."""
+    from s3od_b200.utils import check_padding, get_pad_info
+    for hw in ((1025, 1024), (1024, 1023)):
+        pad = get_pad_info(np.empty(hw + (0,), np.uint8), 1024)
+        assert pad["height_pad"] == 0 and pad["width_pad"] == 0 and pad["resized_size"] != (1024, 1024)
+        with pytest.raises(ValueError, match="non-square"):
+            check_padding(pad, 1024)
+    check_padding(get_pad_info(np.empty((2048, 2048, 0), np.uint8), 1024), 1024)
