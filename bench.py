@@ -59,7 +59,7 @@ def newest_traffic(kernel: str, micro_batch: int, model: str, image_size: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -297,7 +297,7 @@ def extra_leg(model_name, S, src, B, micro_batch, local_rank, rank, world, dev, 
     np_imgs, d_imgs = make_images(B, src, 10_000 + b0, dev)
     ms, launches, _, _, out = time_device(br.model, d_imgs, steps, 3, dev)
     del out
-    t_e2e, res = time_e2e(br, np_imgs, e2e_steps, 1, dev)
+    t_e2e, res = time_e2e(br, np_imgs, e2e_steps, 2, dev)      # 2 warm-ups: both alternating sets of pinned result buffers exist
     del res, d_imgs
     K = arch.num_outputs
     ent = {"workload": f"{model_name} inference bf16, batch {B} synthetic {src}x{src} uint8 images per GPU, image_size {S}",
