@@ -133,6 +133,32 @@ int s3od_mask_pair_counts(const float* d_masks, int num_masks, int h, int w, uns
  *     the soft masks come from s3od_postprocess.  Buffers 16-byte aligned. */
 int s3od_threshold_f32(const float* d_in, float* d_out, size_t n, float threshold, s3od_stream stream);
 
+/* ---- training step (BASELINE.json configs[3]; SURVEY 8e "training"): loss forward + backward and the optimiser update.
+ * s3od_loss_forward_backward replaces LossModule.forward + autograd through it
+ *   (synth_sod/src/synth_sod/model_training/loss.py:242-275 -> compute_multi_mask_losses :190-233 / compute_single_mask_loss
+ *   :166-188, FocalLoss :126-143 fed ALREADY-SIGMOIDED masks, IoULoss :79-99, compute_iou :155-164, and the MSE
+ *   between sigmoid(pred_iou) and the measured IoUs) with the components of config/loss/focal_iou.yaml.
+ *   d_mask_logits (B, K, h, w) fp32 = outputs['pred_masks'], d_iou_logits (B, K) = outputs['pred_iou'], d_targets (B, h, w) in [0, 1];
+ *   d_grad_mask_logits (B, K, h, w) and d_grad_iou_logits (B, K) receive d loss / d input (d_grad_mask_logits may be NULL: forward only);
+ *   d_out = [total, best_iou, mean gt_ious, focal_best, mean focal_full, iou_best, mean iou_full, mse, gt_ious (B*K), best index (B)]
+ *   (s3od_loss_out_floats(B, K) floats); K = 3 or 1, B <= 64; buffers 16-byte aligned, h*w % 4 == 0.
+ * s3od_adamw_step replaces one torch.optim.AdamW update (lightning_module.py:183-193) over a flat fp32 segment: decoupled
+ *   weight decay, bias correction for 1-based `step`, grad_scale folds the 1 / world of the all-reduced gradient mean;
+ *   d_param_bf16 (optional) receives the bf16 copy of the new parameters for the next forward. */
+typedef struct {
+  float focal_weight, iou_weight, mse_weight;     /* 20, 1, 0.05 (config/loss/focal_iou.yaml) */
+  float full_mask_lambda, decay_rate;             /* 0.1, 0.2 */
+  float alpha, gamma, smooth;                     /* FocalLoss 0.25 / 2.0, IoU smooth 1e-6 */
+} s3od_loss_config;
+void s3od_loss_default_config(s3od_loss_config* cfg);
+size_t s3od_loss_workspace_bytes(int batch, int num_masks, int h, int w);
+size_t s3od_loss_out_floats(int batch, int num_masks);
+int s3od_loss_forward_backward(const float* d_mask_logits, const float* d_iou_logits, const float* d_targets, int batch, int num_masks,
+                               int h, int w, int epoch, const s3od_loss_config* cfg, float* d_grad_mask_logits,
+                               float* d_grad_iou_logits, float* d_out, void* d_workspace, size_t workspace_bytes, s3od_stream stream);
+int s3od_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, size_t n, int step, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, float grad_scale, void* d_param_bf16, s3od_stream stream);
+
 /* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
 /* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */
 int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream);

@@ -88,3 +88,11 @@ def adamw_step(p, g, m, v, step: int, lr: float, wd: float = 0.05, b1: float = 0
     bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
     denom = v.sqrt() / math.sqrt(bc2) + eps
     return p - (lr / bc1) * (m / denom), m, v
+
+
+def single_mask_loss(pred_masks, target_masks) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """MaskLossHandler.compute_single_mask_loss (loss.py:166-188), the num_masks == 1 branch of LossModule.forward (:252-257):
+    only the mask components, each reduced to its mean, no best-mask selection and no auxiliary MSE."""
+    pred = torch.sigmoid(pred_masks.squeeze(1))
+    parts = {"focal_loss": focal_loss(pred, target_masks).mean(), "iou_loss": iou_loss(pred, target_masks).mean()}
+    return FOCAL_WEIGHT * parts["focal_loss"] + IOU_WEIGHT * parts["iou_loss"], parts

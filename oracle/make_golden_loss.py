@@ -68,6 +68,15 @@ def main():
         for k in ("best_iou", "gt_ious", "focal_loss_best", "focal_loss_full", "iou_loss_best", "iou_loss_full", "mse_ious_loss"):
             rec[name + "_" + k] = np.float64(parts[k].item())              # LossModule.forward returns the means (loss.py:274-275)
         print(name, float(loss), {k: float(v) for k, v in parts.items()})
+    # num_masks == 1 branch (LossModule.forward -> compute_single_mask_loss, loss.py:252-257 / 166-188): dinol.yaml's configuration
+    name, logits, _, masks, epoch = cases()[1]
+    z1 = logits[:, :1].clone().requires_grad_(True)
+    loss1, parts1 = lm({"pred_masks": z1}, {"masks": masks}, epoch)
+    loss1.backward()
+    rec["single_logits"], rec["single_masks"] = logits[:, :1].numpy(), masks.numpy()
+    rec["single_loss"], rec["single_grad_logits"] = np.float64(loss1.item()), z1.grad.numpy()
+    rec["single_focal_loss"], rec["single_iou_loss"] = np.float64(parts1["focal_loss"].item()), np.float64(parts1["iou_loss"].item())
+    print("single", float(loss1.detach()), {k: float(v.detach()) for k, v in parts1.items()})
     # one AdamW step with the reference's hyper-parameters on a small tensor pair (encoder group lr, head group lr x 10)
     g = torch.Generator().manual_seed(3)
     for tag, lr in (("enc", 1e-5), ("head", 1e-4)):

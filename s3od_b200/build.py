@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libs3od_b200.so")
-SOURCES = ["engine.cu", "kernels_gemm_enc.cu", "kernels_gemm_head.cu", "kernels_misc.cu"]
+SOURCES = ["engine.cu", "kernels_gemm_enc.cu", "kernels_gemm_head.cu", "kernels_misc.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 

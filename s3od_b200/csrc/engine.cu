@@ -235,6 +235,12 @@ struct s3od_ctx {
 
 namespace {
 
+}  // namespace
+namespace s3od {
+int train_fail(int code, const std::string& msg) { return fail(code, msg); }     // train.cu shares the thread-local error string
+}
+namespace {
+
 template <class T>
 T* wptr(s3od_ctx* c, const std::string& name) {
   auto it = c->w.find(name);

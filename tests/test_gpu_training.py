@@ -1,0 +1,123 @@
+"""Training-step kernels on a real B200, through the C ABI (BASELINE.json configs[3]):
+  * loss forward + backward against the golden vectors written by the UNMODIFIED reference loss.py (values and autograd
+    gradients), and against torch.autograd through the oracle restatement at the configuration's real sizes;
+  * fused AdamW against the golden torch.optim.AdamW steps and against torch.optim.AdamW itself on the full 107.8 M layout.
+Tolerances: fp32 arithmetic with fast-math exp / log1p in the kernels - loss values 2e-6 relative, gradients 1e-5 relative to
+the largest gradient, AdamW 2e-7 absolute per step (one fp32 ulp of the update)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss as ol
+from s3od_b200.arch import VITB
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def loss_module():
+    from s3od_b200.training import LossModule
+    return LossModule()
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+
+
+def test_loss_matches_reference_golden(loss_module, golden_dir):
+    g = np.load(os.path.join(golden_dir, "loss.npz"))
+    for n in g["names"]:
+        out = {"pred_masks": torch.from_numpy(g[n + "_logits"]).cuda(), "pred_iou": torch.from_numpy(g[n + "_iou_logits"]).cuda()}
+        tg = {"masks": torch.from_numpy(g[n + "_masks"]).cuda()}
+        loss, parts, grads, extra = loss_module.forward_backward(out, tg, int(g[n + "_epoch"]))
+        assert abs(float(loss) - float(g[n + "_loss"])) <= 2e-6 * abs(float(g[n + "_loss"]))
+        for k in ("best_iou", "gt_ious", "focal_loss_best", "focal_loss_full", "iou_loss_best", "iou_loss_full", "mse_ious_loss"):
+            assert abs(float(parts[k]) - float(g[n + "_" + k])) <= 2e-6 * max(abs(float(g[n + "_" + k])), 1e-3), k
+        assert _rel(grads["pred_masks"].cpu(), torch.from_numpy(g[n + "_grad_logits"])) <= 1e-5
+        assert _rel(grads["pred_iou"].cpu(), torch.from_numpy(g[n + "_grad_iou"])) <= 1e-5
+        l2, p2 = loss_module(out, tg, int(g[n + "_epoch"]))            # forward only (validation_step) gives the same value
+        assert float(l2) == float(loss)
+    # num_masks == 1 branch (dinol.yaml)
+    out = {"pred_masks": torch.from_numpy(g["single_logits"]).cuda()}
+    loss, parts, grads, _ = loss_module.forward_backward(out, {"masks": torch.from_numpy(g["single_masks"]).cuda()}, 3)
+    assert abs(float(loss) - float(g["single_loss"])) <= 2e-6 * float(g["single_loss"])
+    assert abs(float(parts["focal_loss"]) - float(g["single_focal_loss"])) <= 1e-7
+    assert abs(float(parts["iou_loss"]) - float(g["single_iou_loss"])) <= 1e-6
+    assert _rel(grads["pred_masks"].cpu(), torch.from_numpy(g["single_grad_logits"])) <= 1e-5 and grads["pred_iou"] is None
+
+
+@pytest.mark.parametrize("B,S,epoch", [(4, 1024, 0), (8, 224, 12), (1, 64, 40)])
+def test_loss_matches_autograd_at_training_sizes(loss_module, capsys, B, S, epoch):
+    """config/dataset/synth.yaml (batch 4, 1024^2) and duts.yaml (batch 8, 224^2) shapes vs autograd through the oracle on this GPU."""
+    g = torch.Generator(device="cuda").manual_seed(B * S)
+    yy, xx = torch.meshgrid(torch.arange(S, device="cuda").float(), torch.arange(S, device="cuda").float(), indexing="ij")
+    masks = torch.stack([((((yy - (0.35 + 0.07 * b) * S) / (0.3 * S)) ** 2 + ((xx - 0.5 * S) / (0.25 * S)) ** 2) < 1).float() for b in range(B)])
+    z = (3 * torch.randn(B, 3, S, S, device="cuda", generator=g) + 3 * (masks.unsqueeze(1) - 0.5)).requires_grad_(True)
+    q = torch.randn(B, 3, device="cuda", generator=g).requires_grad_(True)
+    ref, rparts = ol.loss_module(z, q, masks, epoch)
+    ref.backward()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    loss_module.forward_backward({"pred_masks": z.detach(), "pred_iou": q.detach()}, {"masks": masks}, epoch)
+    t0.record()
+    loss, parts, grads, extra = loss_module.forward_backward({"pred_masks": z.detach(), "pred_iou": q.detach()}, {"masks": masks}, epoch)
+    t1.record()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) <= 3e-6 * abs(float(ref))
+    assert torch.equal(extra["best_indices"].cpu(), rparts["best_indices"].cpu())
+    assert float((extra["gt_ious_per_mask"] - rparts["gt_ious"]).abs().max()) <= 2e-6
+    assert _rel(grads["pred_masks"], z.grad) <= 1e-5
+    assert _rel(grads["pred_iou"], q.grad) <= 1e-5
+    ms = t0.elapsed_time(t1)
+    nbytes = B * S * S * 4 * (4 + 4 + 3)                              # pass 1 reads z + t, pass 3 reads z + t and writes dz
+    with capsys.disabled():
+        print(f"\n[loss fwd+bwd B={B} S={S}] {ms * 1e3:.1f} us, {nbytes / ms / 1e6:.0f} GB/s algorithmic")
+
+
+def test_fused_adamw_matches_torch(golden_dir):
+    from s3od_b200.training import FusedAdamW, ParameterLayout
+    g = np.load(os.path.join(golden_dir, "loss.npz"))
+
+    class OneGroup:                                               # a 1000-element layout with a single optimiser group
+        def __init__(self, group):
+            self.group_ranges = {group: (0, 1000), 1 - group: (0, 0)}
+    for tag, group in (("enc", 0), ("head", 1)):
+        p = torch.from_numpy(g[f"adamw_{tag}_p0"]).cuda()
+        opt = FusedAdamW(OneGroup(group), p, lr=1e-5)
+        for s in range(3):
+            opt.step(torch.from_numpy(g[f"adamw_{tag}_grads"][s]).cuda())
+            assert float((p.cpu() - torch.from_numpy(g[f"adamw_{tag}_p{s + 1}"])).abs().max()) <= 2e-7
+    # the full 107.8 M-parameter layout against torch.optim.AdamW with the reference's two groups, gradient mean folded in
+    lay = ParameterLayout(VITB)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    flat = torch.randn(lay.total, device="cuda", generator=gen) * 0.05
+    ref = flat.clone()
+    (h0, h1), (e0, e1) = lay.group_ranges[1], lay.group_ranges[0]
+    rp_head, rp_enc = torch.nn.Parameter(ref[h0:h1].clone()), torch.nn.Parameter(ref[e0:e1].clone())
+    topt = torch.optim.AdamW([{"params": [rp_enc], "lr": 1e-5}, {"params": [rp_head], "lr": 1e-4}], weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8)
+    opt = FusedAdamW(lay, flat, lr=1e-5, bf16_copy=True)
+    world = 8
+    for s in range(2):
+        gsum = torch.randn(lay.total, device="cuda", generator=gen)              # what the all-reduce (sum) leaves in the buffer
+        rp_head.grad, rp_enc.grad = gsum[h0:h1] / world, gsum[e0:e1] / world
+        topt.step()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        opt.step(gsum, grad_scale=1.0 / world)
+        t1.record()
+        torch.cuda.synchronize()
+    assert float((flat[h0:h1] - rp_head.detach()).abs().max()) <= 3e-7
+    assert float((flat[e0:e1] - rp_enc.detach()).abs().max()) <= 3e-7
+    assert torch.equal(opt.param_bf16.float(), flat.bfloat16().float())
+    ms = t0.elapsed_time(t1)
+    print(f"\n[fused AdamW, {lay.numel_with_grad() / 1e6:.1f} M parameters] {ms * 1e3:.0f} us, {lay.total * 30 / ms / 1e6:.0f} GB/s (28 B + 2 B bf16 copy per parameter)")
+
+
+def test_loss_rejects_bad_arguments(loss_module):
+    z = torch.zeros(2, 3, 16, 16, device="cuda")
+    with pytest.raises(ValueError):
+        loss_module.forward_backward({"pred_masks": z, "pred_iou": torch.zeros(2, 3, device="cuda")}, {"masks": torch.zeros(2, 8, 8, device="cuda")}, 0)
+    with pytest.raises(ValueError):                                 # two masks: neither branch of the reference
+        loss_module.forward_backward({"pred_masks": z[:, :2].contiguous(), "pred_iou": torch.zeros(2, 2, device="cuda")},
+                                     {"masks": torch.zeros(2, 16, 16, device="cuda")}, 0)
