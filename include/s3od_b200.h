@@ -159,6 +159,24 @@ int s3od_loss_forward_backward(const float* d_mask_logits, const float* d_iou_lo
 int s3od_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, size_t n, int step, float lr, float beta1,
                     float beta2, float eps, float weight_decay, float grad_scale, void* d_param_bf16, s3od_stream stream);
 
+/* Fused data-parallel exchange + optimiser step over peer memory (NVLink / NVSwitch): replaces DistributedDataParallel's
+ * gradient all-reduce (train.py:116-125 via Lightning) FOLLOWED BY torch.optim.AdamW.step (lightning_module.py:183-193) with one
+ * kernel per rank.  d_grads / d_params / d_params_bf16 [world]: the flat buffers of every rank of the box mapped into this
+ * process (s3od_peer_* below; entry `rank` is this process' own).  Rank r reads the r-th 1/world slice of [begin, end) from
+ * every peer's gradients (summed in rank order: bit-identical replicas), averages, updates its slice of parameters and
+ * moments, and writes the new parameters (fp32, and bf16 when d_params_bf16 != NULL) into every peer's buffers.  The caller
+ * brackets the launch with two stream-ordered barriers (all gradients written / all parameters visible).
+ * s3od_peer_alloc returns a whole device allocation (zeroed) that s3od_peer_export can turn into a 64-byte CUDA IPC handle for
+ * another process of the same box to s3od_peer_open (peer access enabled lazily). */
+int s3od_peer_alloc(void** d_ptr, size_t bytes);
+int s3od_peer_free(void* d_ptr);
+int s3od_peer_export(void* d_ptr, unsigned char handle[64]);
+int s3od_peer_open(const unsigned char handle[64], void** d_ptr);
+int s3od_peer_close(void* d_ptr);
+int s3od_ddp_fused_adamw_step(const float* const* d_grads, float* const* d_params, void* const* d_params_bf16, int world, int rank,
+                              float* d_exp_avg, float* d_exp_avg_sq, size_t begin, size_t end, int step, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, s3od_stream stream);
+
 /* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
 /* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */
 int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream);

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <string>
 
 #include "../../include/s3od_b200.h"
@@ -117,6 +118,82 @@ int s3od_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float
                                                                      static_cast<__nv_bfloat16*>(d_param_bf16));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("adamw kernel: ") + cudaGetErrorString(e));
+  return S3OD_OK;
+}
+
+
+// ---- peer-mapped buffers (CUDA IPC) and the fused exchange + optimiser step over them
+int s3od_peer_alloc(void** d_ptr, size_t bytes) {
+  if (d_ptr == nullptr || bytes == 0) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_peer_alloc");
+  cudaError_t e = cudaMalloc(d_ptr, bytes);                // a whole cudaMalloc allocation: exportable with cudaIpcGetMemHandle
+  if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemset(*d_ptr, 0, bytes);
+  if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+  return S3OD_OK;
+}
+
+int s3od_peer_free(void* d_ptr) {
+  cudaError_t e = cudaFree(d_ptr);
+  if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("cudaFree: ") + cudaGetErrorString(e));
+  return S3OD_OK;
+}
+
+int s3od_peer_export(void* d_ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (d_ptr == nullptr || handle == nullptr) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_peer_export");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, d_ptr);
+  if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  memcpy(handle, &h, 64);
+  return S3OD_OK;
+}
+
+int s3od_peer_open(const unsigned char handle[64], void** d_ptr) {
+  if (d_ptr == nullptr || handle == nullptr) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_peer_open");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  return S3OD_OK;
+}
+
+int s3od_peer_close(void* d_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+  if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e));
+  return S3OD_OK;
+}
+
+int s3od_ddp_fused_adamw_step(const float* const* d_grads, float* const* d_params, void* const* d_params_bf16, int world, int rank,
+                              float* d_exp_avg, float* d_exp_avg_sq, size_t begin, size_t end, int step, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, s3od_stream stream) {
+  if (d_grads == nullptr || d_params == nullptr || d_exp_avg == nullptr || d_exp_avg_sq == nullptr || world < 1 || world > kMaxPeers ||
+      rank < 0 || rank >= world || step < 1 || end < begin)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_ddp_fused_adamw_step (1 <= world <= 8, 0 <= rank < world, step counts from 1)");
+  if ((begin & 3) != 0 || (end & 3) != 0) return train_fail(S3OD_ERR_ARG, "s3od_ddp_fused_adamw_step: the range must start and end on 4-element boundaries");
+  PeerBuffers pb{};
+  // pb.param[0] is read as the master copy: rotate the peer list so that this rank's own buffers come first for the
+  // parameter read while the GRADIENT sum keeps the global rank order (bit-identical replicas)
+  for (int w = 0; w < world; ++w) {
+    if (d_grads[w] == nullptr || d_params[w] == nullptr) return train_fail(S3OD_ERR_ARG, "null peer buffer in s3od_ddp_fused_adamw_step");
+    pb.grad[w] = d_grads[w];
+    pb.param[w] = d_params[(rank + w) % world];
+    pb.param_bf16[w] = d_params_bf16 != nullptr ? static_cast<__nv_bfloat16*>(d_params_bf16[(rank + w) % world]) : nullptr;
+  }
+  // rank r owns the r-th slice of [begin, end), cut on 4-element boundaries
+  const size_t groups = (end - begin) >> 2;
+  const size_t g_lo = groups * rank / world, g_hi = groups * (rank + 1) / world;
+  const size_t lo = begin + (g_lo << 2), hi = begin + (g_hi << 2);
+  if (hi <= lo) return S3OD_OK;
+  AdamWCfg c{};
+  c.lr = lr; c.beta1 = beta1; c.beta2 = beta2; c.eps = eps; c.weight_decay = weight_decay;
+  c.grad_scale = 1.0f / static_cast<float>(world);          // DistributedDataParallel averages the gradients
+  c.bias_correction1 = static_cast<float>(1.0 - std::pow(static_cast<double>(beta1), step));
+  c.inv_sqrt_bias_correction2 = static_cast<float>(1.0 / std::sqrt(1.0 - std::pow(static_cast<double>(beta2), step)));
+  const size_t want = ((hi - lo) / 4 + 511) / 512;
+  const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(want, static_cast<size_t>(2) * num_sms())));
+  adamw_p2p_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(pb, world, d_exp_avg, d_exp_avg_sq, lo, hi, c);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("adamw_p2p kernel: ") + cudaGetErrorString(e));
   return S3OD_OK;
 }
 

@@ -319,4 +319,66 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 
+
+// ------------------------------------------------------------------------------ fused gradient exchange + AdamW over peer memory
+// The data-parallel exchange step of the training configuration as ONE kernel per rank instead of "NCCL all-reduce, then
+// optimiser" (C1 of SURVEY 2b + lightning_module.py:183-193): the flat gradient / parameter buffers of all ranks of the box are
+// mapped into every process (CUDA IPC over NVLink / NVSwitch).  Rank r owns the r-th 1/world slice of the range: it READS that
+// slice of every peer's gradient buffer (P2P loads, summed in rank order 0..world-1, so every replica sees the same bits),
+// applies the AdamW update to its slice of the fp32 master parameters with its slice of the moments (optimiser state and
+// optimiser HBM traffic are 1/world of the replicated form), and WRITES the new parameters - fp32 and the bf16 copy the next
+// forward reads - into every peer's buffers (P2P stores).  Link traffic per GPU = (world-1)/world x 4 B per parameter in each
+// direction, the volume of reduce-scatter + all-gather, with no intermediate HBM round trip and no separate optimiser pass.
+// The caller orders the kernel between two stream-ordered barriers (gradients complete everywhere / parameters visible
+// everywhere); nothing in the kernel waits on another GPU.
+constexpr int kMaxPeers = 8;
+struct PeerBuffers {
+  const float* grad[kMaxPeers];
+  float* param[kMaxPeers];
+  __nv_bfloat16* param_bf16[kMaxPeers];       // all null: no bf16 copy
+};
+
+__global__ void __launch_bounds__(512) adamw_p2p_kernel(PeerBuffers pb, int world, float* __restrict__ m, float* __restrict__ v,
+                                                        size_t lo, size_t hi, AdamWCfg c) {
+  const size_t i0 = lo >> 2, i1 = hi >> 2;                 // the shard is a whole number of float4 groups
+  const float step_size = c.lr / c.bias_correction1;
+  for (size_t i = i0 + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < i1; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 gp[kMaxPeers];
+#pragma unroll
+    for (int w = 0; w < kMaxPeers; ++w)                    // all peers' loads are in flight together (link latency ~ 1-2 us)
+      if (w < world) gp[w] = __ldcs(reinterpret_cast<const float4*>(pb.grad[w]) + i);
+    float gv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int w = 0; w < kMaxPeers; ++w)
+      if (w < world) {                                     // fixed summation order: bit-identical on whichever rank owns the slice
+        gv[0] += gp[w].x; gv[1] += gp[w].y; gv[2] += gp[w].z; gv[3] += gp[w].w;
+      }
+    // the owner's copy of the parameters is the master (every replica holds the same values)
+    float4 p4 = reinterpret_cast<const float4*>(pb.param[0])[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    float pv[4] = {p4.x, p4.y, p4.z, p4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = gv[j] * c.grad_scale;
+      pv[j] = pv[j] * (1.0f - c.lr * c.weight_decay);
+      mv[j] = mv[j] + (g - mv[j]) * (1.0f - c.beta1);
+      vv[j] = vv[j] * c.beta2 + g * g * (1.0f - c.beta2);
+      pv[j] = pv[j] - step_size * (mv[j] / (sqrtf(vv[j]) * c.inv_sqrt_bias_correction2 + c.eps));
+    }
+    reinterpret_cast<float4*>(m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    const float4 pn = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(pv[0], pv[1]), b1 = __floats2bfloat162_rn(pv[2], pv[3]);
+    uint2 packed;
+    packed.x = *reinterpret_cast<uint32_t*>(&b0);
+    packed.y = *reinterpret_cast<uint32_t*>(&b1);
+#pragma unroll
+    for (int w = 0; w < kMaxPeers; ++w)
+      if (w < world) {
+        reinterpret_cast<float4*>(pb.param[w])[i] = pn;
+        if (pb.param_bf16[w] != nullptr) reinterpret_cast<uint2*>(pb.param_bf16[w])[i] = packed;
+      }
+  }
+}
+
 }  // namespace s3od

@@ -268,3 +268,157 @@ class FusedAdamW:
                     self.param[lo:hi].data_ptr(), flat_grad[lo:hi].data_ptr(), self.exp_avg[lo:hi].data_ptr(),
                     self.exp_avg_sq[lo:hi].data_ptr(), hi - lo, self.steps, self.lrs[group] * lr_factor, self.betas[0], self.betas[1],
                     self.eps, self.weight_decay, grad_scale, bf, st), "s3od_adamw_step")
+
+
+# -------------------------------------------------------------------- fused exchange + optimiser step over peer memory
+class _RawCuda:
+    """__cuda_array_interface__ holder: lets torch view a device allocation made by the library (no copy, no ownership)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerBuffer:
+    """A flat device buffer that other processes of the box can map (CUDA IPC over NVLink): `s3od_peer_alloc` + a torch view."""
+
+    def __init__(self, numel: int, dtype: torch.dtype, device: torch.device):
+        self.lib = _lib()
+        self.device = torch.device(device)
+        self.nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        p = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.s3od_peer_alloc(ctypes.byref(p), self.nbytes), "s3od_peer_alloc")
+        self.ptr = p.value
+        self._holder = _RawCuda(self.ptr, self.nbytes)
+        self.tensor = torch.as_tensor(self._holder, device=self.device).view(dtype)
+
+    def handle(self) -> bytes:
+        buf = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.s3od_peer_export(ctypes.c_void_p(self.ptr), buf), "s3od_peer_export")
+        return bytes(buf)
+
+    def free(self):
+        if self.ptr:
+            self.tensor = None
+            with torch.cuda.device(self.device):
+                self.lib.s3od_peer_free(ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+def _bind_peer(lib):
+    if not getattr(lib, "_peer_bound", False):
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        lib.s3od_peer_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+        lib.s3od_peer_free.argtypes = [vp]
+        lib.s3od_peer_export.argtypes = [vp, ctypes.POINTER(ctypes.c_ubyte)]
+        lib.s3od_peer_open.argtypes = [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(vp)]
+        lib.s3od_peer_close.argtypes = [vp]
+        lib.s3od_ddp_fused_adamw_step.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, vp, vp, ctypes.c_size_t,
+                                                  ctypes.c_size_t, ci, cf, cf, cf, cf, cf, vp]
+        lib._peer_bound = True
+    return lib
+
+
+class FusedDataParallelAdamW:
+    """DistributedDataParallel's gradient all-reduce + AdamW.step as ONE kernel per rank over peer-mapped buffers
+    (`s3od_ddp_fused_adamw_step`): every rank reduces, updates and re-broadcasts its own 1/world slice of the flat buffers.
+
+    `grad` / `param` / `param_bf16` are this rank's flat buffers (torch views of peer-exportable allocations): the backward pass
+    writes `grad`, the forward pass reads `param_bf16` (GEMM operands) and `param` (fp32 vectors).  `step()` is bracketed by two
+    stream-ordered barriers of the process group (one-element all-reduces: no kernel ever waits on another GPU).
+
+    `emulate_world=N` builds N virtual ranks on ONE device (N sets of buffers, N sequential launches) - the same kernel and
+    slice arithmetic, used to check the path where fewer GPUs than ranks are available."""
+
+    def __init__(self, layout: ParameterLayout, device, lr: float = 1e-5, head_lr_scale: float = 10.0, weight_decay: float = 0.05,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, group=None, emulate_world: int = 0):
+        self.lib = _bind_peer(_lib())
+        self.layout = layout
+        self.device = torch.device(device)
+        self.group = group
+        self.lrs = {0: lr, 1: lr * head_lr_scale}
+        self.weight_decay, self.betas, self.eps = weight_decay, betas, eps
+        self.steps = 0
+        self.emulated = emulate_world > 0
+        n = layout.total
+        if self.emulated:
+            self.world, self.rank = emulate_world, 0
+            self._bufs = [(PeerBuffer(n, torch.float32, self.device), PeerBuffer(n, torch.float32, self.device),
+                           PeerBuffer(n, torch.bfloat16, self.device)) for _ in range(self.world)]
+            self.exp_avg = [torch.zeros(n, device=self.device) for _ in range(self.world)]
+            self.exp_avg_sq = [torch.zeros(n, device=self.device) for _ in range(self.world)]
+            ptrs = [[b[j].ptr for b in self._bufs] for j in range(3)]
+            self._opened = []
+        else:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+            own = (PeerBuffer(n, torch.float32, self.device), PeerBuffer(n, torch.float32, self.device),
+                   PeerBuffer(n, torch.bfloat16, self.device))
+            self._bufs = [own]
+            self.exp_avg = [torch.zeros(n, device=self.device)]
+            self.exp_avg_sq = [torch.zeros(n, device=self.device)]
+            ptrs = [[0] * self.world for _ in range(3)]
+            self._opened = []
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, tuple(b.handle() for b in own), group=group)
+                for w in range(self.world):
+                    for j in range(3):
+                        if w == self.rank:
+                            ptrs[j][w] = own[j].ptr
+                        else:
+                            p = ctypes.c_void_p()
+                            hb = (ctypes.c_ubyte * 64).from_buffer_copy(handles[w][j])
+                            with torch.cuda.device(self.device):
+                                _check(self.lib, self.lib.s3od_peer_open(hb, ctypes.byref(p)), "s3od_peer_open")
+                            ptrs[j][w] = p.value
+                            self._opened.append(p.value)
+            else:
+                ptrs = [[own[j].ptr] for j in range(3)]
+        self._ptr_arrays = [(ctypes.c_void_p * self.world)(*col) for col in ptrs]
+        self._token = torch.zeros(1, device=self.device)
+
+    # this rank's buffers (virtual rank r in emulation)
+    def grad(self, r: int = 0) -> torch.Tensor:
+        return self._bufs[r][0].tensor
+
+    def param(self, r: int = 0) -> torch.Tensor:
+        return self._bufs[r][1].tensor
+
+    def param_bf16(self, r: int = 0) -> torch.Tensor:
+        return self._bufs[r][2].tensor
+
+    def _barrier(self):
+        if not self.emulated and self.world > 1:
+            dist.all_reduce(self._token, group=self.group)        # stream-ordered: enqueued behind everything on this stream
+
+    def step(self, lr_factor: float = 1.0):
+        self.steps += 1
+        self._barrier()                                           # every rank's gradients are complete
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            ranks = range(self.world) if self.emulated else [self.rank]
+            for r in ranks:
+                m, v = (self.exp_avg[r], self.exp_avg_sq[r]) if self.emulated else (self.exp_avg[0], self.exp_avg_sq[0])
+                for group, (lo, hi) in self.layout.group_ranges.items():
+                    if hi <= lo:
+                        continue
+                    _check(self.lib, self.lib.s3od_ddp_fused_adamw_step(
+                        self._ptr_arrays[0], self._ptr_arrays[1], self._ptr_arrays[2], self.world, r, m.data_ptr(), v.data_ptr(), lo, hi,
+                        self.steps, self.lrs[group] * lr_factor, self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
+                        "s3od_ddp_fused_adamw_step")
+        self._barrier()                                           # every rank's parameters are visible everywhere
+
+    def link_bytes_per_step(self) -> int:
+        """Bytes this GPU reads from + writes to its peers per step: (world-1)/world x (4 B gradient in, 4 + 2 B parameter out)."""
+        return int(self.layout.total * (self.world - 1) / self.world * (4 + 6))
+
+    def close(self):
+        for p in self._opened:
+            self.lib.s3od_peer_close(ctypes.c_void_p(p))
+        self._opened = []
+        for bufs in self._bufs:
+            for b in bufs:
+                b.free()
+        self._bufs = []

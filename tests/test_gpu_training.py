@@ -121,3 +121,37 @@ def test_loss_rejects_bad_arguments(loss_module):
     with pytest.raises(ValueError):                                 # two masks: neither branch of the reference
         loss_module.forward_backward({"pred_masks": z[:, :2].contiguous(), "pred_iou": torch.zeros(2, 2, device="cuda")},
                                      {"masks": torch.zeros(2, 16, 16, device="cuda")}, 0)
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_fused_exchange_and_adamw_over_emulated_ranks(world):
+    """`s3od_ddp_fused_adamw_step` with `world` virtual ranks on one GPU (the kernel every rank runs over peer-mapped buffers):
+    after a step every replica holds the SAME bits, equal to torch.optim.AdamW on the rank-averaged gradient."""
+    from s3od_b200.training import FusedDataParallelAdamW, ParameterLayout
+    lay = ParameterLayout(VITB)
+    opt = FusedDataParallelAdamW(lay, "cuda:0", lr=1e-5, emulate_world=world)
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(17 + world)
+        p0 = torch.randn(lay.total, device="cuda", generator=gen) * 0.05
+        for r in range(world):
+            opt.param(r).copy_(p0)
+        (h0, h1), (e0, e1) = lay.group_ranges[1], lay.group_ranges[0]
+        rp_head, rp_enc = torch.nn.Parameter(p0[h0:h1].clone()), torch.nn.Parameter(p0[e0:e1].clone())
+        topt = torch.optim.AdamW([{"params": [rp_enc], "lr": 1e-5}, {"params": [rp_head], "lr": 1e-4}], weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8)
+        for s in range(2):
+            mean = torch.zeros(lay.total, device="cuda")
+            for r in range(world):                                   # summed in rank order, like the kernel
+                opt.grad(r).copy_(torch.randn(lay.total, device="cuda", generator=gen))
+                mean += opt.grad(r)
+            mean /= world
+            rp_head.grad, rp_enc.grad = mean[h0:h1].clone(), mean[e0:e1].clone()
+            topt.step()
+            opt.step()
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(opt.param(r), opt.param(0)), f"replica {r} differs"
+            assert torch.equal(opt.param_bf16(r).float(), opt.param(0).bfloat16().float())
+        assert float((opt.param(0)[h0:h1] - rp_head.detach()).abs().max()) <= 3e-7
+        assert float((opt.param(0)[e0:e1] - rp_enc.detach()).abs().max()) <= 3e-7
+    finally:
+        opt.close()
