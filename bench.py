@@ -313,6 +313,82 @@ def extra_leg(model_name, S, src, B, micro_batch, local_rank, rank, world, dev, 
     return ent
 
 
+def training_slice_leg(rank, world, dev):
+    """BASELINE.json configs[3] - the parts of the training step that exist (DESIGN.md section 6 says what does not): the loss
+    forward + backward kernels at config/dataset/synth.yaml's shape (batch 4 per GPU, 1024^2, 3 masks), and the data-parallel
+    exchange step over the 107.8 M gradients (431 MB fp32): (A) bucketed NCCL all-reduce + fused AdamW, (B) ONE fused kernel per
+    rank over CUDA-IPC peer memory (reduce its slice over NVLink, AdamW, broadcast fp32 + bf16 parameters).  At N > 1 this is the
+    one place the repository moves data between GPUs."""
+    from s3od_b200.training import FusedAdamW, FusedDataParallelAdamW, GradientAllReduce, LossModule, ParameterLayout
+    ent = {"what": "training-step slice: loss fwd+bwd, gradient exchange + AdamW (no network backward yet)", "n_gpus": world}
+    try:
+        lm = LossModule()
+        B, S = 4, 1024
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        z = torch.randn(B, 3, S, S, device=dev, generator=g) * 3
+        q = torch.randn(B, 3, device=dev, generator=g)
+        t = (torch.rand(B, S, S, device=dev, generator=g) > 0.5).float()
+        reps = 8                                            # back-to-back calls: the GPU queue hides the host-side launch cost
+        for _ in range(3):
+            lm.forward_backward({"pred_masks": z, "pred_iou": q}, {"masks": t}, 0)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            loss, _, _, _ = lm.forward_backward({"pred_masks": z, "pred_iou": q}, {"masks": t}, 0)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        nbytes = B * S * S * 4 * (4 + 4 + 3)               # pass 1 reads z (3 planes) + t; pass 3 reads them again and writes dz (3 planes)
+        ent["loss_fwd_bwd"] = {"batch": B, "image_size": S, "ms": round(ms, 4), "hbm_gbs": round(nbytes / ms / 1e6, 1),
+                               "hbm_frac": round(nbytes / ms / 1e6 / load_peaks()["hbm_gbs"], 3), "loss": round(float(loss), 5)}
+        lay = ParameterLayout(VITB)
+        gen = torch.Generator(device=dev).manual_seed(1)
+        p0 = torch.randn(lay.total, device=dev, generator=gen) * 0.05
+        grads = torch.randn(lay.total, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank))
+        pa, ga = p0.clone(), torch.empty_like(p0)
+        opt_a = FusedAdamW(lay, pa, lr=1e-5, bf16_copy=True)
+        red = GradientAllReduce(lay, ga)
+
+        def timed(fn, prep, n=5):
+            best = None
+            for _ in range(n):
+                prep()
+                sharder.barrier()
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize(dev)
+                tm = sharder.max_over_ranks(a.elapsed_time(b), device=dev)
+                best = tm if best is None else min(best, tm)
+            return best
+
+        def step_a():
+            for sgm in lay.segments:
+                red.mark_ready(sgm.name)
+            red.finish()
+            opt_a.step(ga, grad_scale=1.0 / world)
+
+        def prep_a():
+            ga.copy_(grads)
+            red.reset()
+        ta = timed(step_a, prep_a)
+        opt_b = FusedDataParallelAdamW(lay, dev, lr=1e-5)
+        opt_b.param().copy_(p0)
+        tb = timed(opt_b.step, lambda: opt_b.grad().copy_(grads))
+        ent["exchange_and_adamw"] = {
+            "params_with_grad": lay.numel_with_grad(), "grad_bytes": lay.total * 4, "buckets": lay.num_buckets,
+            "nccl_allreduce_plus_adamw_ms": round(ta, 3), "fused_p2p_kernel_ms": round(tb, 3), "speedup": round(ta / tb, 2),
+            "link_gbs_out_per_gpu": round(lay.total * (world - 1) / world * 6 / tb / 1e6, 1) if world > 1 else None,
+            "adamw_hbm_gbs_n1": round(lay.total * 30 / ta / 1e6, 1) if world == 1 else None}
+        opt_b.close()
+    except Exception as e:  # noqa: BLE001 - an extra leg must not take the headline number down with it
+        ent["error"] = repr(e)[:300]
+    return ent
+
+
 def run_b200(args, rank, local_rank, world):
     from s3od_b200 import BackgroundRemoval
     dev = torch.device("cuda", local_rank)
@@ -354,6 +430,7 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.empty_cache()
     if args.extras and args.model == "dinob" and S == 1024 and src == 1024:
         extra["cfg5_dinol"] = extra_leg("dinol", S, 1024, B, args.micro_batch, local_rank, rank, world, dev, 3, 2)
+        extra["cfg4_training_slice"] = training_slice_leg(rank, world, dev)
 
     if rank != 0:
         return None

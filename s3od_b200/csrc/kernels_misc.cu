@@ -11,18 +11,36 @@
 
 namespace s3od {
 
+// S3OD_ATTN_ONE_STREAM=1: one query tile per CTA (attention.cuh); 0 (default): two query-tile streams per CTA sharing one K / V
+// ring.  Measured in the full step at micro-batch 32 (tools/build_variants.sh, round 2): the one-stream form fetches every K / V
+// tile twice as often and runs 1.22 instead of 0.94 ms per image once the 384 (image, head) pairs no longer fit the L2.
+#ifndef S3OD_ATTN_ONE_STREAM
+#define S3OD_ATTN_ONE_STREAM 0
+#endif
+
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   AttnParams q = p;
   q.trace = nullptr;            // per-step clock64() stamps exist only in the tools/lab build (S3OD_ATTN_TRACE_BUILD)
   q.trace_bh = 0;
   q.bh_total = bh;
-  attention_kernel<<<((q_tiles + 1) / 2) * bh, kAttnThreads, kAttnSmemBytes, stream>>>(q);   // two query tiles per CTA, 1-D grid
+  static bool configured = false;
+#if S3OD_ATTN_ONE_STREAM
+  auto kern = attention_kernel_t<1, kAttnStages1>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes1);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<q_tiles * bh, kAttnThreads1, kAttnSmemBytes1, stream>>>(q);
+#else
+  auto kern = attention_kernel_t<2, kAttnStages>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<((q_tiles + 1) / 2) * bh, kAttnThreads, kAttnSmemBytes, stream>>>(q);   // two query tiles per CTA, 1-D grid
+#endif
   return cudaGetLastError();
 }
 

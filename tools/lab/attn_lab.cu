@@ -32,9 +32,22 @@ int main(int argc, char** argv) {
   p.bh_total = (int)BH; p.out = o; p.ntok = ntok; p.heads = H; p.kv_tiles = (ntok + kAttnKvTile - 1) / kAttnKvTile;
   long long* trace; cudaMalloc(&trace, 64 * 8 * 8); cudaMemset(trace, 0, 64 * 8 * 8);
   p.trace = trace; p.trace_bh = 40;
-  cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+#ifndef LAB_STREAMS
+#define LAB_STREAMS 2
+#endif
+#if LAB_STREAMS == 1
+  auto kern = attention_kernel_t<1, kAttnStages1>;
+  const int smem = kAttnSmemBytes1, threads = kAttnThreads1, grid = ((ntok + 127) / 128) * (int)BH;
+#else
+  auto kern = attention_kernel_t<2, kAttnStages>;
+  const int smem = kAttnSmemBytes, threads = kAttnThreads, grid = (((ntok + 127) / 128 + 1) / 2) * (int)BH;
+#endif
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+  printf("streams %d, %d threads, %d B smem, %d CTAs/SM, grid %d\n", LAB_STREAMS, threads, smem, occ, grid);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  auto run = [&] { attention_kernel<<<(((ntok + 127) / 128 + 1) / 2) * BH, kAttnThreads, kAttnSmemBytes>>>(p); };
+  auto run = [&] { kern<<<grid, threads, smem>>>(p); };
   for (int i = 0; i < 5; ++i) run();
   cudaEventRecord(e0);
   const int it = 20;
