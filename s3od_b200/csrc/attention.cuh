@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(kStreams == 2 ? kAttnThreads : kAttnThreads1, 
     attention_kernel_t(const __grid_constant__ AttnParams p) {
   constexpr int kAttnStages = kStages;               // shadows the namespace constant: ring depth of THIS instantiation
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();                        // the next kernel may start its prologue while this one runs
   // align by offsetting the shared array itself (a uintptr_t round trip would turn every access into a generic one)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                          // 2 query tiles
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(kStreams == 2 ? kAttnThreads : kAttnThreads1, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                     // the previous kernel's outputs are complete and visible from here on
 
   if (warp == kWarpTma) {
     if (lane == 0) {

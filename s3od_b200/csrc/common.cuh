@@ -23,6 +23,14 @@ S3OD_DEVICE bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the launch plan is launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch.h::launch_pdl): it
+// lets the NEXT kernel of the stream become resident as soon as SM resources free up, and run its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) under this kernel's tail.  pdl_wait() blocks until the PREVIOUS grid has completed and its
+// memory is visible: no global memory written by a predecessor may be touched (read OR written) before it.
+S3OD_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+S3OD_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 S3OD_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant
   using Cfg = RowConvCfg<NOUT>;
   constexpr int NB = Cfg::kAccBlocks;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();                        // the next kernel may start its prologue while this one runs
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;                                   // [kx][ky = 2, 1, 0][NOUT rows x 128 B]
   uint8_t* sRow = smem + Cfg::kWBytes;                  // ring of input rows
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(192, 1) conv_rows_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                     // the previous kernel's outputs are complete and visible from here on
 
   // strip -> (image, x0, y0, y1)
   auto strip_geom = [&](int s, int& b, int& x0, int& y0, int& y1) {
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(192, 1) convt_rows_kernel(const __grid_constan
   using Cfg = ConvTRowCfg;
   constexpr int NB = 4;                                   // pair blocks in the TMEM ring (128 columns each)
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();                        // the next kernel may start its prologue while this one runs
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;                                     // [t][kb][kh*64 + co rows x 128 B]
   uint8_t* sRow = smem + Cfg::kWBytes;                    // ring of input rows: [slot][kb][130 px x 128 B]
@@ -381,6 +384,7 @@ __global__ void __launch_bounds__(192, 1) convt_rows_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                     // the previous kernel's outputs are complete and visible from here on
 
   // strip -> image, first input column, pair blocks [q0, q1): pair block q = output rows (2q-1, 2q), q in [0, H]
   auto strip_geom = [&](int s, int& b, int& x0, int& q0, int& q1) {

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(128 + 32 * 8, 1) conv_swap128_kernel(const __g
   using Cfg = ConvSwapCfg;
   constexpr int EPI_WARPS = 8;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();                        // the next kernel may start its prologue while this one runs
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;
   uint8_t* sX = smem + Cfg::kStages * Cfg::kWBytes;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(128 + 32 * 8, 1) conv_swap128_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                     // the previous kernel's outputs are complete and visible from here on
 
   const int items = p.m_tiles >> 1;                       // pairs of adjacent M tiles
   const int per_img = p.geom.tiles_h * p.geom.tiles_w;

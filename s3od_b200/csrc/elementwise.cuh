@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(256) pack_input_kernel(const float* __restrict
 
 // cls + register tokens into rows 0..4 of every image (HF:88-90)
 __global__ void fill_prefix_kernel(float* __restrict__ x, const float* __restrict__ prefix, int ntok, int D, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = 5 * D;
   if (i >= B * per) return;
@@ -166,6 +168,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ tap, int M,
                                                         int ntok, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int V = D / 128;      // float4 per lane
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -242,6 +246,8 @@ constexpr int kUpsRows = S3OD_UPS_ROWS;
 template <int C>
 __global__ void __launch_bounds__(256, S3OD_UPS_MINBLOCKS) upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                          float* __restrict__ pool, int h, int w) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int CG = C / 8;                 // channel groups (threads along channels)
   constexpr int PP = 256 / CG;              // input columns per block
   const int b = blockIdx.y;
@@ -350,6 +356,8 @@ __global__ void __launch_bounds__(256) iou_head_kernel(const float* __restrict__
                                                        const float* __restrict__ w1, const float* __restrict__ b1,
                                                        const float* __restrict__ w2, const float* __restrict__ b2,
                                                        float* __restrict__ iou_logits, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float mean[256];
   __shared__ float hid[64];
   const int b = blockIdx.x;

@@ -82,6 +82,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(Cfg::kBBytes % 1024 == 0, "B tile must keep 1024B alignment for SWIZZLE_128B");
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();                        // the next kernel may start its prologue while this one runs
   // align by offsetting the shared array itself (a uintptr_t round trip would turn every access into a generic one)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
@@ -120,6 +121,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams<Epi> p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                     // the previous kernel's outputs are complete and visible from here on
 
   const int total_tiles = p.m_tiles * p.n_tiles;
 

@@ -98,6 +98,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EPI_WARPS
 gemm_tc2_kernel(const __grid_constant__ GemmParams<Epi> p) {
   using Cfg = Gemm2Cfg<BN, EPI_WARPS>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();                        // the next kernel may start its prologue while this one runs
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
@@ -136,6 +137,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams<Epi> p) {
   cluster_sync_all();                             // barriers of both CTAs are initialised before any remote arrival
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                     // the previous kernel's outputs are complete and visible from here on
 
   const int m_pairs = (p.m_tiles + 1) / 2;
   const int total_items = m_pairs * p.n_tiles;

@@ -21,8 +21,7 @@ cudaError_t launch_conv_swap128(const ConvSwapParams& p, int num_sms, cudaStream
   const int items = p.m_tiles / 2;
   if (items <= 0) return cudaSuccess;
   const int grid = items < num_sms ? items : num_sms;
-  conv_swap128_kernel<0><<<grid, 128 + 32 * 8, ConvSwapCfg::kSmemBytes, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(conv_swap128_kernel<0>, dim3(grid), dim3(128 + 32 * 8), ConvSwapCfg::kSmemBytes, stream, p);
 }
 
 cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t stream) {
@@ -34,7 +33,6 @@ cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t
   }
   if (p.num_strips <= 0) return cudaSuccess;
   const int grid = p.num_strips < num_sms ? p.num_strips : num_sms;
-  convt_rows_kernel<0><<<grid, 192, ConvTRowCfg::kSmemBytes, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(convt_rows_kernel<0>, dim3(grid), dim3(192), ConvTRowCfg::kSmemBytes, stream, p);
 }
 }  // namespace s3od

@@ -21,8 +21,7 @@ cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stre
       }
       const int items = ((p.m_tiles + 1) / 2) * p.n_tiles;            // (M-tile pair, N tile) work items
       const int pairs = items < num_sms / 2 ? items : num_sms / 2;
-      kern2<<<2 * pairs, 128 + 32 * EPI_WARPS, Cfg2::kSmemBytes, stream>>>(p);
-      return cudaGetLastError();
+      return launch_pdl(kern2, dim3(2 * pairs), dim3(128 + 32 * EPI_WARPS), Cfg2::kSmemBytes, stream, p);
     }
   }
   using Cfg = GemmCfg<BN, EPI_WARPS>;
@@ -34,8 +33,7 @@ cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stre
     configured = true;
   }
   const int grid = total < num_sms ? total : num_sms;
-  kern<<<grid, 128 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(128 + 32 * EPI_WARPS), Cfg::kSmemBytes, stream, p);
 }
 
 template <int NOUT, class Epi>
@@ -50,8 +48,7 @@ cudaError_t launch_conv_rows(const RowConvParams<Epi>& p, int num_sms, cudaStrea
   }
   if (p.num_strips <= 0) return cudaSuccess;
   const int grid = p.num_strips < num_sms ? p.num_strips : num_sms;
-  kern<<<grid, 192, Cfg::kSmemBytes, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(192), Cfg::kSmemBytes, stream, p);
 }
 
 #define S3OD_INSTANTIATE_CONV_ROWS(NOUT, EPI) \

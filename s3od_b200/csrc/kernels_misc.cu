@@ -31,7 +31,7 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<q_tiles * bh, kAttnThreads1, kAttnSmemBytes1, stream>>>(q);
+  return launch_pdl(kern, dim3(q_tiles * bh), dim3(kAttnThreads1), kAttnSmemBytes1, stream, q);
 #else
   auto kern = attention_kernel_t<2, kAttnStages>;
   if (!configured) {
@@ -39,9 +39,8 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<((q_tiles + 1) / 2) * bh, kAttnThreads, kAttnSmemBytes, stream>>>(q);   // two query tiles per CTA, 1-D grid
+  return launch_pdl(kern, dim3(((q_tiles + 1) / 2) * bh), dim3(kAttnThreads), kAttnSmemBytes, stream, q);   // two query tiles per CTA, 1-D grid
 #endif
-  return cudaGetLastError();
 }
 
 cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,
@@ -49,12 +48,10 @@ cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, 
   const int rows_per_block = 8;
   const int grid = (M + rows_per_block - 1) / rows_per_block;
   if (D == 768)
-    layernorm_kernel<768><<<grid, 256, 0, stream>>>(x, dx, w, b, y, tap, M, ntok, eps);
+    return launch_pdl(layernorm_kernel<768>, dim3(grid), dim3(256), 0, stream, x, dx, w, b, y, tap, M, ntok, eps);
   else if (D == 1024)
-    layernorm_kernel<1024><<<grid, 256, 0, stream>>>(x, dx, w, b, y, tap, M, ntok, eps);
-  else
-    return cudaErrorInvalidValue;
-  return cudaGetLastError();
+    return launch_pdl(layernorm_kernel<1024>, dim3(grid), dim3(256), 0, stream, x, dx, w, b, y, tap, M, ntok, eps);
+  return cudaErrorInvalidValue;
 }
 
 template <int MODE>
@@ -87,8 +84,7 @@ cudaError_t launch_pack_input(const float* x, __nv_bfloat16* patches, int S, int
 
 cudaError_t launch_fill_prefix(float* x, const float* prefix, int ntok, int D, int B, cudaStream_t stream) {
   const int n = B * 5 * D;
-  fill_prefix_kernel<<<(n + 255) / 256, 256, 0, stream>>>(x, prefix, ntok, D, B);
-  return cudaGetLastError();
+  return launch_pdl(fill_prefix_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, x, prefix, ntok, D, B);
 }
 
 cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float* pool, int pool_blocks, int B, int h, int w,
@@ -103,14 +99,12 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, float
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
   }
-  upsample2x_kernel<256><<<dim3(blocks, B), 256, 0, stream>>>(in, out, pool, h, w);
-  return cudaGetLastError();
+  return launch_pdl(upsample2x_kernel<256>, dim3(blocks, B), dim3(256), 0, stream, in, out, pool, h, w);
 }
 
 cudaError_t launch_iou_head(const float* pool, int nblocks, float inv_npix, const float* w1, const float* b1, const float* w2,
                             const float* b2, float* iou_logits, int K, int B, cudaStream_t stream) {
-  iou_head_kernel<<<B, 256, 0, stream>>>(pool, nblocks, inv_npix, w1, b1, w2, b2, iou_logits, K);
-  return cudaGetLastError();
+  return launch_pdl(iou_head_kernel, dim3(B), dim3(256), 0, stream, pool, nblocks, inv_npix, w1, b1, w2, b2, iou_logits, K);
 }
 
 cudaError_t launch_postprocess(const PostDesc* descs, const float* mask_logits, const float* iou_logits, float* ious,

@@ -5,6 +5,8 @@
 #include "conv_swap.cuh"
 #include "types.h"
 
+#include <utility>
+
 namespace s3od {
 
 // BN = 256 / 128 tiles run on the CTA-pair kernel (gemm_tc2.cuh); -DS3OD_PAIR=0 builds the library on the one-CTA kernel
@@ -14,6 +16,27 @@ namespace s3od {
 #define S3OD_PAIR 1
 #endif
 constexpr bool use_pair_kernel() { return S3OD_PAIR != 0; }
+// Launch with programmatic dependent launch allowed (see common.cuh::pdl_wait): the kernel may become resident while its
+// predecessor in the stream is still draining.  ONLY for kernels that call pdl_wait() before their first global access.
+// -DS3OD_PDL=0 builds the library with plain stream-ordered launches (A/B measurements).
+#ifndef S3OD_PDL
+#define S3OD_PDL 1
+#endif
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = S3OD_PDL ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int BN>
 inline int b_box_rows() { return ((BN == 256 || BN == 128) && use_pair_kernel()) ? BN / 2 : BN; }
 
