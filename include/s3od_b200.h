@@ -177,6 +177,46 @@ int s3od_ddp_fused_adamw_step(const float* const* d_grads, float* const* d_param
                               float* d_exp_avg, float* d_exp_avg_sq, size_t begin, size_t end, int step, float lr, float beta1, float beta2,
                               float eps, float weight_decay, s3od_stream stream);
 
+/* ---- encoder-block training step (DINOv3ViTLayer.forward, HF modeling_dinov3_vit.py:424-450, and its autograd): the
+ * contractions run on the tcgen05 GEMM (s3od_op_gemm_f32: C fp32 [M,N] = A bf16 [M,K] * B bf16 [N,K]^T); these are the kernels
+ * between them.  s3od_b200/training.py::EncoderBlockStep orchestrates them; every buffer is a dense device array.
+ *   transpose            out bf16 [batch][cols][rows_padded] = scale * in[batch][rows][cols]^T (zero padded) - the K-major operand
+ *                        layout of dgrad (W^T) and wgrad (dY^T, X^T, tokens as the contraction dimension)
+ *   scale_cast           out bf16 = in * colscale[c]            (LayerScale backward:  d branch = dy * lambda)
+ *   residual_scale_add   out = x + lambda[c] * y                (HF:440-441, 447-448)
+ *   colsum               out[c] (+)= colscale[c] * sum_r a[r][c] * (b ? b[r][c] : 1)   (bias and LayerScale gradients)
+ *   ln_backward          LayerNorm backward (dx, dgamma, dbeta), dx += dres           (HF:433, 445)
+ *   gelu_forward/backward  exact erf GELU (HF:386)
+ *   qkv_split_rope       qkv fp32 [B*N, 3D] -> q (RoPE, pre-scaled), k (RoPE), v bf16 [B, H, Npad, 64]   (HF:305-313, 238-268)
+ *   qkv_merge_rope_backward  dq^T, dk^T, dv^T fp32 [B, H, 64, Npad] -> dqkv [B*N, 3D] through the transpose of RoPE
+ *   split_heads          [B*N, H*64] -> bf16 [B, H, Npad, 64]
+ *   rowdot64             out[row] = sum_d a[row][d] b[row][d]   (D = rowsum(dO * O) of the softmax backward)
+ *   softmax2_rows        P bf16 [Npad, Npad] = softmax over the first N columns of base-2 scores, zero elsewhere
+ *   softmax_backward     dS bf16 = P * (dP - D[row]) */
+int s3od_train_transpose(const void* d_in, int in_is_f32, void* d_out, int batch, int rows, int cols, int rows_padded, long long in_batch_stride,
+                         int in_row_stride, float scale, s3od_stream stream);
+int s3od_train_scale_cast(const float* d_in, const float* d_colscale, void* d_out, long long n, int cols, s3od_stream stream);
+int s3od_train_residual_scale_add(const float* d_x, const float* d_y, const float* d_lambda, float* d_out, long long n, int cols, s3od_stream stream);
+int s3od_train_add_bias(float* d_a, const float* d_bias, long long n, int cols, s3od_stream stream);
+size_t s3od_train_colsum_workspace_bytes(int rows, int cols);
+int s3od_train_colsum(const float* d_a, const float* d_b, int rows, int cols, const float* d_colscale, float* d_out, int accumulate,
+                      void* d_workspace, s3od_stream stream);
+size_t s3od_train_ln_backward_workspace_bytes(int rows, int dim);
+int s3od_train_ln_backward(const float* d_x, const float* d_gamma, const float* d_dy, const float* d_dres, float* d_dx, int rows, int dim, float eps,
+                           float* d_dgamma, float* d_dbeta, void* d_workspace, s3od_stream stream);
+int s3od_train_gelu_forward(const float* d_h, void* d_out, long long n, s3od_stream stream);
+int s3od_train_gelu_backward(const float* d_h, const float* d_dh, void* d_out, float* d_out_f32, long long n, s3od_stream stream);
+int s3od_train_qkv_split_rope(const float* d_qkv, const float* d_cos, const float* d_sin, void* d_q, void* d_k, void* d_v, int batch, int ntok,
+                              int ntok_padded, int heads, int n_prefix, float qscale, s3od_stream stream);
+int s3od_train_qkv_merge_rope_backward(const float* d_dqT, const float* d_dkT, const float* d_dvT, const float* d_cos, const float* d_sin, void* d_dqkv,
+                                       float* d_dqkv_f32, int batch, int ntok, int ntok_padded, int heads, int n_prefix, float qgrad_scale,
+                                       float kgrad_scale, s3od_stream stream);
+int s3od_train_split_heads(const void* d_in, int in_is_f32, void* d_out, int batch, int ntok, int ntok_padded, int heads, s3od_stream stream);
+int s3od_train_rowdot64(const void* d_a, const void* d_b, float* d_out, long long rows, s3od_stream stream);
+int s3od_train_softmax2_rows(const float* d_scores, void* d_probs, int ntok, int ntok_padded, s3od_stream stream);
+int s3od_train_softmax_backward(const void* d_probs, const float* d_dprobs, const float* d_rowdot, void* d_dscores, int ntok, int ntok_padded,
+                                s3od_stream stream);
+
 /* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
 /* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */
 int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream);

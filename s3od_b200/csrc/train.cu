@@ -10,6 +10,7 @@
 
 #include "../../include/s3od_b200.h"
 #include "train.cuh"
+#include "train_block.cuh"
 
 using namespace s3od;
 
@@ -121,6 +122,150 @@ int s3od_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float
   return S3OD_OK;
 }
 
+
+// ---- encoder-block training step: glue kernels between the tcgen05 GEMMs (train_block.cuh)
+#define S3OD_TRAIN_DONE(what)                                                                                      \
+  do {                                                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                                           \
+    if (_e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(_e));   \
+    return S3OD_OK;                                                                                                \
+  } while (0)
+
+static int grid_for(long long n) {
+  const long long want = (n + 255) / 256;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(want, 16LL * num_sms())));
+}
+
+int s3od_train_transpose(const void* d_in, int in_is_f32, void* d_out, int batch, int rows, int cols, int rows_padded, long long in_batch_stride,
+                         int in_row_stride, float scale, s3od_stream stream) {
+  if (d_in == nullptr || d_out == nullptr || batch < 1 || rows < 1 || cols < 1 || rows_padded < rows)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_transpose");
+  const dim3 grid((cols + 31) / 32, (rows_padded + 31) / 32, batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_is_f32)
+    transpose_pad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(d_in), static_cast<bf16_t*>(d_out), rows, cols, rows_padded,
+                                                      in_batch_stride, in_row_stride, scale);
+  else
+    transpose_pad_kernel<bf16_t><<<grid, 256, 0, st>>>(static_cast<const bf16_t*>(d_in), static_cast<bf16_t*>(d_out), rows, cols, rows_padded,
+                                                       in_batch_stride, in_row_stride, scale);
+  S3OD_TRAIN_DONE("transpose_pad_kernel");
+}
+
+int s3od_train_scale_cast(const float* d_in, const float* d_colscale, void* d_out, long long n, int cols, s3od_stream stream) {
+  if (d_in == nullptr || d_out == nullptr || n < 1 || cols < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_scale_cast");
+  scale_cast_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, d_colscale, static_cast<bf16_t*>(d_out), n, cols);
+  S3OD_TRAIN_DONE("scale_cast_kernel");
+}
+
+int s3od_train_residual_scale_add(const float* d_x, const float* d_y, const float* d_lambda, float* d_out, long long n, int cols, s3od_stream stream) {
+  if (d_x == nullptr || d_y == nullptr || d_lambda == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_residual_scale_add");
+  residual_scale_add_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, d_lambda, d_out, n, cols);
+  S3OD_TRAIN_DONE("residual_scale_add_kernel");
+}
+
+int s3od_train_add_bias(float* d_a, const float* d_bias, long long n, int cols, s3od_stream stream) {
+  if (d_a == nullptr || d_bias == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_add_bias");
+  add_bias_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, d_bias, n, cols);
+  S3OD_TRAIN_DONE("add_bias_kernel");
+}
+
+size_t s3od_train_colsum_workspace_bytes(int rows, int cols) { return static_cast<size_t>((rows + 63) / 64) * cols * sizeof(float); }
+
+int s3od_train_colsum(const float* d_a, const float* d_b, int rows, int cols, const float* d_colscale, float* d_out, int accumulate,
+                      void* d_workspace, s3od_stream stream) {
+  if (d_a == nullptr || d_out == nullptr || d_workspace == nullptr || rows < 1 || cols < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_colsum");
+  const int nblk = (rows + 63) / 64;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  colsum_partial_kernel<<<dim3((cols + 255) / 256, nblk), 256, 0, st>>>(d_a, d_b, rows, cols, 64, static_cast<float*>(d_workspace));
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(static_cast<const float*>(d_workspace), nblk, cols, d_colscale, d_out, accumulate);
+  S3OD_TRAIN_DONE("colsum kernels");
+}
+
+size_t s3od_train_ln_backward_workspace_bytes(int rows, int dim) { return static_cast<size_t>(2) * ((rows + 7) / 8) * dim * sizeof(float); }
+
+int s3od_train_ln_backward(const float* d_x, const float* d_gamma, const float* d_dy, const float* d_dres, float* d_dx, int rows, int dim, float eps,
+                           float* d_dgamma, float* d_dbeta, void* d_workspace, s3od_stream stream) {
+  if (d_x == nullptr || d_gamma == nullptr || d_dy == nullptr || d_dx == nullptr || d_dgamma == nullptr || d_dbeta == nullptr || d_workspace == nullptr || rows < 1)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_ln_backward");
+  const int nblk = (rows + 7) / 8;
+  float* pg = static_cast<float*>(d_workspace);
+  float* pb = pg + static_cast<size_t>(nblk) * dim;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dim == 768)
+    ln_backward_kernel<768><<<nblk, 256, 0, st>>>(d_x, d_gamma, d_dy, d_dres, d_dx, rows, eps, pg, pb);
+  else if (dim == 1024)
+    ln_backward_kernel<1024><<<nblk, 256, 0, st>>>(d_x, d_gamma, d_dy, d_dres, d_dx, rows, eps, pg, pb);
+  else
+    return train_fail(S3OD_ERR_ARG, "s3od_train_ln_backward: hidden size must be 768 or 1024");
+  colsum_final_kernel<<<(dim + 255) / 256, 256, 0, st>>>(pg, nblk, dim, nullptr, d_dgamma, 0);
+  colsum_final_kernel<<<(dim + 255) / 256, 256, 0, st>>>(pb, nblk, dim, nullptr, d_dbeta, 0);
+  S3OD_TRAIN_DONE("ln_backward kernels");
+}
+
+int s3od_train_gelu_forward(const float* d_h, void* d_out, long long n, s3od_stream stream) {
+  if (d_h == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_gelu_forward");
+  gelu_forward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_h, static_cast<bf16_t*>(d_out), n);
+  S3OD_TRAIN_DONE("gelu_forward_kernel");
+}
+
+int s3od_train_gelu_backward(const float* d_h, const float* d_dh, void* d_out, float* d_out_f32, long long n, s3od_stream stream) {
+  if (d_h == nullptr || d_dh == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_gelu_backward");
+  gelu_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_h, d_dh, static_cast<bf16_t*>(d_out), d_out_f32, n);
+  S3OD_TRAIN_DONE("gelu_backward_kernel");
+}
+
+int s3od_train_qkv_split_rope(const float* d_qkv, const float* d_cos, const float* d_sin, void* d_q, void* d_k, void* d_v, int batch, int ntok,
+                              int ntok_padded, int heads, int n_prefix, float qscale, s3od_stream stream) {
+  if (d_qkv == nullptr || d_cos == nullptr || d_sin == nullptr || d_q == nullptr || d_k == nullptr || d_v == nullptr || ntok_padded < ntok)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_qkv_split_rope");
+  const long long n = static_cast<long long>(batch) * heads * ntok_padded * 32;
+  qkv_split_rope_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_qkv, d_cos, d_sin, static_cast<bf16_t*>(d_q), static_cast<bf16_t*>(d_k),
+                                                                                    static_cast<bf16_t*>(d_v), batch, ntok, ntok_padded, heads, n_prefix, qscale);
+  S3OD_TRAIN_DONE("qkv_split_rope_kernel");
+}
+
+int s3od_train_qkv_merge_rope_backward(const float* d_dqT, const float* d_dkT, const float* d_dvT, const float* d_cos, const float* d_sin, void* d_dqkv,
+                                       float* d_dqkv_f32, int batch, int ntok, int ntok_padded, int heads, int n_prefix, float qgrad_scale,
+                                       float kgrad_scale, s3od_stream stream) {
+  if (d_dqT == nullptr || d_dkT == nullptr || d_dvT == nullptr || d_dqkv == nullptr || d_dqkv_f32 == nullptr)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_qkv_merge_rope_backward");
+  const long long n = static_cast<long long>(batch) * heads * ntok * 32;
+  qkv_merge_rope_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dqT, d_dkT, d_dvT, d_cos, d_sin, static_cast<bf16_t*>(d_dqkv), d_dqkv_f32,
+                                                                                        batch, ntok, ntok_padded, heads, n_prefix, qgrad_scale, kgrad_scale);
+  S3OD_TRAIN_DONE("qkv_merge_rope_bwd_kernel");
+}
+
+int s3od_train_split_heads(const void* d_in, int in_is_f32, void* d_out, int batch, int ntok, int ntok_padded, int heads, s3od_stream stream) {
+  if (d_in == nullptr || d_out == nullptr || ntok_padded < ntok) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_split_heads");
+  const long long n = static_cast<long long>(batch) * heads * ntok_padded * 64;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_is_f32)
+    split_heads_kernel<float><<<grid_for(n), 256, 0, st>>>(static_cast<const float*>(d_in), static_cast<bf16_t*>(d_out), batch, ntok, ntok_padded, heads);
+  else
+    split_heads_kernel<bf16_t><<<grid_for(n), 256, 0, st>>>(static_cast<const bf16_t*>(d_in), static_cast<bf16_t*>(d_out), batch, ntok, ntok_padded, heads);
+  S3OD_TRAIN_DONE("split_heads_kernel");
+}
+
+int s3od_train_rowdot64(const void* d_a, const void* d_b, float* d_out, long long rows, s3od_stream stream) {
+  if (d_a == nullptr || d_b == nullptr || d_out == nullptr || rows < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_rowdot64");
+  rowdot64_kernel<<<static_cast<int>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(d_a), static_cast<const bf16_t*>(d_b), d_out, rows);
+  S3OD_TRAIN_DONE("rowdot64_kernel");
+}
+
+int s3od_train_softmax2_rows(const float* d_scores, void* d_probs, int ntok, int ntok_padded, s3od_stream stream) {
+  if (d_scores == nullptr || d_probs == nullptr || ntok < 1 || ntok_padded < ntok) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_softmax2_rows");
+  softmax2_rows_kernel<<<ntok_padded, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_scores, static_cast<bf16_t*>(d_probs), ntok, ntok_padded);
+  S3OD_TRAIN_DONE("softmax2_rows_kernel");
+}
+
+int s3od_train_softmax_backward(const void* d_probs, const float* d_dprobs, const float* d_rowdot, void* d_dscores, int ntok, int ntok_padded,
+                                s3od_stream stream) {
+  if (d_probs == nullptr || d_dprobs == nullptr || d_rowdot == nullptr || d_dscores == nullptr) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_softmax_backward");
+  const long long n = static_cast<long long>(ntok_padded) * ntok_padded;
+  softmax_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(d_probs), d_dprobs, d_rowdot,
+                                                                                      static_cast<bf16_t*>(d_dscores), ntok, ntok_padded);
+  S3OD_TRAIN_DONE("softmax_backward_kernel");
+}
 
 // ---- peer-mapped buffers (CUDA IPC) and the fused exchange + optimiser step over them
 int s3od_peer_alloc(void** d_ptr, size_t bytes) {

@@ -422,3 +422,240 @@ class FusedDataParallelAdamW:
             for b in bufs:
                 b.free()
         self._bufs = []
+
+
+# ------------------------------------------------------------------------------------ encoder block: forward + backward
+def _bind_block(lib):
+    if not getattr(lib, "_block_bound", False):
+        vp, ci, cf, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+        lib.s3od_train_transpose.argtypes = [vp, ci, vp, ci, ci, ci, ci, ll, ci, cf, vp]
+        lib.s3od_train_scale_cast.argtypes = [vp, vp, vp, ll, ci, vp]
+        lib.s3od_train_residual_scale_add.argtypes = [vp, vp, vp, vp, ll, ci, vp]
+        lib.s3od_train_add_bias.argtypes = [vp, vp, ll, ci, vp]
+        lib.s3od_train_colsum_workspace_bytes.argtypes = [ci, ci]
+        lib.s3od_train_colsum_workspace_bytes.restype = ctypes.c_size_t
+        lib.s3od_train_colsum.argtypes = [vp, vp, ci, ci, vp, vp, ci, vp, vp]
+        lib.s3od_train_ln_backward_workspace_bytes.argtypes = [ci, ci]
+        lib.s3od_train_ln_backward_workspace_bytes.restype = ctypes.c_size_t
+        lib.s3od_train_ln_backward.argtypes = [vp, vp, vp, vp, vp, ci, ci, cf, vp, vp, vp, vp]
+        lib.s3od_train_gelu_forward.argtypes = [vp, vp, ll, vp]
+        lib.s3od_train_gelu_backward.argtypes = [vp, vp, vp, vp, ll, vp]
+        lib.s3od_train_qkv_split_rope.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp]
+        lib.s3od_train_qkv_merge_rope_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, cf, vp]
+        lib.s3od_train_split_heads.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp]
+        lib.s3od_train_rowdot64.argtypes = [vp, vp, vp, ll, vp]
+        lib.s3od_train_softmax2_rows.argtypes = [vp, vp, ci, ci, vp]
+        lib.s3od_train_softmax_backward.argtypes = [vp, vp, vp, vp, ci, ci, vp]
+        lib._block_bound = True
+    return lib
+
+
+class EncoderBlockStep:
+    """Forward (with saved activations) and backward of ONE encoder block - DINOv3ViTLayer.forward, HF modeling_dinov3_vit.py:424-450
+    with the attention of HF:294-334 - on the CUDA library: every contraction (the four linears and their dgrad / wgrad, Q K^T,
+    dO V^T, dS K, dS^T Q, P^T dO) is a tcgen05 GEMM (`s3od_op_gemm_f32`: fp32 C = bf16 A x bf16 B^T), the forward attention is the
+    fused flash kernel (`s3od_op_attention`), everything between them is a kernel of csrc/train_block.cuh.  dgrad reads the
+    transposed weights, wgrad contracts over the tokens (dY^T and X^T, zero-padded to a multiple of 64 rows), the attention
+    backward re-materialises S and P per (image, head).  A first, correctness-first form: unfused, O(N^2) scratch per head.
+
+    Precision: bf16 operands / fp32 accumulation in every GEMM (the reference trains with float32_matmul_precision "medium",
+    train.py:74), fp32 LayerNorm / GELU / softmax / reductions; the gradients that feed a GEMM are rounded to bf16 once."""
+
+    LOG2E = 1.4426950408889634
+
+    def __init__(self, sd: Dict[str, torch.Tensor], layer_prefix: str, arch: ArchSpec, image_size: int, device="cuda:0"):
+        from .weights import rope_tables
+        self.lib = _bind_block(_lib())
+        self.arch, self.dev = arch, torch.device(device)
+        self.D, self.H, self.I = arch.hidden, arch.heads, arch.mlp
+        g = image_size // arch.patch
+        self.N = g * g + arch.n_prefix
+        self.Npad = (self.N + 127) // 128 * 128
+        f = lambda t: t.detach().to(self.dev, torch.float32).contiguous()           # noqa: E731
+        a = layer_prefix + "attention."
+        D = self.D
+        kb = sd.get(a + "k_proj.bias", torch.zeros(D))
+        self.w = {"qkv.w": f(torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0)),
+                  "qkv.b": f(torch.cat([sd[a + "q_proj.bias"], kb, sd[a + "v_proj.bias"]], 0)),
+                  "o.w": f(sd[a + "o_proj.weight"]), "o.b": f(sd[a + "o_proj.bias"]),
+                  "up.w": f(sd[layer_prefix + "mlp.up_proj.weight"]), "up.b": f(sd[layer_prefix + "mlp.up_proj.bias"]),
+                  "down.w": f(sd[layer_prefix + "mlp.down_proj.weight"]), "down.b": f(sd[layer_prefix + "mlp.down_proj.bias"]),
+                  "ln1.w": f(sd[layer_prefix + "norm1.weight"]), "ln1.b": f(sd[layer_prefix + "norm1.bias"]),
+                  "ln2.w": f(sd[layer_prefix + "norm2.weight"]), "ln2.b": f(sd[layer_prefix + "norm2.bias"]),
+                  "ls1": f(sd[layer_prefix + "layer_scale1.lambda1"]), "ls2": f(sd[layer_prefix + "layer_scale2.lambda1"])}
+        self.wb = {k: self.w[k].to(torch.bfloat16) for k in ("qkv.w", "o.w", "up.w", "down.w")}       # forward B operands [N_out, K_in]
+        self.wt = {k: self._transpose(self.wb[k], 1, self.wb[k].shape[0], self.wb[k].shape[1], self.wb[k].shape[0]) .view(self.wb[k].shape[1], self.wb[k].shape[0])
+                   for k in self.wb}                                                                  # dgrad B operands [K_in, N_out]
+        cos, sin = rope_tables(g, g, arch.head_dim, arch.rope_theta)
+        self.cos, self.sin = cos.to(self.dev).contiguous(), sin.to(self.dev).contiguous()
+        self.saved = None
+
+    # ---- thin wrappers around the C ABI -------------------------------------------------------------------------
+    def _st(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _ck(self, rc, what):
+        _check(self.lib, rc, what)
+
+    def _gemm(self, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
+        c = torch.empty(M, N, dtype=torch.float32, device=self.dev)
+        self._ck(self.lib.s3od_op_gemm_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, self._st()), "s3od_op_gemm_f32")
+        return c
+
+    def _transpose(self, t: torch.Tensor, batch: int, rows: int, cols: int, rows_padded: int, scale: float = 1.0) -> torch.Tensor:
+        """[batch][rows][cols] (dense) -> bf16 [batch][cols][rows_padded], zero padded."""
+        out = torch.empty(batch, cols, rows_padded, dtype=torch.bfloat16, device=self.dev)
+        self._ck(self.lib.s3od_train_transpose(t.data_ptr(), 1 if t.dtype == torch.float32 else 0, out.data_ptr(), batch, rows, cols, rows_padded,
+                                               rows * cols, cols, scale, self._st()), "s3od_train_transpose")
+        return out
+
+    def _layernorm(self, x: torch.Tensor, w, b) -> torch.Tensor:
+        M, D = x.shape
+        y = torch.empty(M, D, dtype=torch.bfloat16, device=self.dev)
+        self._ck(self.lib.s3od_op_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, D, self.arch.ln_eps, self._st()), "s3od_op_layernorm")
+        return y
+
+    def _add_bias(self, a, bias):
+        self._ck(self.lib.s3od_train_add_bias(a.data_ptr(), bias.data_ptr(), a.numel(), a.shape[1], self._st()), "s3od_train_add_bias")
+        return a
+
+    def _residual(self, x, y, lam):
+        out = torch.empty_like(x)
+        self._ck(self.lib.s3od_train_residual_scale_add(x.data_ptr(), y.data_ptr(), lam.data_ptr(), out.data_ptr(), x.numel(), x.shape[1], self._st()),
+                 "s3od_train_residual_scale_add")
+        return out
+
+    def _scale_cast(self, x, colscale=None):
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=self.dev)
+        self._ck(self.lib.s3od_train_scale_cast(x.data_ptr(), colscale.data_ptr() if colscale is not None else None, out.data_ptr(), x.numel(),
+                                                x.shape[-1], self._st()), "s3od_train_scale_cast")
+        return out
+
+    def _colsum(self, a, b=None, colscale=None):
+        M, C = a.shape
+        ws = torch.empty(self.lib.s3od_train_colsum_workspace_bytes(M, C), dtype=torch.uint8, device=self.dev)
+        out = torch.empty(C, dtype=torch.float32, device=self.dev)
+        self._ck(self.lib.s3od_train_colsum(a.data_ptr(), b.data_ptr() if b is not None else None, M, C,
+                                            colscale.data_ptr() if colscale is not None else None, out.data_ptr(), 0, ws.data_ptr(), self._st()),
+                 "s3od_train_colsum")
+        return out
+
+    def _ln_backward(self, x, gamma, dy, dres):
+        M, D = x.shape
+        ws = torch.empty(self.lib.s3od_train_ln_backward_workspace_bytes(M, D), dtype=torch.uint8, device=self.dev)
+        dx = torch.empty_like(x)
+        dg, db = torch.empty(D, device=self.dev), torch.empty(D, device=self.dev)
+        self._ck(self.lib.s3od_train_ln_backward(x.data_ptr(), gamma.data_ptr(), dy.data_ptr(), dres.data_ptr() if dres is not None else None,
+                                                 dx.data_ptr(), M, D, self.arch.ln_eps, dg.data_ptr(), db.data_ptr(), ws.data_ptr(), self._st()),
+                 "s3od_train_ln_backward")
+        return dx, dg, db
+
+    def _split_rope(self, qkv, B, npad):
+        q, k, v = (torch.empty(B, self.H, npad, 64, dtype=torch.bfloat16, device=self.dev) for _ in range(3))
+        self._ck(self.lib.s3od_train_qkv_split_rope(qkv.data_ptr(), self.cos.data_ptr(), self.sin.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                                    B, self.N, npad, self.H, self.arch.n_prefix, self.LOG2E / 8.0, self._st()), "s3od_train_qkv_split_rope")
+        return q, k, v
+
+    def _split_heads(self, t, B):
+        out = torch.empty(B, self.H, self.Npad, 64, dtype=torch.bfloat16, device=self.dev)
+        self._ck(self.lib.s3od_train_split_heads(t.data_ptr(), 1 if t.dtype == torch.float32 else 0, out.data_ptr(), B, self.N, self.Npad, self.H,
+                                                 self._st()), "s3od_train_split_heads")
+        return out
+
+    # ---- forward ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x fp32 (B, N, D) -> block output fp32 (B, N, D); keeps what backward needs."""
+        B, N, D = x.shape
+        assert N == self.N and D == self.D
+        w, wb, I, H = self.w, self.wb, self.I, self.H
+        M = B * N
+        x0 = x.to(self.dev, torch.float32).contiguous().view(M, D)
+        with torch.cuda.device(self.dev):
+            xn1 = self._layernorm(x0, w["ln1.w"], w["ln1.b"])
+            qkv = self._add_bias(self._gemm(xn1, wb["qkv.w"], M, 3 * D, D), w["qkv.b"])
+            qu, ku, vu = self._split_rope(qkv, B, N)                       # dense [B, H, N, 64] for the fused attention kernel
+            q, k, v = self._split_rope(qkv, B, self.Npad)                   # zero-padded rows for the backward GEMMs
+            ctx = torch.empty(M, D, dtype=torch.bfloat16, device=self.dev)
+            self._ck(self.lib.s3od_op_attention(qu.data_ptr(), ku.data_ptr(), vu.data_ptr(), ctx.data_ptr(), B, H, N, self._st()), "s3od_op_attention")
+            o = self._add_bias(self._gemm(ctx, wb["o.w"], M, D, D), w["o.b"])
+            x1 = self._residual(x0, o, w["ls1"])
+            xn2 = self._layernorm(x1, w["ln2.w"], w["ln2.b"])
+            hpre = self._add_bias(self._gemm(xn2, wb["up.w"], M, I, D), w["up.b"])
+            hmid = torch.empty(M, I, dtype=torch.bfloat16, device=self.dev)
+            self._ck(self.lib.s3od_train_gelu_forward(hpre.data_ptr(), hmid.data_ptr(), hpre.numel(), self._st()), "s3od_train_gelu_forward")
+            y = self._add_bias(self._gemm(hmid, wb["down.w"], M, D, I), w["down.b"])
+            x2 = self._residual(x1, y, w["ls2"])
+        self.saved = dict(B=B, x0=x0, xn1=xn1, q=q, k=k, v=v, ctx=ctx, o=o, x1=x1, xn2=xn2, hpre=hpre, hmid=hmid, y=y)
+        return x2.view(B, N, D)
+
+    # ---- backward -----------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def backward(self, dx2: torch.Tensor):
+        """dx2 = d loss / d output, fp32 (B, N, D) -> (d loss / d input, {reference parameter name suffix: gradient})."""
+        s, w, wt = self.saved, self.w, self.wt
+        B, N, Npad, D, I, H = s["B"], self.N, self.Npad, self.D, self.I, self.H
+        M = B * N
+        Mpad = (M + 63) // 64 * 64
+        grads: Dict[str, torch.Tensor] = {}
+        dx2 = dx2.to(self.dev, torch.float32).contiguous().view(M, D)
+        with torch.cuda.device(self.dev):
+            st = self._st()
+            T = lambda t, rows, cols: self._transpose(t, 1, rows, cols, Mpad).view(cols, Mpad)       # noqa: E731  tokens become the K dimension
+            # ---- MLP branch: x2 = x1 + ls2 * (down(gelu(up(LN2(x1)))))
+            grads["layer_scale2.lambda1"] = self._colsum(dx2, s["y"])
+            grads["mlp.down_proj.bias"] = self._colsum(dx2, None, w["ls2"])
+            dy = self._scale_cast(dx2, w["ls2"])
+            dhmid = self._gemm(dy, wt["down.w"], M, I, D)                                   # dgrad: dY W
+            grads["mlp.down_proj.weight"] = self._gemm(T(dy, M, D), T(s["hmid"], M, I), D, I, Mpad)      # wgrad: dY^T X
+            dhpre = torch.empty(M, I, dtype=torch.bfloat16, device=self.dev)
+            dhpre32 = torch.empty(M, I, dtype=torch.float32, device=self.dev)
+            self._ck(self.lib.s3od_train_gelu_backward(s["hpre"].data_ptr(), dhmid.data_ptr(), dhpre.data_ptr(), dhpre32.data_ptr(), dhmid.numel(), st),
+                     "s3od_train_gelu_backward")
+            grads["mlp.up_proj.bias"] = self._colsum(dhpre32)
+            dxn2 = self._gemm(dhpre, wt["up.w"], M, D, I)
+            grads["mlp.up_proj.weight"] = self._gemm(T(dhpre, M, I), T(s["xn2"], M, D), I, D, Mpad)
+            dx1, grads["norm2.weight"], grads["norm2.bias"] = self._ln_backward(s["x1"], w["ln2.w"], dxn2, dx2)
+            # ---- attention branch: x1 = x0 + ls1 * o_proj(attn(LN1(x0)))
+            grads["layer_scale1.lambda1"] = self._colsum(dx1, s["o"])
+            grads["attention.o_proj.bias"] = self._colsum(dx1, None, w["ls1"])
+            do = self._scale_cast(dx1, w["ls1"])
+            dctx = self._gemm(do, wt["o.w"], M, D, D)
+            grads["attention.o_proj.weight"] = self._gemm(T(do, M, D), T(s["ctx"], M, D), D, D, Mpad)
+            dO = self._split_heads(dctx, B)                                                 # [B, H, Npad, 64] bf16
+            Oh = self._split_heads(s["ctx"], B)
+            BH = B * H
+            Dvec = torch.empty(BH * Npad, dtype=torch.float32, device=self.dev)
+            self._ck(self.lib.s3od_train_rowdot64(dO.data_ptr(), Oh.data_ptr(), Dvec.data_ptr(), BH * Npad, st), "s3od_train_rowdot64")
+            kT = self._transpose(s["k"], BH, Npad, 64, Npad)                                # [BH][64][Npad]
+            qT = self._transpose(s["q"], BH, Npad, 64, Npad)
+            dOT = self._transpose(dO, BH, Npad, 64, Npad)
+            dqT = torch.empty(BH, 64, Npad, dtype=torch.float32, device=self.dev)
+            dkT, dvT = torch.empty_like(dqT), torch.empty_like(dqT)
+            q, k, v = s["q"].view(BH, Npad, 64), s["k"].view(BH, Npad, 64), s["v"].view(BH, Npad, 64)
+            dOv = dO.view(BH, Npad, 64)
+            P = torch.empty(Npad, Npad, dtype=torch.bfloat16, device=self.dev)
+            dS = torch.empty_like(P)
+            for bh in range(BH):
+                S = self._gemm(q[bh], k[bh], Npad, Npad, 64)                                # base-2 scores (q carries log2e / 8)
+                self._ck(self.lib.s3od_train_softmax2_rows(S.data_ptr(), P.data_ptr(), N, Npad, st), "s3od_train_softmax2_rows")
+                dP = self._gemm(dOv[bh], v[bh], Npad, Npad, 64)
+                self._ck(self.lib.s3od_train_softmax_backward(P.data_ptr(), dP.data_ptr(), Dvec[bh * Npad:].data_ptr(), dS.data_ptr(), N, Npad, st),
+                         "s3od_train_softmax_backward")
+                dST = self._transpose(dS, 1, Npad, Npad, Npad).view(Npad, Npad)
+                PT = self._transpose(P, 1, Npad, Npad, Npad).view(Npad, Npad)
+                dqT[bh].copy_(self._gemm(kT[bh], dS, 64, Npad, Npad))                       # (dS K)^T
+                dkT[bh].copy_(self._gemm(qT[bh], dST, 64, Npad, Npad))                      # (dS^T Q')^T
+                dvT[bh].copy_(self._gemm(dOT[bh], PT, 64, Npad, Npad))                      # (P^T dO)^T
+            dqkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=self.dev)
+            dqkv32 = torch.empty(M, 3 * D, dtype=torch.float32, device=self.dev)
+            self._ck(self.lib.s3od_train_qkv_merge_rope_backward(dqT.data_ptr(), dkT.data_ptr(), dvT.data_ptr(), self.cos.data_ptr(), self.sin.data_ptr(),
+                                                                 dqkv.data_ptr(), dqkv32.data_ptr(), B, N, Npad, H, self.arch.n_prefix, 1.0 / 8.0,
+                                                                 1.0 / self.LOG2E, st), "s3od_train_qkv_merge_rope_backward")
+            bq = self._colsum(dqkv32)
+            grads["attention.q_proj.bias"], grads["attention.v_proj.bias"] = bq[:D].clone(), bq[2 * D:].clone()      # k_proj has no bias
+            dxn1 = self._gemm(dqkv, wt["qkv.w"], M, D, 3 * D)
+            dW = self._gemm(T(dqkv, M, 3 * D), T(s["xn1"], M, D), 3 * D, D, Mpad)
+            grads["attention.q_proj.weight"], grads["attention.k_proj.weight"], grads["attention.v_proj.weight"] = dW[:D], dW[D:2 * D], dW[2 * D:]
+            dx0, grads["norm1.weight"], grads["norm1.bias"] = self._ln_backward(s["x0"], w["ln1.w"], dxn1, dx1)
+        return dx0.view(B, N, D), grads

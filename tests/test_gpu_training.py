@@ -155,3 +155,42 @@ def test_fused_exchange_and_adamw_over_emulated_ranks(world):
         assert float((opt.param(0)[e0:e1] - rp_enc.detach()).abs().max()) <= 3e-7
     finally:
         opt.close()
+
+
+@pytest.mark.parametrize("S,B,layer", [(224, 2, 3), (96, 3, 0), (1024, 1, 7)])
+def test_encoder_block_forward_backward_matches_autograd(vitb_sd, capsys, S, B, layer):
+    """One DINOv3ViTLayer (HF:424-450) forward + backward on the CUDA library against torch.autograd through the oracle's
+    encoder_layer in fp32 (TF32 off) on the same GPU.  224 = config/dataset/duts.yaml, 1024 = synth.yaml.  bf16 operands /
+    fp32 accumulation: every gradient within 2e-2 relative L2 (measured ~3e-3 ... 8e-3), forward within 1e-2."""
+    from oracle import model as om
+    from s3od_b200.training import EncoderBlockStep
+    p = f"encoder.model.layer.{layer}."
+    blk = EncoderBlockStep(vitb_sd, p, VITB, S, "cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(S + layer)
+    N = (S // 16) ** 2 + 5
+    x = torch.randn(B, N, 768, device="cuda", generator=g)
+    G = torch.randn(B, N, 768, device="cuda", generator=g)
+    out = blk.forward(x)
+    dx, grads = blk.backward(G)
+    torch.cuda.synchronize()
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = {k: v.cuda().clone().requires_grad_(True) for k, v in vitb_sd.items() if k.startswith(p)}
+        xr = x.clone().requires_grad_(True)
+        cos, sin = om.rope_tables(S // 16, S // 16, 64, 100.0)
+        ref = om.encoder_layer(sd, p, xr, cos.cuda(), sin.cuda(), 12, 1e-5)
+        (ref * G).sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    rel = lambda a, b: float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))      # noqa: E731
+    report = {"forward": rel(out, ref.detach()), "dx": rel(dx, xr.grad)}
+    for name, gte in grads.items():
+        report[name] = rel(gte, sd[p + name].grad)
+    with capsys.disabled():
+        print(f"\n[encoder block S={S} B={B} layer {layer}] worst relative L2: forward {report['forward']:.2e}, dx {report['dx']:.2e}, "
+              f"parameters {max(v for k, v in report.items() if k not in ('forward', 'dx')):.2e}")
+    assert report["forward"] <= 1e-2, report
+    assert set(grads) == {k[len(p):] for k in sd}, "a gradient is missing"
+    for k, v in report.items():
+        assert v <= 2e-2, (k, v, report)
