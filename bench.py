@@ -384,6 +384,25 @@ def training_slice_leg(rank, world, dev):
             "link_gbs_out_per_gpu": round(lay.total * (world - 1) / world * 6 / tb / 1e6, 1) if world > 1 else None,
             "adamw_hbm_gbs_n1": round(lay.total * 30 / ta / 1e6, 1) if world == 1 else None}
         opt_b.close()
+        # one encoder block forward + backward at the configuration's resolution (first, unfused form: see DESIGN.md section 6)
+        from s3od_b200.training import EncoderBlockStep
+        blk = EncoderBlockStep(synth_state_dict(VITB, 0), "encoder.model.layer.3.", VITB, 1024, dev)
+        Bb = 2
+        xb = torch.randn(Bb, 4101, 768, device=dev, generator=gen)
+        gb = torch.randn(Bb, 4101, 768, device=dev, generator=gen)
+        blk.forward(xb)
+        blk.backward(gb)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        blk.forward(xb)
+        blk.backward(gb)
+        b.record()
+        torch.cuda.synchronize(dev)
+        tms = a.elapsed_time(b)
+        ent["encoder_block_fwd_bwd"] = {"batch": Bb, "image_size": 1024, "ms": round(tms, 2),
+                                        "tflops": round(3 * 109.7 * Bb / tms, 1),
+                                        "note": "109.7 GFLOP forward per image and block (SURVEY 8d), backward counted as 2x"}
     except Exception as e:  # noqa: BLE001 - an extra leg must not take the headline number down with it
         ent["error"] = repr(e)[:300]
     return ent
