@@ -12,12 +12,8 @@ S3OD_INSTANTIATE_CONV_ROWS(96, EpiMask)
 S3OD_INSTANTIATE_CONV_ROWS(32, EpiMask)
 
 cudaError_t launch_conv_swap128(const ConvSwapParams& p, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_swap128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSwapCfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemOptIn configured;
+  if (cudaError_t e = configured.ensure(conv_swap128_kernel<0>, ConvSwapCfg::kSmemBytes); e != cudaSuccess) return e;
   const int items = p.m_tiles / 2;
   if (items <= 0) return cudaSuccess;
   const int grid = items < num_sms ? items : num_sms;
@@ -25,12 +21,8 @@ cudaError_t launch_conv_swap128(const ConvSwapParams& p, int num_sms, cudaStream
 }
 
 cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(convt_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvTRowCfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemOptIn configured;
+  if (cudaError_t e = configured.ensure(convt_rows_kernel<0>, ConvTRowCfg::kSmemBytes); e != cudaSuccess) return e;
   if (p.num_strips <= 0) return cudaSuccess;
   const int grid = p.num_strips < num_sms ? p.num_strips : num_sms;
   return launch_pdl(convt_rows_kernel<0>, dim3(grid), dim3(192), ConvTRowCfg::kSmemBytes, stream, p);

@@ -13,12 +13,8 @@ cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stre
     if (use_pair_kernel()) {
       using Cfg2 = Gemm2Cfg<BN, EPI_WARPS>;
       auto kern2 = gemm_tc2_kernel<BN, AMODE, Epi, EPI_WARPS>;
-      static bool configured2 = false;
-      if (!configured2) {
-        cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::kSmemBytes);
-        if (e != cudaSuccess) return e;
-        configured2 = true;
-      }
+      static SmemOptIn configured2;
+      if (cudaError_t e = configured2.ensure(kern2, Cfg2::kSmemBytes); e != cudaSuccess) return e;
       const int items = ((p.m_tiles + 1) / 2) * p.n_tiles;            // (M-tile pair, N tile) work items
       const int pairs = items < num_sms / 2 ? items : num_sms / 2;
       return launch_pdl(kern2, dim3(2 * pairs), dim3(128 + 32 * EPI_WARPS), Cfg2::kSmemBytes, stream, p);
@@ -26,12 +22,8 @@ cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stre
   }
   using Cfg = GemmCfg<BN, EPI_WARPS>;
   auto kern = gemm_tc_kernel<BN, AMODE, Epi, EPI_WARPS>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemOptIn configured;
+  if (cudaError_t e = configured.ensure(kern, Cfg::kSmemBytes); e != cudaSuccess) return e;
   const int grid = total < num_sms ? total : num_sms;
   return launch_pdl(kern, dim3(grid), dim3(128 + 32 * EPI_WARPS), Cfg::kSmemBytes, stream, p);
 }
@@ -40,12 +32,8 @@ template <int NOUT, class Epi>
 cudaError_t launch_conv_rows(const RowConvParams<Epi>& p, int num_sms, cudaStream_t stream) {
   using Cfg = RowConvCfg<NOUT>;
   auto kern = conv_rows_kernel<NOUT, Epi>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemOptIn configured;
+  if (cudaError_t e = configured.ensure(kern, Cfg::kSmemBytes); e != cudaSuccess) return e;
   if (p.num_strips <= 0) return cudaSuccess;
   const int grid = p.num_strips < num_sms ? p.num_strips : num_sms;
   return launch_pdl(kern, dim3(grid), dim3(192), Cfg::kSmemBytes, stream, p);

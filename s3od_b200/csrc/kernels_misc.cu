@@ -23,22 +23,14 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
   q.trace = nullptr;            // per-step clock64() stamps exist only in the tools/lab build (S3OD_ATTN_TRACE_BUILD)
   q.trace_bh = 0;
   q.bh_total = bh;
-  static bool configured = false;
+  static SmemOptIn configured;
 #if S3OD_ATTN_ONE_STREAM
   auto kern = attention_kernel_t<1, kAttnStages1>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes1);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = configured.ensure(kern, kAttnSmemBytes1); e != cudaSuccess) return e;
   return launch_pdl(kern, dim3(q_tiles * bh), dim3(kAttnThreads1), kAttnSmemBytes1, stream, q);
 #else
   auto kern = attention_kernel_t<2, kAttnStages>;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = configured.ensure(kern, kAttnSmemBytes); e != cudaSuccess) return e;
   return launch_pdl(kern, dim3(((q_tiles + 1) / 2) * bh), dim3(kAttnThreads), kAttnSmemBytes, stream, q);   // two query tiles per CTA, 1-D grid
 #endif
 }

@@ -5,6 +5,7 @@
 #include "conv_swap.cuh"
 #include "types.h"
 
+#include <atomic>
 #include <utility>
 
 namespace s3od {
@@ -36,6 +37,24 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.numAttrs = S3OD_PDL ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE setting: a multi-GPU predictor (one host thread per device)
+// must opt in on every device it launches on, and two host threads may get here at once.
+struct SmemOptIn {
+  std::atomic<unsigned> devices{0};          // bit d: configured on device d (d < 32)
+  template <class K>
+  cudaError_t ensure(K kern, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned bit = 1u << (dev & 31);
+    if (devices.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);      // idempotent: a race only sets it twice
+    if (e != cudaSuccess) return e;
+    devices.fetch_or(bit, std::memory_order_release);
+    return cudaSuccess;
+  }
+};
 
 template <int BN>
 inline int b_box_rows() { return ((BN == 256 || BN == 128) && use_pair_kernel()) ? BN / 2 : BN; }
