@@ -1,5 +1,5 @@
 set -x
-B="python bench.py --steps 2 --warmup 3 --cpu-sample 0 --e2e-steps 1"
+B="python bench.py --steps 2 --warmup 3 --cpu-sample 0 --e2e-steps 1 --no-extras --no-gpu-baseline"
 N="ncu --set full --import-source on --clock-control none --kernel-name-base demangled"
 $N -k regex:"tc2_kernel.*256.*1, s3od::EpiConv" -s 40 -c 1 -o gpurun_out/k_pairconv -f $B > /dev/null 2>&1
 $N -k regex:"tc2_kernel.*128.*1, s3od::EpiConv" -s 3 -c 1 -o gpurun_out/k_mhc1 -f $B > /dev/null 2>&1
