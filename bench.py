@@ -381,9 +381,20 @@ def training_slice_leg(rank, world, dev):
         ent["exchange_and_adamw"] = {
             "params_with_grad": lay.numel_with_grad(), "grad_bytes": lay.total * 4, "buckets": lay.num_buckets,
             "nccl_allreduce_plus_adamw_ms": round(ta, 3), "fused_p2p_kernel_ms": round(tb, 3), "speedup": round(ta / tb, 2),
-            "link_gbs_out_per_gpu": round(lay.total * (world - 1) / world * 6 / tb / 1e6, 1) if world > 1 else None,
+            # each link direction of a GPU carries its pushes (6 B / parameter of its slice per peer) plus the gradient slices its
+            # peers read from it (4 B): the roofline of the fused step is that volume over the measured 770 GB/s peer bandwidth
+            "link_bytes_per_direction": opt_b.link_bytes_per_step(),
+            "link_gbs": round(opt_b.link_bytes_per_step() / tb / 1e6, 1) if world > 1 else None,
+            "frac_of_link_roofline_770": round(opt_b.link_bytes_per_step() / 770e6 / tb, 3) if world > 1 else None,
             "adamw_hbm_gbs_n1": round(lay.total * 30 / ta / 1e6, 1) if world == 1 else None}
         opt_b.close()
+        if world > 1:
+            opt_c = FusedDataParallelAdamW(lay, dev, lr=1e-5, replicate_fp32=False)       # fp32 masters sharded, bf16 copy pushed
+            opt_c.param().copy_(p0)
+            tc = timed(opt_c.step, lambda: opt_c.grad().copy_(grads))
+            ent["exchange_and_adamw"]["fused_p2p_sharded_masters_ms"] = round(tc, 3)
+            ent["exchange_and_adamw"]["sharded_frac_of_link_roofline_770"] = round(opt_c.link_bytes_per_step() / 770e6 / tc, 3)
+            opt_c.close()
         # one encoder block forward + backward at the configuration's resolution (first, unfused form: see DESIGN.md section 6)
         from s3od_b200.training import EncoderBlockStep
         blk = EncoderBlockStep(synth_state_dict(VITB, 0), "encoder.model.layer.3.", VITB, 1024, dev)

@@ -165,7 +165,9 @@ int s3od_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float
  * process (s3od_peer_* below; entry `rank` is this process' own).  Rank r reads the r-th 1/world slice of [begin, end) from
  * every peer's gradients (summed in rank order: bit-identical replicas), averages, updates its slice of parameters and
  * moments, and writes the new parameters (fp32, and bf16 when d_params_bf16 != NULL) into every peer's buffers.  The caller
- * brackets the launch with two stream-ordered barriers (all gradients written / all parameters visible).
+ * brackets the launch with two stream-ordered barriers (all gradients written / all parameters visible).  d_params[w] may be NULL
+ * for w != rank: that peer then receives only the bf16 copy (fp32 masters sharded like the moments, 2 instead of 6 bytes per
+ * parameter pushed).  Each link direction of a GPU carries its pushes PLUS the gradient slices its peers read from it.
  * s3od_peer_alloc returns a whole device allocation (zeroed) that s3od_peer_export can turn into a 64-byte CUDA IPC handle for
  * another process of the same box to s3od_peer_open (peer access enabled lazily). */
 int s3od_peer_alloc(void** d_ptr, size_t bytes);

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "../../include/s3od_b200.h"
 #include "train.cuh"
@@ -319,24 +320,56 @@ int s3od_ddp_fused_adamw_step(const float* const* d_grads, float* const* d_param
   // pb.param[0] is read as the master copy: rotate the peer list so that this rank's own buffers come first for the
   // parameter read while the GRADIENT sum keeps the global rank order (bit-identical replicas)
   for (int w = 0; w < world; ++w) {
-    if (d_grads[w] == nullptr || d_params[w] == nullptr) return train_fail(S3OD_ERR_ARG, "null peer buffer in s3od_ddp_fused_adamw_step");
+    // a peer's fp32 parameter buffer may be NULL: that peer then only receives the bf16 copy (sharded fp32 masters)
+    if (d_grads[w] == nullptr || (w == rank && d_params[w] == nullptr) || (d_params[w] == nullptr && d_params_bf16 == nullptr))
+      return train_fail(S3OD_ERR_ARG, "null peer buffer in s3od_ddp_fused_adamw_step");
     pb.grad[w] = d_grads[w];
     pb.param[w] = d_params[(rank + w) % world];
     pb.param_bf16[w] = d_params_bf16 != nullptr ? static_cast<__nv_bfloat16*>(d_params_bf16[(rank + w) % world]) : nullptr;
   }
-  // rank r owns the r-th slice of [begin, end), cut on 4-element boundaries
-  const size_t groups = (end - begin) >> 2;
-  const size_t g_lo = groups * rank / world, g_hi = groups * (rank + 1) / world;
-  const size_t lo = begin + (g_lo << 2), hi = begin + (g_hi << 2);
-  if (hi <= lo) return S3OD_OK;
+  if (world < kMaxPeers) pb.grad[world] = d_grads[rank];     // lab builds (S3OD_P2P_TEST & 4) read every term from the local buffer
+  // The 8-aligned body [b8, e8) is cut into `world` slices of whole 8-element groups (rank r owns the r-th); the up to 4 + 4
+  // elements outside it go to rank 0 through a one-block edge kernel.
+  const size_t b8 = (begin + 7) & ~size_t(7), e8 = end & ~size_t(7);
   AdamWCfg c{};
   c.lr = lr; c.beta1 = beta1; c.beta2 = beta2; c.eps = eps; c.weight_decay = weight_decay;
   c.grad_scale = 1.0f / static_cast<float>(world);          // DistributedDataParallel averages the gradients
   c.bias_correction1 = static_cast<float>(1.0 - std::pow(static_cast<double>(beta1), step));
   c.inv_sqrt_bias_correction2 = static_cast<float>(1.0 / std::sqrt(1.0 - std::pow(static_cast<double>(beta2), step)));
-  const size_t want = ((hi - lo) / 4 + 511) / 512;
-  const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(want, static_cast<size_t>(2) * num_sms())));
-  adamw_p2p_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(pb, world, d_exp_avg, d_exp_avg_sq, lo, hi, c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t lo = 0, hi = 0;
+  if (e8 > b8) {
+    const size_t groups = (e8 - b8) >> 3;
+    lo = b8 + ((groups * rank / world) << 3);
+    hi = b8 + ((groups * (rank + 1) / world) << 3);
+  }
+  const bool edges = rank == 0 && (e8 <= b8 || b8 > begin || e8 < end);
+  auto launch = [&](auto wc) {
+    constexpr int W = decltype(wc)::value;
+    if (hi > lo) {
+      const size_t want = (hi - lo + kP2PChunk - 1) / kP2PChunk;
+      const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>(want, static_cast<size_t>(4) * num_sms())));
+      adamw_p2p_kernel<W><<<grid, 256, 0, st>>>(pb, d_exp_avg, d_exp_avg_sq, lo, hi, c);
+    }
+    if (edges) {
+      if (e8 <= b8) {
+        adamw_p2p_edge_kernel<W><<<1, 32, 0, st>>>(pb, d_exp_avg, d_exp_avg_sq, begin, end, c);
+      } else {
+        if (b8 > begin) adamw_p2p_edge_kernel<W><<<1, 32, 0, st>>>(pb, d_exp_avg, d_exp_avg_sq, begin, b8, c);
+        if (e8 < end) adamw_p2p_edge_kernel<W><<<1, 32, 0, st>>>(pb, d_exp_avg, d_exp_avg_sq, e8, end, c);
+      }
+    }
+  };
+  switch (world) {
+    case 1: launch(std::integral_constant<int, 1>{}); break;
+    case 2: launch(std::integral_constant<int, 2>{}); break;
+    case 3: launch(std::integral_constant<int, 3>{}); break;
+    case 4: launch(std::integral_constant<int, 4>{}); break;
+    case 5: launch(std::integral_constant<int, 5>{}); break;
+    case 6: launch(std::integral_constant<int, 6>{}); break;
+    case 7: launch(std::integral_constant<int, 7>{}); break;
+    default: launch(std::integral_constant<int, 8>{}); break;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return train_fail(S3OD_ERR_CUDA, std::string("adamw_p2p kernel: ") + cudaGetErrorString(e));
   return S3OD_OK;

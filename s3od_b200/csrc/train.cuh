@@ -17,6 +17,8 @@
 
 namespace s3od {
 
+#define S3OD_TRAIN_DEVICE __device__ __forceinline__
+
 struct LossCfg {
   float focal_weight, iou_weight, mse_weight;
   float full_mask_lambda, decay_rate;
@@ -338,46 +340,136 @@ struct PeerBuffers {
   __nv_bfloat16* param_bf16[kMaxPeers];       // all null: no bf16 copy
 };
 
-__global__ void __launch_bounds__(512) adamw_p2p_kernel(PeerBuffers pb, int world, float* __restrict__ m, float* __restrict__ v,
-                                                        size_t lo, size_t hi, AdamWCfg c) {
-  const size_t i0 = lo >> 2, i1 = hi >> 2;                 // the shard is a whole number of float4 groups
+// W = number of ranks (compile time: the peer loops unroll without predicates).  A thread owns EIGHT consecutive parameters per
+// iteration: two 16-byte gradient loads per peer (up to 8 remote loads in flight per thread; the link latency is ~2 us, so bytes
+// in flight are what matter) and, per peer, two 16-byte fp32 stores + ONE 16-byte bf16 store.  Measured on 2 x B200 (lab switches
+// S3OD_P2P_TEST): with 8-byte bf16 stores (four parameters per thread) the bf16 copy alone cost 0.19 ms for 108 MB while the
+// 215 MB of fp32 stores cost 0.12 ms - sub-16-byte remote stores waste link packets.
+#ifndef S3OD_P2P_TEST
+#define S3OD_P2P_TEST 0            // lab only: 1 = no remote bf16 stores, 2 = no remote stores at all, 4 = no remote loads
+#endif
+__device__ __forceinline__ void adamw_update4(float4& p4, float4& m4, float4& v4, const float4& g4, const AdamWCfg& c, float step_size) {
+  float pv[4] = {p4.x, p4.y, p4.z, p4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+  const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float g = gv[j] * c.grad_scale;
+    pv[j] = pv[j] * (1.0f - c.lr * c.weight_decay);
+    mv[j] = mv[j] + (g - mv[j]) * (1.0f - c.beta1);
+    vv[j] = vv[j] * c.beta2 + g * g * (1.0f - c.beta2);
+    pv[j] = pv[j] - step_size * (mv[j] / (sqrtf(vv[j]) * c.inv_sqrt_bias_correction2 + c.eps));
+  }
+  p4 = make_float4(pv[0], pv[1], pv[2], pv[3]);
+  m4 = make_float4(mv[0], mv[1], mv[2], mv[3]);
+  v4 = make_float4(vv[0], vv[1], vv[2], vv[3]);
+}
+__device__ __forceinline__ uint2 bf16x4(const float4& p) {
+  __nv_bfloat162 b0 = __floats2bfloat162_rn(p.x, p.y), b1 = __floats2bfloat162_rn(p.z, p.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&b0);
+  r.y = *reinterpret_cast<uint32_t*>(&b1);
+  return r;
+}
+
+// [lo, hi) in elements, both multiples of 8 (absolute indices: every bulk copy is 16-byte aligned and a multiple of 16 bytes).
+// A CTA walks chunks of 2048 parameters: every thread reduces two float4 groups over the peers (coalesced 512-byte warp loads,
+// 2 W loads in flight), updates them, stores m / v locally and stages the new parameters - fp32 and bf16 - in shared memory;
+// ONE thread then pushes the chunk to every peer with bulk asynchronous copies (cp.async.bulk, 8 KB + 4 KB per peer): the copy
+// engine of the SM writes full link packets while the threads are already on the next chunk (two staging buffers).  Per-thread
+// remote stores measured 0.5 ms for the same 323 MB at 2 GPUs, and 8-byte bf16 stores were the worst part of it.
+constexpr int kP2PChunk = 2048;
+S3OD_TRAIN_DEVICE void bulk_store(void* dst_global, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst_global)),
+               "r"(static_cast<uint32_t>(__cvta_generic_to_shared(src_smem))), "r"(bytes)
+               : "memory");
+}
+template <int W>
+__global__ void __launch_bounds__(256, 4) adamw_p2p_kernel(PeerBuffers pb, float* __restrict__ m, float* __restrict__ v, size_t lo, size_t hi,
+                                                           AdamWCfg c) {
+  __shared__ __align__(128) float s_p[2][kP2PChunk];
+  __shared__ __align__(128) uint2 s_b[2][kP2PChunk / 4];
   const float step_size = c.lr / c.bias_correction1;
-  for (size_t i = i0 + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < i1; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    float4 gp[kMaxPeers];
+  const size_t nchunks = (hi - lo + kP2PChunk - 1) / kP2PChunk;
+  int it = 0;
+  for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const size_t e0 = lo + ch * kP2PChunk;                       // first element of the chunk
+    const int n = static_cast<int>(hi - e0 < kP2PChunk ? hi - e0 : kP2PChunk);      // multiple of 8
+    const int ng = n >> 2;                                       // float4 groups in the chunk
+    const size_t f0 = e0 >> 2;
+    float4 sa[2];
+    {
+      float4 gp[2][W];
 #pragma unroll
-    for (int w = 0; w < kMaxPeers; ++w)                    // all peers' loads are in flight together (link latency ~ 1-2 us)
-      if (w < world) gp[w] = __ldcs(reinterpret_cast<const float4*>(pb.grad[w]) + i);
-    float gv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int h = 0; h < 2; ++h) {
+        const int gi = threadIdx.x + 256 * h;
 #pragma unroll
-    for (int w = 0; w < kMaxPeers; ++w)
-      if (w < world) {                                     // fixed summation order: bit-identical on whichever rank owns the slice
-        gv[0] += gp[w].x; gv[1] += gp[w].y; gv[2] += gp[w].z; gv[3] += gp[w].w;
+        for (int w = 0; w < W; ++w)
+          gp[h][w] = gi < ng ? __ldcs(reinterpret_cast<const float4*>(pb.grad[(S3OD_P2P_TEST & 4) ? W : w]) + f0 + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    // the owner's copy of the parameters is the master (every replica holds the same values)
-    float4 p4 = reinterpret_cast<const float4*>(pb.param[0])[i];
-    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
-    float pv[4] = {p4.x, p4.y, p4.z, p4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float g = gv[j] * c.grad_scale;
-      pv[j] = pv[j] * (1.0f - c.lr * c.weight_decay);
-      mv[j] = mv[j] + (g - mv[j]) * (1.0f - c.beta1);
-      vv[j] = vv[j] * c.beta2 + g * g * (1.0f - c.beta2);
-      pv[j] = pv[j] - step_size * (mv[j] / (sqrtf(vv[j]) * c.inv_sqrt_bias_correction2 + c.eps));
+      for (int h = 0; h < 2; ++h) {
+        sa[h] = gp[h][0];
+#pragma unroll
+        for (int w = 1; w < W; ++w) {                            // fixed summation order 0..W-1: bit-identical on whichever rank owns the slice
+          sa[h].x += gp[h][w].x; sa[h].y += gp[h][w].y; sa[h].z += gp[h][w].z; sa[h].w += gp[h][w].w;
+        }
+      }
     }
-    reinterpret_cast<float4*>(m)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
-    reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    const float4 pn = make_float4(pv[0], pv[1], pv[2], pv[3]);
-    __nv_bfloat162 b0 = __floats2bfloat162_rn(pv[0], pv[1]), b1 = __floats2bfloat162_rn(pv[2], pv[3]);
-    uint2 packed;
-    packed.x = *reinterpret_cast<uint32_t*>(&b0);
-    packed.y = *reinterpret_cast<uint32_t*>(&b1);
+    // the staging buffer is free once the bulk copies issued from it two iterations ago have READ it
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
 #pragma unroll
-    for (int w = 0; w < kMaxPeers; ++w)
-      if (w < world) {
-        reinterpret_cast<float4*>(pb.param[w])[i] = pn;
-        if (pb.param_bf16[w] != nullptr) reinterpret_cast<uint2*>(pb.param_bf16[w])[i] = packed;
+    for (int h = 0; h < 2; ++h) {
+      const int gi = threadIdx.x + 256 * h;
+      if (gi < ng) {
+        // the owner's copy of the parameters is the master (every replica holds the same values)
+        float4 p4 = reinterpret_cast<const float4*>(pb.param[0])[f0 + gi];
+        float4 m4 = reinterpret_cast<float4*>(m)[f0 + gi], v4 = reinterpret_cast<float4*>(v)[f0 + gi];
+        adamw_update4(p4, m4, v4, sa[h], c, step_size);
+        reinterpret_cast<float4*>(m)[f0 + gi] = m4;
+        reinterpret_cast<float4*>(v)[f0 + gi] = v4;
+        reinterpret_cast<float4*>(s_p[buf])[gi] = p4;
+        s_b[buf][gi] = bf16x4(p4);
       }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk copy engine
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        if ((S3OD_P2P_TEST & 2) && w > 0) continue;
+        if (pb.param[w] != nullptr) bulk_store(pb.param[w] + e0, s_p[buf], static_cast<uint32_t>(n) * 4u);
+        if ((S3OD_P2P_TEST & 1) && w > 0) continue;
+        if (pb.param_bf16[w] != nullptr) bulk_store(pb.param_bf16[w] + e0, s_b[buf], static_cast<uint32_t>(n) * 2u);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // every pushed byte has left before the CTA exits
+}
+
+// the (at most 4 + 4) elements of a range outside the 8-aligned body: one thread, same arithmetic, 4-element groups
+template <int W>
+__global__ void adamw_p2p_edge_kernel(PeerBuffers pb, float* __restrict__ m, float* __restrict__ v, size_t lo, size_t hi, AdamWCfg c) {
+  const float step_size = c.lr / c.bias_correction1;
+  for (size_t i = (lo >> 2) + threadIdx.x; i < (hi >> 2); i += blockDim.x) {
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const float4 g4 = reinterpret_cast<const float4*>(pb.grad[w])[i];
+      s4.x += g4.x; s4.y += g4.y; s4.z += g4.z; s4.w += g4.w;
+    }
+    float4 p4 = reinterpret_cast<const float4*>(pb.param[0])[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    adamw_update4(p4, m4, v4, s4, c, step_size);
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    const uint2 q = bf16x4(p4);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      if (pb.param[w] != nullptr) reinterpret_cast<float4*>(pb.param[w])[i] = p4;
+      if (pb.param_bf16[w] != nullptr) reinterpret_cast<uint2*>(pb.param_bf16[w])[i] = q;
+    }
   }
 }
 

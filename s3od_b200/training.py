@@ -332,8 +332,13 @@ class FusedDataParallelAdamW:
     slice arithmetic, used to check the path where fewer GPUs than ranks are available."""
 
     def __init__(self, layout: ParameterLayout, device, lr: float = 1e-5, head_lr_scale: float = 10.0, weight_decay: float = 0.05,
-                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, group=None, emulate_world: int = 0):
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, group=None, emulate_world: int = 0,
+                 replicate_fp32: bool = True):
+        """replicate_fp32=True (default) keeps DistributedDataParallel's invariant: every rank holds the full, bit-identical fp32
+        parameters.  False shards the fp32 masters like the moments (each rank's `param()` is current only on its own slice;
+        gather the slices for a checkpoint) and pushes just the bf16 working copy: 2 instead of 6 bytes per parameter."""
         self.lib = _bind_peer(_lib())
+        self.replicate_fp32 = replicate_fp32
         self.layout = layout
         self.device = torch.device(device)
         self.group = group
@@ -377,6 +382,9 @@ class FusedDataParallelAdamW:
             else:
                 ptrs = [[own[j].ptr] for j in range(3)]
         self._ptr_arrays = [(ctypes.c_void_p * self.world)(*col) for col in ptrs]
+        # per (virtual) rank view of the fp32 parameter pointers: peers are NULL when the masters are sharded
+        self._param_ptrs = {r: (ctypes.c_void_p * self.world)(*[p if (replicate_fp32 or w == r) else None for w, p in enumerate(ptrs[1])])
+                            for r in (range(self.world) if self.emulated else [self.rank])}
         self._token = torch.zeros(1, device=self.device)
 
     # this rank's buffers (virtual rank r in emulation)
@@ -405,14 +413,15 @@ class FusedDataParallelAdamW:
                     if hi <= lo:
                         continue
                     _check(self.lib, self.lib.s3od_ddp_fused_adamw_step(
-                        self._ptr_arrays[0], self._ptr_arrays[1], self._ptr_arrays[2], self.world, r, m.data_ptr(), v.data_ptr(), lo, hi,
+                        self._ptr_arrays[0], self._param_ptrs[r], self._ptr_arrays[2], self.world, r, m.data_ptr(), v.data_ptr(), lo, hi,
                         self.steps, self.lrs[group] * lr_factor, self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
                         "s3od_ddp_fused_adamw_step")
         self._barrier()                                           # every rank's parameters are visible everywhere
 
     def link_bytes_per_step(self) -> int:
-        """Bytes this GPU reads from + writes to its peers per step: (world-1)/world x (4 B gradient in, 4 + 2 B parameter out)."""
-        return int(self.layout.total * (self.world - 1) / self.world * (4 + 6))
+        """Bytes ONE direction of this GPU's link carries per step: its pushes (4 + 2 B per parameter of its slice to each peer, or 2
+        B with sharded masters) plus the gradient slices its peers read from it (4 B) = (world-1)/world x 10 (or 6) B per parameter."""
+        return int(self.layout.total * (self.world - 1) / self.world * (4 + (6 if self.replicate_fp32 else 2)))
 
     def close(self):
         for p in self._opened:

@@ -194,3 +194,46 @@ def test_encoder_block_forward_backward_matches_autograd(vitb_sd, capsys, S, B, 
     assert set(grads) == {k[len(p):] for k in sd}, "a gradient is missing"
     for k, v in report.items():
         assert v <= 2e-2, (k, v, report)
+
+
+def test_fused_exchange_with_sharded_fp32_masters():
+    """replicate_fp32=False: every rank updates only its slice of the fp32 masters and pushes the bf16 working copy - after a step
+    all bf16 replicas are identical and equal bf16(torch.optim.AdamW result); each fp32 slice is current on its owner."""
+    from s3od_b200.training import FusedDataParallelAdamW, ParameterLayout
+    world = 4
+    lay = ParameterLayout(VITB)
+    opt = FusedDataParallelAdamW(lay, "cuda:0", lr=1e-5, emulate_world=world, replicate_fp32=False)
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(23)
+        p0 = torch.randn(lay.total, device="cuda", generator=gen) * 0.05
+        mean = torch.zeros(lay.total, device="cuda")
+        for r in range(world):
+            opt.param(r).copy_(p0)
+            opt.grad(r).copy_(torch.randn(lay.total, device="cuda", generator=gen))
+            mean += opt.grad(r)
+        mean /= world
+        (h0, h1), (e0, e1) = lay.group_ranges[1], lay.group_ranges[0]
+        rp_head, rp_enc = torch.nn.Parameter(p0[h0:h1].clone()), torch.nn.Parameter(p0[e0:e1].clone())
+        rp_head.grad, rp_enc.grad = mean[h0:h1].clone(), mean[e0:e1].clone()
+        torch.optim.AdamW([{"params": [rp_enc], "lr": 1e-5}, {"params": [rp_head], "lr": 1e-4}], weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8).step()
+        opt.step()
+        torch.cuda.synchronize()
+        want = torch.cat([rp_head.detach(), rp_enc.detach()])
+        for r in range(world):
+            assert torch.equal(opt.param_bf16(r), opt.param_bf16(0))
+        # the bf16 copy is the rounding of the owner's fp32 result: at most one bf16 ulp from bf16(reference)
+        assert float((opt.param_bf16(0).float() - want.bfloat16().float()).abs().max()) <= 2e-3 * float(want.abs().max())
+        # owner slices: rank r's fp32 masters are current on the r-th eighth-aligned slice of each group range
+        merged = torch.empty_like(p0)
+        for lo, hi in (lay.group_ranges[1], lay.group_ranges[0]):
+            b8, e8 = (lo + 7) // 8 * 8, hi // 8 * 8
+            groups = (e8 - b8) // 8
+            merged[lo:b8] = opt.param(0)[lo:b8]
+            merged[e8:hi] = opt.param(0)[e8:hi]
+            for r in range(world):
+                s0, s1 = b8 + (groups * r // world) * 8, b8 + (groups * (r + 1) // world) * 8
+                merged[s0:s1] = opt.param(r)[s0:s1]
+        assert float((merged - want).abs().max()) <= 3e-7
+        assert not torch.equal(opt.param(1), opt.param(0))            # the masters really are sharded
+    finally:
+        opt.close()

@@ -79,7 +79,8 @@ def main():
         print(json.dumps({"world": world, "params_with_grad": lay.numel_with_grad(), "grad_bytes": nbytes, "buckets": lay.num_buckets,
                           "nccl_allreduce_plus_adamw_ms": round(ta, 3), "fused_p2p_step_ms": round(tb, 3), "speedup": round(ta / tb, 2),
                           "fused_link_bytes_per_gpu": opt_b.link_bytes_per_step(),
-                          "fused_link_gbs_per_direction": round(lay.total * (world - 1) / world * 6 / tb / 1e6, 1) if world > 1 else None,
+                          "fused_link_gbs_per_direction": round(opt_b.link_bytes_per_step() / tb / 1e6, 1) if world > 1 else None,
+                          "frac_of_link_roofline_770": round(opt_b.link_bytes_per_step() / 770e6 / tb, 3) if world > 1 else None,
                           "max_abs_diff_vs_allreduce_path": diff, "bf16_copy_consistent": bf_ok, "replicas_bit_identical": same,
                           "ok": bool(diff <= 1e-6 and bf_ok and same)}), flush=True)
     opt_b.close()
