@@ -112,6 +112,13 @@ int s3od_metrics_stats(const float* d_pred, const float* d_mask, int h, int w, c
                        s3od_stream stream);
 int s3od_metrics_region(const float* d_pred, const float* d_mask, int h, int w, int x_split, int y_split, void* d_region,
                         size_t region_bytes, s3od_stream stream);
+/* s3od_metrics_weighted_f replaces WeightedFMeasure.cal_wfm (metrics.py:159-190: scipy distance_transform_edt with indices, 7x7
+ * Gaussian, weighted sums - on the CPU in the reference): exact separable Euclidean feature transform with scipy's tie-breaking,
+ * d_sums = {double sum of Ew over the foreground, double sum of Ew over the background, uint64 foreground pixels}; the caller
+ * finishes R = 1 - fg / n_fg, P = (n_fg - fg) / (n_fg - fg + bg + eps), Q = 2 R P / (R + P + eps)  (wfm = 0 when n_fg == 0). */
+int s3od_metrics_weighted_f(const float* d_pred, const float* d_mask, int h, int w, void* d_workspace, size_t workspace_bytes, void* d_sums,
+                            s3od_stream stream);
+size_t s3od_metrics_weighted_f_workspace_bytes(int h, int w);
 size_t s3od_metrics_stats_bytes(void);
 size_t s3od_metrics_region_bytes(void);
 

@@ -43,6 +43,7 @@ def main():
         rec[name + "_pred"], rec[name + "_mask"] = pred.numpy(), mask.numpy()
         rec[name + "_vals"] = np.array([em.metrics["mae"][0], em.metrics["max_f"][0], em.metrics["avg_f"][0], em.metrics["s_score"][0]], np.float64)
         rec[name + "_ems"] = np.asarray(em.emeasure.metrics["changeable_ems"][0], np.float64)
+        rec[name + "_wfm"] = np.float64(em.weighted_fmeasure.metrics["weighted_fms"][0])        # WeightedFMeasure.step (metrics.py:146-153)
         em2 = ref.EvaluationMetrics(device=None, sm_only=True)
         em2.step(pred.clone(), mask.clone())
         assert abs(em2.metrics["s_score"][0] - em.metrics["s_score"][0]) < 1e-7
@@ -50,7 +51,9 @@ def main():
     full = ref.EvaluationMetrics(device=None)
     for name, pred, mask in cases():
         full.step(pred.clone(), mask.clone())
-    rec["em_all_cases"] = np.float64(full.compute_metrics()["Em"])
+    allm = full.compute_metrics()
+    rec["em_all_cases"] = np.float64(allm["Em"])
+    rec["wf_all_cases"] = np.float64(allm["wF"])
     rec["names"] = np.array(names)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "metrics.npz"), **rec)
 

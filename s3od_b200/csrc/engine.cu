@@ -1188,6 +1188,20 @@ int s3od_metrics_region(const float* d_pred, const float* d_mask, int h, int w, 
   return S3OD_OK;
 }
 
+size_t s3od_metrics_weighted_f_workspace_bytes(int h, int w) { return h < 0 || w < 0 ? 0 : sod_wfm_workspace_bytes(h, w); }
+
+int s3od_metrics_weighted_f(const float* d_pred, const float* d_mask, int h, int w, void* d_workspace, size_t workspace_bytes, void* d_sums,
+                            s3od_stream stream) {
+  if (d_pred == nullptr || d_mask == nullptr || d_workspace == nullptr || d_sums == nullptr || h < 1 || w < 1 || w > 12000 ||
+      workspace_bytes < sod_wfm_workspace_bytes(h, w))
+    return fail(S3OD_ERR_ARG, "bad argument for s3od_metrics_weighted_f (workspace needs s3od_metrics_weighted_f_workspace_bytes(h, w) bytes)");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(launch_sod_wfm(d_pred, d_mask, h, w, d_workspace, d_sums, sms, static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
 size_t s3od_metrics_stats_bytes(void) { return sod_stats_bytes(); }
 size_t s3od_metrics_region_bytes(void) { return sod_region_bytes(); }
 

@@ -4,6 +4,7 @@
 #include "visualize.cuh"
 #include "metrics.cuh"
 #include <algorithm>
+#include <cmath>
 
 #include "launch.h"
 
@@ -176,6 +177,30 @@ cudaError_t launch_sod_region(const float* pred, const float* mask, int H, int W
   size_t blocks = (n + 255) / 256;
   if (blocks > static_cast<size_t>(8 * num_sms)) blocks = 8 * num_sms;
   sod_region_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pred, mask, H, W, X, Y, static_cast<SodRegion*>(region));
+  return cudaGetLastError();
+}
+
+size_t sod_wfm_workspace_bytes(int H, int W) { return static_cast<size_t>(H) * W * (sizeof(int) + 2 * sizeof(float)) + 256; }
+
+cudaError_t launch_sod_wfm(const float* pred, const float* mask, int H, int W, void* workspace, void* sums, int num_sms, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(WfmSums), stream);
+  if (e != cudaSuccess) return e;
+  const size_t n = static_cast<size_t>(H) * W;
+  if (n == 0) return cudaSuccess;
+  int* near_row = static_cast<int*>(workspace);
+  float* Et = reinterpret_cast<float*>(near_row + n);
+  int* dist2 = reinterpret_cast<int*>(Et + n);
+  // fspecial('gaussian', 7, 5) as matlab_style_gauss2D builds it (metrics.py:192-204): float64, normalised, then used on float32 data
+  WfmGauss g;
+  double k[49], sum = 0.0;
+  for (int a = -3; a <= 3; ++a)
+    for (int b = -3; b <= 3; ++b) sum += k[(a + 3) * 7 + b + 3] = std::exp(-(a * a + b * b) / 50.0);
+  for (int i = 0; i < 49; ++i) g.k[i] = k[i] / sum;
+  wfm_columns_kernel<<<(W + 255) / 256, 256, 0, stream>>>(mask, H, W, near_row);
+  wfm_rows_kernel<<<H, 256, static_cast<size_t>(W) * sizeof(int), stream>>>(pred, mask, near_row, H, W, Et, dist2);
+  size_t blocks = (n + 255) / 256;
+  if (blocks > static_cast<size_t>(8 * num_sms)) blocks = 8 * num_sms;
+  wfm_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(pred, mask, Et, dist2, H, W, g, static_cast<WfmSums*>(sums));
   return cudaGetLastError();
 }
 

@@ -94,6 +94,9 @@ cudaError_t launch_sod_stats(const float* pred, const float* mask, int H, int W,
                              cudaStream_t stream);
 cudaError_t launch_sod_region(const float* pred, const float* mask, int H, int W, int X, int Y, void* region, int num_sms,
                               cudaStream_t stream);
+// weighted F-measure (metrics.cuh): sums = {double fg_ew, double bg_ew, uint64 n_fg}
+cudaError_t launch_sod_wfm(const float* pred, const float* mask, int H, int W, void* workspace, void* sums, int num_sms, cudaStream_t stream);
+size_t sod_wfm_workspace_bytes(int H, int W);
 size_t sod_stats_bytes();
 size_t sod_region_bytes();
 // visualisation (visualize.cuh)

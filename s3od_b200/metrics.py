@@ -7,8 +7,9 @@ Same surface: `EvaluationMetrics(device, sm_only=False)`, `step(pred, mask)`, `c
 Differences, on purpose: `step` does not binarise the caller's `mask` in place (the reference does, metrics.py:269-270);
 the E-measure (metrics.py:14-137: its cumulative-histogram form) is evaluated from two 256-bin histograms the same
 device pass produces instead of numpy on a host copy; the weighted F-measure (scipy distance transform + 7x7 Gaussian on
-the CPU in the reference, metrics.py:140-210) is not part of this path, so `compute_metrics()` returns MAE, MaxF, AvgF, Sm,
-Em (or Sm alone with `sm_only=True`) and no wFm.  The ground truth of the E-measure is `mask >= 0.5`, which for masks in
+the CPU in the reference, metrics.py:140-210) runs on the device too (`s3od_metrics_weighted_f`: exact separable Euclidean
+feature transform with scipy's tie-breaking, double-accumulated 7x7 filter, weighted sums), so `compute_metrics()` returns MAE,
+MaxF, AvgF, Sm, Em and wF like the reference (or Sm alone with `sm_only=True`).  The ground truth of the E-measure is `mask >= 0.5`, which for masks in
 [0, 1] is what the reference's in-place binarisation followed by `gt > 0` amounts to.  Values agree with the reference to float32 rounding (sums are accumulated in
 double here, in float32 there).  There is no CPU fallback.
 """
@@ -29,6 +30,10 @@ class _Stats(ctypes.Structure):
                 ("em_all", ctypes.c_uint64 * 256), ("em_fg", ctypes.c_uint64 * 256)]
 
 
+class _WfmSums(ctypes.Structure):
+    _fields_ = [("fg_ew", ctypes.c_double), ("bg_ew", ctypes.c_double), ("n_fg", ctypes.c_uint64)]
+
+
 class _Region(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double * 4) for n in ("sp", "sm", "spp", "smm", "spm")]
 
@@ -45,12 +50,19 @@ class EvaluationMetrics:
         self.sm_only = sm_only
         self.metrics: Dict[str, List[float]] = {"mae": [], "max_f": [], "avg_f": [], "s_score": []}
         self.changeable_ems: List[np.ndarray] = []                     # EMeasure.metrics['changeable_ems'] (metrics.py:18-21)
+        self.weighted_fms: List[float] = []                            # WeightedFMeasure.metrics['weighted_fms'] (metrics.py:143-145)
         self._lib = load_library()
         assert self._lib.s3od_metrics_stats_bytes() == ctypes.sizeof(_Stats)
         assert self._lib.s3od_metrics_region_bytes() == ctypes.sizeof(_Region)
         self._th = torch.linspace(0, 1 - 1e-10, 255).to(self.device)  # metrics.py:319 (float32, same generator call)
         self._d_stats = torch.empty(ctypes.sizeof(_Stats), dtype=torch.uint8, device=self.device)
         self._d_region = torch.empty(ctypes.sizeof(_Region), dtype=torch.uint8, device=self.device)
+        self._lib.s3od_metrics_weighted_f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                      ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        self._lib.s3od_metrics_weighted_f_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+        self._lib.s3od_metrics_weighted_f_workspace_bytes.restype = ctypes.c_size_t
+        self._d_wfm = torch.empty(ctypes.sizeof(_WfmSums), dtype=torch.uint8, device=self.device)
+        self._wfm_ws = None
 
     # ---- device passes ---------------------------------------------------------------------------------------------
     def _stats(self, pred: torch.Tensor, mask: torch.Tensor) -> _Stats:
@@ -67,6 +79,24 @@ class EvaluationMetrics:
             _check(self._lib, self._lib.s3od_metrics_region(pred.data_ptr(), mask.data_ptr(), h, w, X, Y, self._d_region.data_ptr(),
                                                            self._d_region.numel(), _stream_ptr(self.device)), "s3od_metrics_region")
         return _Region.from_buffer_copy(self._d_region.cpu().numpy().tobytes())
+
+    def _weighted_f(self, pred: torch.Tensor, mask: torch.Tensor, beta: float = 1.0) -> float:
+        """WeightedFMeasure.step (metrics.py:146-190) with the per-pixel work on the device."""
+        h, w = pred.shape
+        need = self._lib.s3od_metrics_weighted_f_workspace_bytes(h, w)
+        if self._wfm_ws is None or self._wfm_ws.numel() < need:
+            self._wfm_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self._lib, self._lib.s3od_metrics_weighted_f(pred.data_ptr(), mask.data_ptr(), h, w, self._wfm_ws.data_ptr(), self._wfm_ws.numel(),
+                                                               self._d_wfm.data_ptr(), _stream_ptr(self.device)), "s3od_metrics_weighted_f")
+        sm = _WfmSums.from_buffer_copy(self._d_wfm.cpu().numpy().tobytes())
+        if sm.n_fg == 0:                                               # metrics.py:148-150
+            return 0.0
+        eps = float(np.spacing(1))
+        tpw, fpw = sm.n_fg - sm.fg_ew, sm.bg_ew
+        r = 1.0 - sm.fg_ew / sm.n_fg
+        p = tpw / (tpw + fpw + eps)
+        return float((1 + beta) * r * p / (r + beta * p + eps))
 
     # ---- formulas of the reference on the reduced quantities ---------------------------------------------------------
     @staticmethod
@@ -167,6 +197,7 @@ class EvaluationMetrics:
         f_score = (1 + 0.3) * prec * recall / (0.3 * prec + recall)  # metrics.py:250-252
         f_score[f_score != f_score] = 0
         self.changeable_ems.append(self._changeable_em(st, n))
+        self.weighted_fms.append(self._weighted_f(pred, mask))
         self.metrics["mae"].append(st.abs_err / n)
         self.metrics["max_f"].append(f_score.max().item())
         self.metrics["avg_f"].append(f_score.mean().item())
@@ -177,9 +208,11 @@ class EvaluationMetrics:
             return {"Sm": np.mean(self.metrics["s_score"])}
         return {"MAE": np.mean(self.metrics["mae"]), "MaxF": np.mean(self.metrics["max_f"]), "AvgF": np.mean(self.metrics["avg_f"]),
                 "Sm": np.mean(self.metrics["s_score"]),
-                "Em": np.mean(np.array(self.changeable_ems, dtype=np.float64), axis=0).mean()}          # metrics.py:134-137
+                "Em": np.mean(np.array(self.changeable_ems, dtype=np.float64), axis=0).mean(),          # metrics.py:134-137
+                "wF": np.mean(np.array(self.weighted_fms))}                                               # metrics.py:206-210
 
     def reset(self) -> None:
         for v in self.metrics.values():
             v.clear()
         self.changeable_ems.clear()
+        self.weighted_fms.clear()

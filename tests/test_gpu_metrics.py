@@ -30,9 +30,12 @@ def test_metrics_match_reference_golden(golden_dir):
         assert abs(sm.metrics["s_score"][i] - g[name + "_vals"][3]) <= TOL
         # E-measure: integer histograms + the reference's float64 formulas -> equal to rounding
         np.testing.assert_allclose(em.changeable_ems[i], g[name + "_ems"], rtol=1e-12, atol=1e-12)
+        # weighted F-measure: exact feature transform (scipy's tie-breaking), double-accumulated filter and sums
+        assert abs(em.weighted_fms[i] - float(g[name + "_wfm"])) <= 1e-9, (name, em.weighted_fms[i], float(g[name + "_wfm"]))
     out = em.compute_metrics()
-    assert set(out) == {"MAE", "MaxF", "AvgF", "Sm", "Em"} and set(sm.compute_metrics()) == {"Sm"}
+    assert set(out) == {"MAE", "MaxF", "AvgF", "Sm", "Em", "wF"} and set(sm.compute_metrics()) == {"Sm"}
     assert abs(out["Em"] - float(g["em_all_cases"])) <= 1e-12
+    assert abs(out["wF"] - float(g["wf_all_cases"])) <= 1e-9
     vals = np.stack([g[n + "_vals"] for n in g["names"]])
     assert abs(out["MAE"] - vals[:, 0].mean()) <= TOL and abs(out["Sm"] - vals[:, 3].mean()) <= TOL
     em.reset()
@@ -53,6 +56,12 @@ def test_metrics_fullsize_matches_oracle(capsys):
     got = {k: em.metrics[k][0] for k in ("mae", "max_f", "avg_f", "s_score")}
     for k in got:
         assert abs(got[k] - ref[k]) <= 2e-5, (k, got[k], ref[k])      # float32 sums over 1 M pixels in the oracle
+    from oracle.wfm import weighted_f
+    wf_ref = weighted_f(pred[::4, ::4].numpy(), mask[::4, ::4].numpy())               # the numpy oracle is O(H W^2): a 256 x 256 sub-sample
+    em_small = EvaluationMetrics("cuda:0")
+    em_small.step(pred[::4, ::4].contiguous().cuda(), mask[::4, ::4].contiguous().cuda())
+    assert abs(em_small.weighted_fms[0] - wf_ref) <= 1e-9, (em_small.weighted_fms[0], wf_ref)
+    assert 0.0 < em.weighted_fms[0] < 1.0
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(20):
@@ -60,4 +69,4 @@ def test_metrics_fullsize_matches_oracle(capsys):
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 20
     with capsys.disabled():
-        print(f"\n[metrics 1024x1024] step (2 device passes + 2 small D2H): {dt * 1e3:.2f} ms per image")
+        print(f"\n[metrics 1024x1024] step (stats + region + weighted-F passes, 3 small D2H): {dt * 1e3:.2f} ms per image")

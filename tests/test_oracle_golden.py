@@ -117,3 +117,28 @@ def test_metrics_oracle_matches_reference_golden(golden_dir):
         r = omt.step(torch.from_numpy(g[name + "_pred"]), torch.from_numpy(g[name + "_mask"]))
         got = np.array([r["mae"], r["max_f"], r["avg_f"], r["s_score"]])
         assert np.abs(got - g[name + "_vals"]).max() <= 1e-7, name
+        # weighted F-measure: the scipy-free restatement reproduces the unmodified reference (scipy EDT + convolve) to the last bit
+        from oracle.wfm import weighted_f
+        assert abs(weighted_f(g[name + "_pred"], g[name + "_mask"]) - float(g[name + "_wfm"])) <= 1e-12, name
+
+
+def test_feature_transform_ties_match_scipy():
+    """oracle/wfm.py::feature_transform against scipy.ndimage.distance_transform_edt(return_indices=True) - the call the
+    reference makes (metrics.py:161) - on tie-heavy masks: same distances AND the same nearest pixel for every background pixel."""
+    from scipy.ndimage import distance_transform_edt
+    from oracle.wfm import feature_transform
+    rng = np.random.default_rng(4)
+    for trial in range(8):
+        H, W = int(rng.integers(9, 45)), int(rng.integers(9, 45))
+        gt = rng.random((H, W)) > rng.choice([0.5, 0.85, 0.97])
+        if trial % 3 == 0:
+            gt = np.zeros((H, W), bool)
+            gt[H // 4:H // 2, W // 3:W // 2] = True
+            gt[1, 1] = gt[H - 2, W - 3] = True
+        if not gt.any():
+            continue
+        dist, idx = distance_transform_edt(gt == 0, return_indices=True)
+        d2, iy, ix = feature_transform(gt)
+        bg = ~gt
+        assert np.array_equal(iy[bg], idx[0][bg]) and np.array_equal(ix[bg], idx[1][bg])
+        assert np.abs(np.sqrt(d2[bg]) - dist[bg]).max() <= 1e-12
