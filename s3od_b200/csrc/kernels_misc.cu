@@ -1,5 +1,6 @@
 // Attention and bandwidth-bound kernel launchers.
 #include "attention.cuh"
+#include "attention_persist.cuh"
 #include "elementwise.cuh"
 #include "visualize.cuh"
 #include "metrics.cuh"
@@ -18,6 +19,13 @@ namespace s3od {
 #ifndef S3OD_ATTN_ONE_STREAM
 #define S3OD_ATTN_ONE_STREAM 0
 #endif
+// S3OD_ATTN_PERSIST=1: one persistent CTA per SM walking the item list (attention_persist.cuh; bit-identical results).  Measured
+// (round 2): 4 % faster than the one-item-per-CTA kernel in short bursts at 1.97 GHz (tools/lab), but no faster inside the sustained
+// step - every major kernel of the step, attention included, sits at the 1000 W power cap (tools/power_probe.py: 994 W at 1.77 GHz
+// for attention alone, 1.11 GHz for the 256 -> 256 convolution), so removing idle cycles only lowers the clock.  Off by default.
+#ifndef S3OD_ATTN_PERSIST
+#define S3OD_ATTN_PERSIST 0
+#endif
 
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream) {
   AttnParams q = p;
@@ -25,7 +33,17 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
   q.trace_bh = 0;
   q.bh_total = bh;
   static SmemOptIn configured;
-#if S3OD_ATTN_ONE_STREAM
+#if S3OD_ATTN_PERSIST
+  {
+    // persistent form: one CTA per SM walks the item list (attention_persist.cuh)
+    if (cudaError_t e = configured.ensure(attention_persist_kernel, kAttnPSmemBytes); e != cudaSuccess) return e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int items = (q_tiles / 2) * bh + ((q_tiles & 1) ? bh : 0);
+    return launch_pdl(attention_persist_kernel, dim3(items < sms ? items : sms), dim3(kAttnThreads), kAttnPSmemBytes, stream, q);
+  }
+#elif S3OD_ATTN_ONE_STREAM
   auto kern = attention_kernel_t<1, kAttnStages1>;
   if (cudaError_t e = configured.ensure(kern, kAttnSmemBytes1); e != cudaSuccess) return e;
   return launch_pdl(kern, dim3(q_tiles * bh), dim3(kAttnThreads1), kAttnSmemBytes1, stream, q);

@@ -2,6 +2,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -lcuda -o attn_lab tools/lab/attn_lab.cu [-DS3OD_ATTN_...]
 #define S3OD_ATTN_TRACE_BUILD
 #include "../../s3od_b200/csrc/attention.cuh"
+#include "../../s3od_b200/csrc/attention_persist.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cudaTypedefs.h>
@@ -35,7 +36,12 @@ int main(int argc, char** argv) {
 #ifndef LAB_STREAMS
 #define LAB_STREAMS 2
 #endif
-#if LAB_STREAMS == 1
+#if LAB_STREAMS == 3
+  auto kern = attention_persist_kernel;
+  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int items = (((ntok + 127) / 128) / 2) * (int)BH + ((((ntok + 127) / 128) & 1) ? (int)BH : 0);
+  const int smem = kAttnPSmemBytes, threads = kAttnThreads, grid = items < sms ? items : sms;
+#elif LAB_STREAMS == 1
   auto kern = attention_kernel_t<1, kAttnStages1>;
   const int smem = kAttnSmemBytes1, threads = kAttnThreads1, grid = ((ntok + 127) / 128) * (int)BH;
 #else
