@@ -668,3 +668,94 @@ class EncoderBlockStep:
             grads["attention.q_proj.weight"], grads["attention.k_proj.weight"], grads["attention.v_proj.weight"] = dW[:D], dW[D:2 * D], dW[2 * D:]
             dx0, grads["norm1.weight"], grads["norm1.bias"] = self._ln_backward(s["x0"], w["ln1.w"], dxn1, dx1)
         return dx0.view(B, N, D), grads
+
+
+class EncoderTrainer:
+    """Forward + backward of the WHOLE encoder path the segmentation head consumes: patch embedding + prefix tokens
+    (DINOv3ViTEmbeddings.forward, HF:75-92), the `layers_needed` blocks (`EncoderBlockStep`) and the four un-normed taps
+    (`extract_intermediate_features`, /root/reference/src/s3od/model.py:62-86).  `backward` takes d loss / d tap_j (what the DPT
+    head's backward would hand over - that head backward is not built yet) and returns the gradient of every encoder parameter
+    under its reference name; with a `ParameterLayout` + flat buffer it writes them straight into the flat gradient buffer and
+    marks them ready for `GradientAllReduce` in backward order, so the exchange of the late layers overlaps the backward of the
+    early ones.  The (image -> patch row) im2col of the 16 x 16 / stride-16 convolution is a pure permutation of the input and is
+    done with a torch view + copy (data layout only); every contraction and reduction is a kernel of this library."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int, device="cuda:0"):
+        self.arch, self.dev, self.S = arch, torch.device(device), image_size
+        self.prefix = "encoder.model.layer." if any(k.startswith("encoder.model.layer.") for k in sd) else "encoder.layer."
+        self.blocks = [EncoderBlockStep(sd, f"{self.prefix}{i}.", arch, image_size, device) for i in range(arch.layers_needed)]
+        self.b0 = self.blocks[0]
+        e = "encoder.embeddings."
+        f = lambda t: t.detach().to(self.dev, torch.float32).contiguous()           # noqa: E731
+        D = arch.hidden
+        self.patch_w = f(sd[e + "patch_embeddings.weight"]).reshape(D, -1)            # [D, 3*16*16], k = c*256 + ky*16 + kx
+        self.patch_wb = self.patch_w.to(torch.bfloat16)
+        self.patch_b = f(sd[e + "patch_embeddings.bias"])
+        self.prefix_tokens = torch.cat([f(sd[e + "cls_token"]).reshape(1, D), f(sd[e + "register_tokens"]).reshape(-1, D)], 0)
+        self.saved = None
+
+    def _im2col(self, x: torch.Tensor) -> torch.Tensor:
+        B, g, ps = x.shape[0], self.S // self.arch.patch, self.arch.patch
+        return x.view(B, 3, g, ps, g, ps).permute(0, 2, 4, 1, 3, 5).reshape(B * g * g, 3 * ps * ps).to(torch.bfloat16).contiguous()
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """x fp32 (B, 3, S, S) -> [tap_0 .. tap_3], each fp32 (B, P, D) (hidden_states[taps][:, n_prefix:])."""
+        b0, D, npre = self.b0, self.arch.hidden, self.arch.n_prefix
+        x = x.to(self.dev, torch.float32).contiguous()
+        B = x.shape[0]
+        P = (self.S // self.arch.patch) ** 2
+        with torch.cuda.device(self.dev):
+            cols = self._im2col(x)
+            tok = b0._add_bias(b0._gemm(cols, self.patch_wb, B * P, D, cols.shape[1]), self.patch_b)
+            h = torch.empty(B, P + npre, D, dtype=torch.float32, device=self.dev)
+            h[:, :npre] = self.prefix_tokens
+            h[:, npre:] = tok.view(B, P, D)
+            taps = []
+            for i, blk in enumerate(self.blocks):
+                h = blk.forward(h)
+                if (i + 1) in self.arch.taps:
+                    taps.append(h[:, npre:])
+        self.saved = dict(cols=cols, B=B, P=P)
+        return taps
+
+    @torch.no_grad()
+    def backward(self, dtaps: Sequence[torch.Tensor], layout: Optional[ParameterLayout] = None, flat_grad: Optional[torch.Tensor] = None,
+                 reducer: Optional["GradientAllReduce"] = None) -> Dict[str, torch.Tensor]:
+        b0, D, npre = self.b0, self.arch.hidden, self.arch.n_prefix
+        B, P, cols = self.saved["B"], self.saved["P"], self.saved["cols"]
+        N = P + npre
+        grads: Dict[str, torch.Tensor] = {}
+
+        def emit(name: str, g: torch.Tensor):
+            grads[name] = g
+            if layout is not None and name in layout.by_name:
+                layout.view(flat_grad, name).copy_(g.reshape(layout.shapes[name]))
+                if reducer is not None:
+                    reducer.mark_ready(name)
+        tap_of_layer = {t: j for j, t in enumerate(self.arch.taps)}
+        with torch.cuda.device(self.dev):
+            dh = torch.zeros(B, N, D, dtype=torch.float32, device=self.dev)
+            for i in reversed(range(len(self.blocks))):
+                if (i + 1) in tap_of_layer:
+                    dh[:, npre:] += dtaps[tap_of_layer[i + 1]].to(self.dev, torch.float32)      # fan-in of the residual stream
+                dh, g = self.blocks[i].backward(dh)
+                dh = dh.contiguous()
+                # reverse definition order inside the block = the order autograd produces them
+                for name in ("layer_scale2.lambda1", "mlp.down_proj.bias", "mlp.down_proj.weight", "mlp.up_proj.bias", "mlp.up_proj.weight",
+                             "norm2.bias", "norm2.weight", "layer_scale1.lambda1", "attention.o_proj.bias", "attention.o_proj.weight",
+                             "attention.v_proj.bias", "attention.v_proj.weight", "attention.k_proj.weight", "attention.q_proj.bias",
+                             "attention.q_proj.weight", "norm1.bias", "norm1.weight"):
+                    emit(f"{self.prefix}{i}.{name}", g[name])
+            # embeddings: patch rows -> conv weight / bias (wgrad with the patches as K), prefix rows -> cls / register tokens
+            dtok = dh[:, npre:].reshape(B * P, D).contiguous()
+            Mpad = (B * P + 63) // 64 * 64
+            dtok_T = b0._transpose(dtok, 1, B * P, D, Mpad).view(D, Mpad)
+            cols_T = b0._transpose(cols, 1, B * P, cols.shape[1], Mpad).view(cols.shape[1], Mpad)
+            e = "encoder.embeddings."
+            emit(e + "patch_embeddings.bias", b0._colsum(dtok))
+            emit(e + "patch_embeddings.weight", b0._gemm(dtok_T, cols_T, D, cols.shape[1], Mpad).view(D, 3, self.arch.patch, self.arch.patch))
+            dpre = b0._colsum(dh[:, :npre].reshape(B, npre * D).contiguous()).view(npre, D)      # summed over the batch
+            emit(e + "register_tokens", dpre[1:].reshape(1, npre - 1, D).clone())
+            emit(e + "cls_token", dpre[:1].reshape(1, 1, D).clone())
+        return grads
