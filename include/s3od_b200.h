@@ -226,6 +226,37 @@ int s3od_train_softmax2_rows(const float* d_scores, void* d_probs, int ntok, int
 int s3od_train_softmax_backward(const void* d_probs, const float* d_dprobs, const float* d_rowdot, void* d_dscores, int ntok, int ntok_padded,
                                 s3od_stream stream);
 
+/* ---- DPT head training step (DPTSegmentationHead.forward in train mode, src/s3od/model.py:193-238, 301-345, 348-405, 421-467, and its
+ * autograd): every convolution is the tcgen05 GEMM over an explicit im2col matrix; activations fp32 NHWC.
+ *   im2col / col2im            cols bf16 [B*OH*OW, k*k*C] <-> x fp32 (B, H, W, C), zero padding, stride; col2im is the dgrad fold
+ *   convt_fold / convt_unfold  ConvTranspose2d(k, stride, pad): y = fold(x W) + bias, and the gather of dy back into column form
+ *   copy_cols                  compacts a GEMM output padded to 128 columns (+ bias)
+ *   bn_forward / bn_backward   train-mode BatchNorm2d over the B*H*W rows (batch statistics, biased variance; model.py:334-345)
+ *   relu / relu_backward / add, upsample2x / upsample2x_backward (bilinear, align_corners=False; model.py:395-402)
+ *   small_linear / _backward   fp32 dense layers too small for the tensor path: classifier head (model.py:185-191), per-mask 1x1
+ *                              convolutions as a grouped form (group_step = input columns per output) */
+int s3od_train_im2col(const float* d_x, void* d_cols, int batch, int h, int w, int c, int k, int stride, int pad, s3od_stream stream);
+int s3od_train_col2im(const float* d_dcols, float* d_dx, int batch, int h, int w, int c, int k, int stride, int pad, int pitch, int accumulate,
+                      s3od_stream stream);
+int s3od_train_convt_fold(const float* d_cols, const float* d_bias, float* d_y, int batch, int h, int w, int cout, int k, int stride, int pad, int pitch,
+                          s3od_stream stream);
+int s3od_train_convt_unfold(const float* d_dy, void* d_dcols, int batch, int h, int w, int cout, int k, int stride, int pad, s3od_stream stream);
+int s3od_train_copy_cols(const float* d_in, float* d_out, long long rows, int cols, int pitch, const float* d_bias, s3od_stream stream);
+size_t s3od_train_bn_workspace_bytes(int rows, int cols);
+int s3od_train_bn_forward(const float* d_x, const float* d_gamma, const float* d_beta, float* d_xhat, float* d_y, float* d_mean, float* d_rstd, int rows,
+                          int cols, float eps, void* d_workspace, s3od_stream stream);
+int s3od_train_bn_backward(const float* d_dy, const float* d_xhat, const float* d_gamma, const float* d_rstd, float* d_dx, float* d_dgamma, float* d_dbeta,
+                           int rows, int cols, void* d_workspace, s3od_stream stream);
+int s3od_train_relu(const float* d_x, float* d_y, long long n, s3od_stream stream);
+int s3od_train_relu_backward(const float* d_dy, const float* d_x, float* d_dx, long long n, s3od_stream stream);
+int s3od_train_add(const float* d_a, const float* d_b, float* d_out, long long n, s3od_stream stream);
+int s3od_train_upsample2x(const float* d_x, float* d_y, int batch, int h, int w, int c, s3od_stream stream);
+int s3od_train_upsample2x_backward(const float* d_dy, float* d_dx, int batch, int h, int w, int c, s3od_stream stream);
+int s3od_train_small_linear(const float* d_a, const float* d_w, const float* d_bias, float* d_out, long long m, int n, int k, int lda, int group_step,
+                            s3od_stream stream);
+int s3od_train_small_linear_backward(const float* d_dout, const float* d_a, const float* d_w, float* d_da, float* d_dw, float* d_dbias, long long m, int n,
+                                     int k, int lda, int group_step, s3od_stream stream);
+
 /* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
 /* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */
 int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream);

@@ -119,23 +119,25 @@ def encoder_taps(sd, x, arch, stages=None, sdpa=False) -> List[torch.Tensor]:
     return taps
 
 
-def _bn(sd, p, x, eps):
+def _bn(sd, p, x, eps, train=False):
+    if train:       # nn.BatchNorm2d in train mode: batch statistics (the running buffers' update does not enter the output)
+        return F.batch_norm(x, None, None, sd[p + "weight"], sd[p + "bias"], True, 0.0, eps)
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, eps)
 
 
-def rcu(sd, p, x, eps):
+def rcu(sd, p, x, eps, train=False):
     o = F.conv2d(F.relu(x), sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
-    o = _bn(sd, p + "bn1.", o, eps)
+    o = _bn(sd, p + "bn1.", o, eps, train)
     o = F.conv2d(F.relu(o), sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
-    o = _bn(sd, p + "bn2.", o, eps)
+    o = _bn(sd, p + "bn2.", o, eps, train)
     return o + x
 
 
-def fusion(sd, p, x0, skip, size, eps):
+def fusion(sd, p, x0, skip, size, eps, train=False):
     out = x0
     if skip is not None:
-        out = out + rcu(sd, p + "resConfUnit1.", skip, eps)
-    out = rcu(sd, p + "resConfUnit2.", out, eps)
+        out = out + rcu(sd, p + "resConfUnit1.", skip, eps, train)
+    out = rcu(sd, p + "resConfUnit2.", out, eps, train)
     if size is None:
         out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=False)
     else:
@@ -143,7 +145,8 @@ def fusion(sd, p, x0, skip, size, eps):
     return F.conv2d(out, sd[p + "out_conv.weight"], sd[p + "out_conv.bias"])
 
 
-def head_forward(sd, taps, gh, gw, arch, stages=None) -> Dict[str, torch.Tensor]:
+def head_forward(sd, taps, gh, gw, arch, stages=None, train=False) -> Dict[str, torch.Tensor]:
+    """train=True: BatchNorm with batch statistics, as the reference's training step runs the head (lightning_module.py:234-245)."""
     h = "seg_head."
     B = taps[0].shape[0]
     feats = []
@@ -160,10 +163,10 @@ def head_forward(sd, taps, gh, gw, arch, stages=None) -> Dict[str, torch.Tensor]
     s = h + "scratch."
     l = [F.conv2d(feats[i], sd[s + f"layer{i + 1}_rn.weight"], None, padding=1) for i in range(4)]
     eps = arch.bn_eps
-    p4 = fusion(sd, s + "refinenet4.", l[3], None, l[2].shape[2:], eps)
-    p3 = fusion(sd, s + "refinenet3.", p4, l[2], l[1].shape[2:], eps)
-    p2 = fusion(sd, s + "refinenet2.", p3, l[1], l[0].shape[2:], eps)
-    p1 = fusion(sd, s + "refinenet1.", p2, l[0], None, eps)
+    p4 = fusion(sd, s + "refinenet4.", l[3], None, l[2].shape[2:], eps, train)
+    p3 = fusion(sd, s + "refinenet3.", p4, l[2], l[1].shape[2:], eps, train)
+    p2 = fusion(sd, s + "refinenet2.", p3, l[1], l[0].shape[2:], eps, train)
+    p1 = fusion(sd, s + "refinenet1.", p2, l[0], None, eps, train)
     pooled = p1.mean(dim=(2, 3))
     c = h + "classifier_head."
     iou = F.linear(F.relu(F.linear(pooled, sd[c + "2.weight"], sd[c + "2.bias"])), sd[c + "4.weight"], sd[c + "4.bias"])

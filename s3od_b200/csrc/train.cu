@@ -12,6 +12,7 @@
 #include "../../include/s3od_b200.h"
 #include "train.cuh"
 #include "train_block.cuh"
+#include "train_head.cuh"
 
 using namespace s3od;
 
@@ -266,6 +267,125 @@ int s3od_train_softmax_backward(const void* d_probs, const float* d_dprobs, cons
   softmax_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(d_probs), d_dprobs, d_rowdot,
                                                                                       static_cast<bf16_t*>(d_dscores), ntok, ntok_padded);
   S3OD_TRAIN_DONE("softmax_backward_kernel");
+}
+
+// ---- DPT head training step: glue kernels (train_head.cuh)
+int s3od_train_im2col(const float* d_x, void* d_cols, int batch, int h, int w, int c, int k, int stride, int pad, s3od_stream stream) {
+  if (d_x == nullptr || d_cols == nullptr || batch < 1 || h < 1 || w < 1 || c < 1 || k < 1 || stride < 1 || pad < 0)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_im2col");
+  const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
+  const long long n = static_cast<long long>(batch) * oh * ow * k * k * c;
+  im2col_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, static_cast<__nv_bfloat16*>(d_cols), batch, h, w, c, k, stride, pad, oh, ow);
+  S3OD_TRAIN_DONE("im2col_kernel");
+}
+
+int s3od_train_col2im(const float* d_dcols, float* d_dx, int batch, int h, int w, int c, int k, int stride, int pad, int pitch, int accumulate,
+                      s3od_stream stream) {
+  if (d_dcols == nullptr || d_dx == nullptr || pitch < k * k * c) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_col2im");
+  const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
+  const long long n = static_cast<long long>(batch) * h * w * c;
+  col2im_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dcols, d_dx, batch, h, w, c, k, stride, pad, oh, ow, pitch, accumulate);
+  S3OD_TRAIN_DONE("col2im_kernel");
+}
+
+int s3od_train_convt_fold(const float* d_cols, const float* d_bias, float* d_y, int batch, int h, int w, int cout, int k, int stride, int pad, int pitch,
+                          s3od_stream stream) {
+  if (d_cols == nullptr || d_y == nullptr || pitch < k * k * cout) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_convt_fold");
+  const int oh = (h - 1) * stride - 2 * pad + k, ow = (w - 1) * stride - 2 * pad + k;
+  const long long n = static_cast<long long>(batch) * oh * ow * cout;
+  convt_fold_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_cols, d_bias, d_y, batch, h, w, cout, k, stride, pad, oh, ow, pitch);
+  S3OD_TRAIN_DONE("convt_fold_kernel");
+}
+
+int s3od_train_convt_unfold(const float* d_dy, void* d_dcols, int batch, int h, int w, int cout, int k, int stride, int pad, s3od_stream stream) {
+  if (d_dy == nullptr || d_dcols == nullptr) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_convt_unfold");
+  const int oh = (h - 1) * stride - 2 * pad + k, ow = (w - 1) * stride - 2 * pad + k;
+  const long long n = static_cast<long long>(batch) * h * w * k * k * cout;
+  convt_unfold_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, static_cast<__nv_bfloat16*>(d_dcols), batch, h, w, cout, k, stride, pad, oh, ow);
+  S3OD_TRAIN_DONE("convt_unfold_kernel");
+}
+
+int s3od_train_copy_cols(const float* d_in, float* d_out, long long rows, int cols, int pitch, const float* d_bias, s3od_stream stream) {
+  if (d_in == nullptr || d_out == nullptr || rows < 1 || cols < 1 || pitch < cols) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_copy_cols");
+  copy_cols_kernel<<<grid_for(rows * cols), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, d_out, rows, cols, pitch, d_bias);
+  S3OD_TRAIN_DONE("copy_cols_kernel");
+}
+
+size_t s3od_train_bn_workspace_bytes(int rows, int cols) { return s3od_train_colsum_workspace_bytes(rows, cols) + 4 * static_cast<size_t>(cols) * sizeof(float); }
+
+int s3od_train_bn_forward(const float* d_x, const float* d_gamma, const float* d_beta, float* d_xhat, float* d_y, float* d_mean, float* d_rstd, int rows,
+                          int cols, float eps, void* d_workspace, s3od_stream stream) {
+  if (d_x == nullptr || d_gamma == nullptr || d_beta == nullptr || d_xhat == nullptr || d_y == nullptr || d_mean == nullptr || d_rstd == nullptr ||
+      d_workspace == nullptr || rows < 1 || cols < 1)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_bn_forward");
+  float* sums = static_cast<float*>(d_workspace);                           // [sum x | sum x^2 | - | -], then the column-sum partials
+  void* ws = sums + 4 * static_cast<size_t>(cols);
+  int rc = s3od_train_colsum(d_x, nullptr, rows, cols, nullptr, sums, 0, ws, stream);
+  if (rc != S3OD_OK) return rc;
+  rc = s3od_train_colsum(d_x, d_x, rows, cols, nullptr, sums + cols, 0, ws, stream);
+  if (rc != S3OD_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bn_stats_kernel<<<(cols + 255) / 256, 256, 0, st>>>(sums, sums + cols, d_mean, d_rstd, cols, 1.0f / rows, eps);
+  const long long n = static_cast<long long>(rows) * cols;
+  bn_apply_kernel<<<grid_for(n), 256, 0, st>>>(d_x, d_mean, d_rstd, d_gamma, d_beta, d_xhat, d_y, n, cols);
+  S3OD_TRAIN_DONE("bn forward kernels");
+}
+
+int s3od_train_bn_backward(const float* d_dy, const float* d_xhat, const float* d_gamma, const float* d_rstd, float* d_dx, float* d_dgamma, float* d_dbeta,
+                           int rows, int cols, void* d_workspace, s3od_stream stream) {
+  if (d_dy == nullptr || d_xhat == nullptr || d_gamma == nullptr || d_rstd == nullptr || d_dx == nullptr || d_dgamma == nullptr || d_dbeta == nullptr ||
+      d_workspace == nullptr)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_bn_backward");
+  void* ws = static_cast<float*>(d_workspace) + 4 * static_cast<size_t>(cols);
+  int rc = s3od_train_colsum(d_dy, nullptr, rows, cols, nullptr, d_dbeta, 0, ws, stream);
+  if (rc != S3OD_OK) return rc;
+  rc = s3od_train_colsum(d_dy, d_xhat, rows, cols, nullptr, d_dgamma, 0, ws, stream);
+  if (rc != S3OD_OK) return rc;
+  const long long n = static_cast<long long>(rows) * cols;
+  bn_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, d_xhat, d_gamma, d_rstd, d_dbeta, d_dgamma, d_dx, n, cols, 1.0f / rows);
+  S3OD_TRAIN_DONE("bn backward kernels");
+}
+
+int s3od_train_relu(const float* d_x, float* d_y, long long n, s3od_stream stream) {
+  if (d_x == nullptr || d_y == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_relu");
+  relu_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, n);
+  S3OD_TRAIN_DONE("relu_kernel");
+}
+int s3od_train_relu_backward(const float* d_dy, const float* d_x, float* d_dx, long long n, s3od_stream stream) {
+  if (d_dy == nullptr || d_x == nullptr || d_dx == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_relu_backward");
+  relu_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, d_x, d_dx, n);
+  S3OD_TRAIN_DONE("relu_backward_kernel");
+}
+int s3od_train_add(const float* d_a, const float* d_b, float* d_out, long long n, s3od_stream stream) {
+  if (d_a == nullptr || d_b == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_add");
+  add_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, d_b, d_out, n);
+  S3OD_TRAIN_DONE("add_kernel");
+}
+int s3od_train_upsample2x(const float* d_x, float* d_y, int batch, int h, int w, int c, s3od_stream stream) {
+  if (d_x == nullptr || d_y == nullptr || batch < 1 || h < 1 || w < 1 || c < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_upsample2x");
+  const long long n = static_cast<long long>(batch) * 4 * h * w * c;
+  upsample2x_f32_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, batch, h, w, c);
+  S3OD_TRAIN_DONE("upsample2x_f32_kernel");
+}
+int s3od_train_upsample2x_backward(const float* d_dy, float* d_dx, int batch, int h, int w, int c, s3od_stream stream) {
+  if (d_dy == nullptr || d_dx == nullptr || batch < 1 || h < 1 || w < 1 || c < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_upsample2x_backward");
+  const long long n = static_cast<long long>(batch) * h * w * c;
+  upsample2x_f32_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, d_dx, batch, h, w, c);
+  S3OD_TRAIN_DONE("upsample2x_f32_backward_kernel");
+}
+int s3od_train_small_linear(const float* d_a, const float* d_w, const float* d_bias, float* d_out, long long m, int n, int k, int lda, int group_step,
+                            s3od_stream stream) {
+  if (d_a == nullptr || d_w == nullptr || d_out == nullptr || m < 1 || n < 1 || k < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_small_linear");
+  small_linear_kernel<<<grid_for(m * n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, d_w, d_bias, d_out, m, n, k, lda, group_step);
+  S3OD_TRAIN_DONE("small_linear_kernel");
+}
+int s3od_train_small_linear_backward(const float* d_dout, const float* d_a, const float* d_w, float* d_da, float* d_dw, float* d_dbias, long long m, int n,
+                                     int k, int lda, int group_step, s3od_stream stream) {
+  if (d_dout == nullptr || d_a == nullptr || d_w == nullptr || d_da == nullptr || d_dw == nullptr) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_small_linear_backward");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  small_linear_dgrad_kernel<<<grid_for(m * (group_step ? static_cast<long long>(n) * k : k)), 256, 0, st>>>(d_dout, d_w, d_da, m, n, k, lda, group_step);
+  small_linear_wgrad_kernel<<<n * (k + 1), 256, 0, st>>>(d_dout, d_a, d_dw, d_dbias, m, n, k, lda, group_step);
+  S3OD_TRAIN_DONE("small_linear backward kernels");
 }
 
 // ---- peer-mapped buffers (CUDA IPC) and the fused exchange + optimiser step over them

@@ -298,3 +298,66 @@ def test_whole_encoder_backward_matches_autograd(vitb_sd, capsys, S, B):
     FusedAdamW(lay, params, lr=1e-5).step(flat)
     (h0, h1), (e0, e1) = lay.group_ranges[1], lay.group_ranges[0]
     assert float((params[e0:e1] - before[e0:e1]).abs().max()) > 0
+
+
+@pytest.mark.parametrize("S,B", [(64, 2), (128, 1)])
+def test_head_train_forward_backward_matches_autograd(vitb_sd, loss_module, capsys, S, B):
+    """The whole DPT head in TRAIN mode (batch-statistics BatchNorm, up-sampling before out_conv, nothing folded) + the loss:
+    forward, and every parameter / tap gradient of the REAL training loss, against torch.autograd through the oracle's
+    head_forward(train=True) + loss restatement in fp32 on the same GPU.  (A white-noise output gradient would make every
+    parameter gradient a heavily cancelling sum: the reference's own bf16 autocast backward then sits at 18 % relative error.)
+    The convolution biases in front of a train-mode BatchNorm have an exactly zero gradient; they are checked in absolute terms."""
+    import re
+    from oracle import model as om
+    from s3od_b200.training_head import HeadTrainer
+    head = HeadTrainer(vitb_sd, VITB, S, "cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(7 * S + B)
+    gp = S // 16
+    P = gp * gp
+    taps = [torch.randn(B, P, 768, device="cuda", generator=g) * (1.0 + 0.5 * j) for j in range(4)]
+    yy, xx = torch.meshgrid(torch.arange(S, device="cuda").float(), torch.arange(S, device="cuda").float(), indexing="ij")
+    masks = torch.stack([((((yy - (0.4 + 0.1 * b) * S) / (0.3 * S)) ** 2 + ((xx - 0.5 * S) / (0.25 * S)) ** 2) < 1).float() for b in range(B)])
+    out = head.forward(taps)
+    loss, parts, lg, _ = loss_module.forward_backward(out, {"masks": masks}, 2)
+    dtaps, grads = head.backward(lg["pred_masks"], lg["pred_iou"])
+    torch.cuda.synchronize()
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = {k: v.cuda().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in vitb_sd.items() if k.startswith("seg_head.")}
+        tr = [t.clone().requires_grad_(True) for t in taps]
+        with torch.enable_grad():
+            ref = om.head_forward(sd, tr, gp, gp, VITB, train=True)
+            ref_loss, _ = ol.loss_module(ref["pred_masks"], ref["pred_iou"], masks, 2)
+            ref_loss.backward()
+            sd_a = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in sd.items()}
+            tr_a = [t.clone().requires_grad_(True) for t in taps]
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ra = om.head_forward(sd_a, tr_a, gp, gp, VITB, train=True)
+            la, _ = ol.loss_module(ra["pred_masks"].float(), ra["pred_iou"].float(), masks, 2)
+            la.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    rel = lambda a, b: float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))      # noqa: E731
+    fm, fi = rel(out["pred_masks"], ref["pred_masks"].detach()), rel(out["pred_iou"], ref["pred_iou"].detach())
+    want = {k for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    assert set(grads) == want, (sorted(want - set(grads))[:6], sorted(set(grads) - want)[:6])
+    dead = re.compile(r"resConfUnit\d\.conv\d\.bias$")                  # a bias in front of a train-mode BatchNorm: gradient exactly 0
+    errs = {k: (rel(grads[k], sd[k].grad), rel(sd_a[k].grad, sd[k].grad)) for k in grads if not dead.search(k)}
+    for k in grads:
+        if dead.search(k):
+            bn_bias = k.replace("conv", "bn")
+            assert float(grads[k].norm()) <= 2e-2 * float(sd[bn_bias].grad.norm()) + 1e-6, k
+    for j in range(4):
+        errs[f"tap{j}"] = (rel(dtaps[j], tr[j].grad), rel(tr_a[j].grad, tr[j].grad))
+    med = sorted(v[0] for v in errs.values())[len(errs) // 2]
+    med_a = sorted(v[1] for v in errs.values())[len(errs) // 2]
+    worst = max((v[0], k) for k, v in errs.items())
+    with capsys.disabled():
+        print(f"\n[DPT head train step S={S} B={B}] loss {float(loss):.5f} vs {float(ref_loss):.5f}; forward masks {fm:.2e} iou {fi:.2e}; {len(errs)} gradients: "
+              f"median {med:.2e} (autocast {med_a:.2e}), worst {worst[0]:.2e} ({worst[1]}; autocast there {errs[worst[1]][1]:.2e})")
+    assert fm <= 2e-2 and fi <= 2e-2, (fm, fi)
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss))
+    assert med <= max(2e-2, med_a), (med, med_a)
+    for k, (mine, auto) in errs.items():
+        assert mine <= max(3e-2, 2.0 * auto), (k, mine, auto)
