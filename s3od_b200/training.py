@@ -483,7 +483,7 @@ class EncoderBlockStep:
         f = lambda t: t.detach().to(self.dev, torch.float32).contiguous()           # noqa: E731
         a = layer_prefix + "attention."
         D = self.D
-        kb = sd.get(a + "k_proj.bias", torch.zeros(D))
+        kb = sd.get(a + "k_proj.bias", torch.zeros(D, device=sd[a + "q_proj.bias"].device))
         self.w = {"qkv.w": f(torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0)),
                   "qkv.b": f(torch.cat([sd[a + "q_proj.bias"], kb, sd[a + "v_proj.bias"]], 0)),
                   "o.w": f(sd[a + "o_proj.weight"]), "o.b": f(sd[a + "o_proj.bias"]),

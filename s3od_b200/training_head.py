@@ -445,3 +445,59 @@ class HeadTrainer:
                     dfe = self.rs3.backward(dfe, em)
                 dtaps[i] = self.proj[i].backward(dfe, em).reshape(B, self.g * self.g, -1)
         return dtaps, grads
+
+
+class TrainStep:
+    """One optimisation step of BASELINE.json configs[3] - `SegmentationLightningModule.training_step` + `configure_optimizers`
+    (/root/reference/synth_sod/src/synth_sod/model_training/lightning_module.py:183-209, 234-285) without Lightning:
+        predictions = model(images)            EncoderTrainer + HeadTrainer (train mode)
+        loss = LossModule(predictions, batch)  training.LossModule (forward + backward kernels)
+        loss.backward()                        HeadTrainer.backward -> EncoderTrainer.backward, gradients written into the flat
+                                               reverse-autograd buffer and marked ready bucket by bucket
+        DDP gradient all-reduce                training.GradientAllReduce (overlaps the rest of the backward), mean folded below
+        AdamW.step()                           training.FusedAdamW (encoder lr, head lr x 10, weight decay 0.05)
+    The parameters live in ONE flat fp32 buffer (`ParameterLayout`); the per-layer GEMM operands are re-packed from it at the start
+    of every step (correctness-first: no persistent bf16 shadow yet).  Train-mode RoPE rescaling is not applied: the
+    encoder runs the deterministic eval-mode tables, like the parity oracle."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], arch: ArchSpec, image_size: int, device="cuda:0", lr: float = 1e-5, group=None,
+                 bucket_bytes: int = 64 << 20):
+        from .training import FusedAdamW, GradientAllReduce, LossModule, ParameterLayout
+        self.arch, self.S, self.dev = arch, image_size, torch.device(device)
+        prefix = "encoder.model.layer." if any(k.startswith("encoder.model.layer.") for k in sd) else "encoder.layer."
+        self.layout = ParameterLayout(arch, bucket_bytes, prefix)
+        self.static = {k: v.detach().to(self.dev) for k, v in sd.items() if k not in self.layout.by_name}      # buffers + grad-less parameters
+        self.param = self.layout.flatten({k: v for k, v in sd.items() if k in self.layout.by_name}, device=self.dev)
+        self.grad = torch.zeros_like(self.param)
+        self.reducer = GradientAllReduce(self.layout, self.grad, group)
+        self.opt = FusedAdamW(self.layout, self.param, lr=lr)
+        self.loss_module = LossModule()
+        self.epoch = 0
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        sd = dict(self.static)
+        for s in self.layout.segments:
+            sd[s.name] = self.layout.view(self.param, s.name)
+        return sd
+
+    @torch.no_grad()
+    def step(self, images: torch.Tensor, masks: torch.Tensor):
+        """images fp32 (B, 3, S, S), masks fp32 (B, S, S) in [0, 1] -> (loss, loss parts); parameters are updated in place."""
+        from .training import EncoderTrainer
+        sd = self.state_dict()
+        enc = EncoderTrainer(sd, self.arch, self.S, self.dev)
+        head = HeadTrainer(sd, self.arch, self.S, self.dev)
+        self.reducer.reset()
+        self.grad.zero_()
+
+        def emit(name, g):
+            if name in self.layout.by_name:
+                self.layout.view(self.grad, name).copy_(g.reshape(self.layout.shapes[name]))
+                self.reducer.mark_ready(name)
+        out = head.forward(enc.forward(images))
+        loss, parts, lg, _ = self.loss_module.forward_backward(out, {"masks": masks.to(self.dev)}, self.epoch)
+        dtaps, _ = head.backward(lg["pred_masks"], lg["pred_iou"], emit)
+        enc.backward(dtaps, self.layout, self.grad, self.reducer)
+        self.reducer.finish()
+        self.opt.step(self.grad, grad_scale=1.0 / self.reducer.world)
+        return loss, parts

@@ -361,3 +361,47 @@ def test_head_train_forward_backward_matches_autograd(vitb_sd, loss_module, caps
     assert med <= max(2e-2, med_a), (med, med_a)
     for k, (mine, auto) in errs.items():
         assert mine <= max(3e-2, 2.0 * auto), (k, mine, auto)
+
+
+def test_full_training_steps_follow_the_torch_reference(vitb_sd, capsys):
+    """Three optimisation steps of config 4 end to end on the library (encoder + head forward in train mode, loss, backward, bucketed
+    gradient exchange (single process: tracked only), fused AdamW with the reference's two groups) against the same three steps
+    of the fp32 torch reference arithmetic (autograd + torch.optim.AdamW); a learning rate large enough to move the loss."""
+    from oracle import model as om
+    from s3od_b200.training_head import TrainStep
+    S, B, lr = 64, 2, 2e-4
+    g = torch.Generator(device="cuda").manual_seed(99)
+    images = torch.randn(B, 3, S, S, device="cuda", generator=g)
+    yy, xx = torch.meshgrid(torch.arange(S, device="cuda").float(), torch.arange(S, device="cuda").float(), indexing="ij")
+    masks = torch.stack([((((yy - (0.4 + 0.15 * b) * S) / (0.3 * S)) ** 2 + ((xx - 0.5 * S) / (0.25 * S)) ** 2) < 1).float() for b in range(B)])
+    ts = TrainStep(vitb_sd, VITB, S, "cuda:0", lr=lr)
+    mine = [float(ts.step(images, masks)[0]) for _ in range(3)]
+    # reference
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = {k: v.cuda().clone() for k, v in vitb_sd.items()}
+        enc_p = [k for k in ts.layout.by_name if k.startswith("encoder.")]
+        head_p = [k for k in ts.layout.by_name if k.startswith("seg_head.")]
+        for k in enc_p + head_p:
+            sd[k].requires_grad_(True)
+        opt = torch.optim.AdamW([{"params": [sd[k] for k in enc_p], "lr": lr}, {"params": [sd[k] for k in head_p], "lr": lr * 10}],
+                                weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8)
+        ref = []
+        for _ in range(3):
+            opt.zero_grad()
+            with torch.enable_grad():
+                taps = om.encoder_taps(sd, images, VITB)
+                out = om.head_forward(sd, taps, S // 16, S // 16, VITB, train=True)
+                loss, _ = ol.loss_module(out["pred_masks"], out["pred_iou"], masks, 0)
+                loss.backward()
+            opt.step()
+            ref.append(float(loss))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    with capsys.disabled():
+        print(f"\n[training steps S={S} B={B} lr={lr}] loss here {['%.4f' % v for v in mine]} reference {['%.4f' % v for v in ref]}")
+    assert ref[2] < ref[0] and mine[2] < mine[0]                       # the step optimises
+    for a, b in zip(mine, ref):
+        assert abs(a - b) <= 3e-2 * abs(b), (mine, ref)
+    assert sorted(ts.reducer.launch_order) == list(range(ts.layout.num_buckets))
