@@ -320,7 +320,7 @@ def training_slice_leg(rank, world, dev):
     rank over CUDA-IPC peer memory (reduce its slice over NVLink, AdamW, broadcast fp32 + bf16 parameters).  At N > 1 this is the
     one place the repository moves data between GPUs."""
     from s3od_b200.training import FusedAdamW, FusedDataParallelAdamW, GradientAllReduce, LossModule, ParameterLayout
-    ent = {"what": "training-step slice: loss fwd+bwd, gradient exchange + AdamW (no network backward yet)", "n_gpus": world}
+    ent = {"what": "training step (config 4): loss fwd+bwd, gradient exchange + AdamW, encoder block, whole step", "n_gpus": world}
     try:
         lm = LossModule()
         B, S = 4, 1024
@@ -414,6 +414,32 @@ def training_slice_leg(rank, world, dev):
         ent["encoder_block_fwd_bwd"] = {"batch": Bb, "image_size": 1024, "ms": round(tms, 2),
                                         "tflops": round(3 * 109.7 * Bb / tms, 1),
                                         "note": "109.7 GFLOP forward per image and block (SURVEY 8d), backward counted as 2x"}
+        del blk, xb, gb
+        torch.cuda.empty_cache()
+        # the whole optimisation step of config 4 (train-mode forward, loss, backward, gradient exchange over the process group,
+        # fused AdamW) at one 1024^2 image per GPU: correctness-first kernels, but a REAL step with a REAL
+        # collective, so the N = 1, 2, 4, 8 records show how the exchange scales
+        from s3od_b200.training_head import TrainStep
+        ts = TrainStep(synth_state_dict(VITB, 0), VITB, 1024, dev, lr=1e-5)
+        g2 = torch.Generator(device=dev).manual_seed(11 + rank)
+        xi = torch.randn(1, 3, 1024, 1024, device=dev, generator=g2)
+        mi = (torch.rand(1, 1024, 1024, device=dev, generator=g2) > 0.5).float()
+        ts.step(xi, mi)
+        torch.cuda.synchronize(dev)
+        sharder.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nst = 2
+        for _ in range(nst):
+            lossv, _ = ts.step(xi, mi)
+        b.record()
+        torch.cuda.synchronize(dev)
+        tstep = sharder.max_over_ranks(a.elapsed_time(b), device=dev) / nst
+        ent["train_step"] = {"batch_per_gpu": 1, "image_size": 1024, "ms_per_step": round(tstep, 1), "images_per_s": round(world * 1e3 / tstep, 2),
+                             "loss": round(float(lossv), 4), "allreduce_buckets": ts.layout.num_buckets,
+                             "what": "TrainStep.step: encoder + head forward (train mode), loss fwd+bwd, full backward, bucketed all-reduce, fused AdamW"}
+        del ts
+        torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001 - an extra leg must not take the headline number down with it
         ent["error"] = repr(e)[:300]
     return ent

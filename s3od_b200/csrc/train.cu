@@ -142,7 +142,8 @@ int s3od_train_transpose(const void* d_in, int in_is_f32, void* d_out, int batch
                          int in_row_stride, float scale, s3od_stream stream) {
   if (d_in == nullptr || d_out == nullptr || batch < 1 || rows < 1 || cols < 1 || rows_padded < rows)
     return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_transpose");
-  const dim3 grid((cols + 31) / 32, (rows_padded + 31) / 32, batch);
+  if ((cols + 31) / 32 > 65535 || batch > 65535) return train_fail(S3OD_ERR_ARG, "s3od_train_transpose: more than 2 M columns or 65535 batches");
+  const dim3 grid((rows_padded + 31) / 32, (cols + 31) / 32, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in_is_f32)
     transpose_pad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(d_in), static_cast<bf16_t*>(d_out), rows, cols, rows_padded,

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const TIn* __restric
   const int b = blockIdx.z;
   const TIn* ib = in + static_cast<long long>(b) * in_batch_stride;
   bf16_t* ob = out + static_cast<long long>(b) * C * Rpad;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;          // rows (pixels / tokens: up to millions) on the unbounded grid axis
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -1,0 +1,20 @@
+"""Kernel-time breakdown of one full training step (torch.profiler, CUDA activities):  python tools/train_profile.py [S] [B]"""
+import sys
+import torch
+sys.path.insert(0, "/root/repo")
+from torch.profiler import ProfilerActivity, profile
+from s3od_b200.arch import VITB
+from s3od_b200.synth import synth_state_dict
+from s3od_b200.training_head import TrainStep
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+ts = TrainStep(synth_state_dict(VITB, 0), VITB, S, "cuda:0")
+g = torch.Generator(device="cuda").manual_seed(1)
+x = torch.randn(B, 3, S, S, device="cuda", generator=g)
+m = (torch.rand(B, S, S, device="cuda", generator=g) > 0.5).float()
+ts.step(x, m)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    ts.step(x, m)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
