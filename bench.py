@@ -268,6 +268,40 @@ def gpu_baseline(S, batch, dev):
         sd_bf = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v) for k, v in sd_dev.items()}
         sd_bf["_dtype"] = torch.bfloat16
         run("bf16_weights", False, True, sd_bf)          # + autocast: the fp32 RoPE tables / LayerNorm outputs meet bf16 operands
+        # the training step of config 4 the same way: oracle arithmetic (train-mode head) + loss restatement under autocast(bf16),
+        # torch.autograd, torch.optim.AdamW with the reference's two groups; batch 2 at 1024^2
+        try:
+            from oracle import loss as ol
+            sd_t = {k: v.detach().clone() for k, v in sd_dev.items()}
+            names = [k for k, v in sd_t.items() if v.is_floating_point() and "running" not in k]
+            for k in names:
+                sd_t[k].requires_grad_(True)
+            opt = torch.optim.AdamW([{"params": [sd_t[k] for k in names if k.startswith("encoder.")], "lr": 1e-5},
+                                     {"params": [sd_t[k] for k in names if k.startswith("seg_head.")], "lr": 1e-4}], weight_decay=0.05)
+            xt = torch.randn(2, 3, S, S, device=dev)
+            mt = (torch.rand(2, S, S, device=dev) > 0.5).float()
+
+            def train_step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    taps = om.encoder_taps(sd_t, xt, VITB, None, True)
+                    out = om.head_forward(sd_t, taps, S // 16, S // 16, VITB, train=True)
+                loss, _ = ol.loss_module(out["pred_masks"].float(), out["pred_iou"].float(), mt, 0)
+                loss.backward()
+                opt.step()
+            for _ in range(2):
+                train_step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                train_step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            res["train_step_bf16_autocast"] = round(3 * 2 / (e0.elapsed_time(e1) / 1e3), 2)
+        except Exception as e:  # noqa: BLE001
+            res["train_step_bf16_autocast"] = None
+            res["train_step_error"] = repr(e)[:200]
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
     return res

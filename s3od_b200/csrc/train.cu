@@ -172,14 +172,24 @@ int s3od_train_add_bias(float* d_a, const float* d_bias, long long n, int cols, 
   S3OD_TRAIN_DONE("add_bias_kernel");
 }
 
-size_t s3od_train_colsum_workspace_bytes(int rows, int cols) { return static_cast<size_t>((rows + 63) / 64) * cols * sizeof(float); }
+// rows per partial-sum block: 64 for short matrices, grown so that the second stage never walks more than ~1024 partials per column
+static int colsum_rows_per_block(int rows) {
+  int rpb = 64;
+  while ((rows + rpb - 1) / rpb > 1024) rpb *= 2;
+  return rpb;
+}
+size_t s3od_train_colsum_workspace_bytes(int rows, int cols) {
+  const int rpb = colsum_rows_per_block(rows);
+  return static_cast<size_t>((rows + rpb - 1) / rpb) * cols * sizeof(float);
+}
 
 int s3od_train_colsum(const float* d_a, const float* d_b, int rows, int cols, const float* d_colscale, float* d_out, int accumulate,
                       void* d_workspace, s3od_stream stream) {
   if (d_a == nullptr || d_out == nullptr || d_workspace == nullptr || rows < 1 || cols < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_colsum");
-  const int nblk = (rows + 63) / 64;
+  const int rpb = colsum_rows_per_block(rows);
+  const int nblk = (rows + rpb - 1) / rpb;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  colsum_partial_kernel<<<dim3((cols + 255) / 256, nblk), 256, 0, st>>>(d_a, d_b, rows, cols, 64, static_cast<float*>(d_workspace));
+  colsum_partial_kernel<<<dim3((cols + 255) / 256, nblk), 256, 0, st>>>(d_a, d_b, rows, cols, rpb, static_cast<float*>(d_workspace));
   colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(static_cast<const float*>(d_workspace), nblk, cols, d_colscale, d_out, accumulate);
   S3OD_TRAIN_DONE("colsum kernels");
 }
@@ -272,19 +282,22 @@ int s3od_train_softmax_backward(const void* d_probs, const float* d_dprobs, cons
 
 // ---- DPT head training step: glue kernels (train_head.cuh)
 int s3od_train_im2col(const float* d_x, void* d_cols, int batch, int h, int w, int c, int k, int stride, int pad, s3od_stream stream) {
-  if (d_x == nullptr || d_cols == nullptr || batch < 1 || h < 1 || w < 1 || c < 1 || k < 1 || stride < 1 || pad < 0)
-    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_im2col");
+  if (d_x == nullptr || d_cols == nullptr || batch < 1 || h < 1 || w < 1 || c < 8 || c % 8 != 0 || k < 1 || stride < 1 || pad < 0 ||
+      (reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_cols)) & 15)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_im2col (channels must be a multiple of 8, buffers 16-byte aligned)");
   const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
-  const long long n = static_cast<long long>(batch) * oh * ow * k * k * c;
+  const long long n = static_cast<long long>(batch) * oh * ow * k * k * (c / 8);
   im2col_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, static_cast<__nv_bfloat16*>(d_cols), batch, h, w, c, k, stride, pad, oh, ow);
   S3OD_TRAIN_DONE("im2col_kernel");
 }
 
 int s3od_train_col2im(const float* d_dcols, float* d_dx, int batch, int h, int w, int c, int k, int stride, int pad, int pitch, int accumulate,
                       s3od_stream stream) {
-  if (d_dcols == nullptr || d_dx == nullptr || pitch < k * k * c) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_col2im");
+  if (d_dcols == nullptr || d_dx == nullptr || pitch < k * k * c || c % 4 != 0 || pitch % 4 != 0 ||
+      (reinterpret_cast<uintptr_t>(d_dcols) | reinterpret_cast<uintptr_t>(d_dx)) & 15)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_col2im (channels and pitch must be multiples of 4, buffers 16-byte aligned)");
   const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
-  const long long n = static_cast<long long>(batch) * h * w * c;
+  const long long n = static_cast<long long>(batch) * h * w * (c / 4);
   col2im_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dcols, d_dx, batch, h, w, c, k, stride, pad, oh, ow, pitch, accumulate);
   S3OD_TRAIN_DONE("col2im_kernel");
 }

@@ -11,37 +11,48 @@
 
 namespace s3od {
 
-// cols[(b, oy, ox)][(ky*kw + kx)*C + c] = x[b, oy*stride - pad + ky, ox*stride - pad + kx, c]  (0 outside), bf16
+// cols[(b, oy, ox)][(ky*kw + kx)*C + c] = x[b, oy*stride - pad + ky, ox*stride - pad + kx, c]  (0 outside), bf16.
+// One thread per 8 channels (C % 8 == 0: every channel count of the head is a multiple of 64): two float4 loads, one 16-byte store.
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, int B, int H, int W, int C, int k,
                                                      int stride, int pad, int OH, int OW) {
-  const long long K = static_cast<long long>(k) * k * C;
-  const long long total = static_cast<long long>(B) * OH * OW * K;
+  const int C8 = C >> 3;
+  const long long total = static_cast<long long>(B) * OH * OW * k * k * C8;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
-    const int c = static_cast<int>(i % C);
-    long long r = i / C;
+    const int c8 = static_cast<int>(i % C8);
+    long long r = i / C8;
     const int tap = static_cast<int>(r % (k * k));
     r /= (k * k);
     const int ox = static_cast<int>(r % OW);
     r /= OW;
     const int oy = static_cast<int>(r % OH), b = static_cast<int>(r / OH);
     const int iy = oy * stride - pad + tap / k, ix = ox * stride - pad + tap % k;
-    const float v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[((static_cast<long long>(b) * H + iy) * W + ix) * C + c] : 0.0f;
-    cols[i] = __float2bfloat16_rn(v);
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float4* src = reinterpret_cast<const float4*>(x + ((static_cast<long long>(b) * H + iy) * W + ix) * C + 8 * c8);
+      const float4 a = __ldg(src), d = __ldg(src + 1);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(d.x, d.y), p3 = __floats2bfloat162_rn(d.z, d.w);
+      out = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                       *reinterpret_cast<uint32_t*>(&p3));
+    }
+    reinterpret_cast<uint4*>(cols)[i] = out;                 // i enumerates the 8-channel groups of the row-major [P, k*k*C] matrix in order
   }
 }
 
 // transpose of im2col (the dgrad fold): dx[b, iy, ix, c] = sum over the output positions / taps that read this input pixel of
-// dcols[(b, oy, ox)][tap*C + c]; dcols has row pitch `pitch` (>= k*k*C: GEMM outputs are padded to a multiple of 128 columns)
+// dcols[(b, oy, ox)][tap*C + c]; dcols has row pitch `pitch` (>= k*k*C: GEMM outputs are padded to a multiple of 128 columns).
+// One thread per 4 channels.
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcols, float* __restrict__ dx, int B, int H, int W, int C, int k, int stride,
                                                      int pad, int OH, int OW, int pitch, int accumulate) {
-  const long long total = static_cast<long long>(B) * H * W * C;
+  const int C4 = C >> 2;
+  const long long total = static_cast<long long>(B) * H * W * C4;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
-    const int c = static_cast<int>(i % C);
-    long long r = i / C;
+    const int c4 = static_cast<int>(i % C4);
+    long long r = i / C4;
     const int ix = static_cast<int>(r % W);
     r /= W;
     const int iy = static_cast<int>(r % H), b = static_cast<int>(r / H);
-    float s = 0.0f;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int ky = 0; ky < k; ++ky) {
       const int ty = iy + pad - ky;
       if (ty < 0 || ty % stride != 0) continue;
@@ -52,10 +63,16 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
         if (tx < 0 || tx % stride != 0) continue;
         const int ox = tx / stride;
         if (ox >= OW) continue;
-        s += dcols[((static_cast<long long>(b) * OH + oy) * OW + ox) * pitch + (ky * k + kx) * C + c];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dcols + ((static_cast<long long>(b) * OH + oy) * OW + ox) * pitch + (ky * k + kx) * C) + c4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
     }
-    dx[i] = accumulate ? dx[i] + s : s;
+    float4* dst = reinterpret_cast<float4*>(dx) + i;
+    if (accumulate) {
+      const float4 o = *dst;
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    *dst = s;
   }
 }
 
