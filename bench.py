@@ -677,6 +677,7 @@ def main():
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the short cfg3 (2048^2 sources) / cfg5 (ViT-L) legs")
     ap.add_argument("--no-gpu-baseline", dest="gpu_baseline", action="store_false", help="skip the PyTorch-on-this-GPU baseline leg")
     ap.add_argument("--gpu-baseline-batch", type=int, default=8)
+    ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false", help="do not pin the rank to the GPU's local CPU cores")
     ap.add_argument("--model", default="dinob", choices=["dinob", "dinol"], help="dinol = ViT-L backbone, one mask (BASELINE.json configs[4])")
     ap.add_argument("--dump-profile", default=None, help="write the per-kernel CUDA-event table (label, launches, images, ms) here")
     ap.add_argument("--cpu-sample", type=int, default=2, help="images timed on the CPU oracle (0 = skip)")
@@ -693,7 +694,11 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     rank, local_rank, world = sharder.init_from_env("nccl")
+    # N > 1: host staging / pinned result buffers stay on the GPU's socket (at N = 1 the CPU-baseline leg wants every core)
+    numa_bound = sharder.bind_to_gpu_numa(local_rank) if (args.numa_bind and world > 1) else False
     line = run_b200(args, rank, local_rank, world)
+    if rank == 0:
+        line["config"]["numa_bound"] = bool(numa_bound)
     if rank == 0:
         api_first = line.pop("_api_first")
         if world == 1 and args.gpu_baseline and args.model == "dinob":

@@ -297,6 +297,11 @@ class BackgroundRemoval:
     @torch.no_grad()
     def _run_on(self, r: int, arrays: List[np.ndarray]) -> List[RemovalResult]:
         torch.cuda.set_device(self.models[r].device)
+        if not getattr(self, "_bound", None):
+            self._bound = {}
+        if r not in self._bound:                               # this device's host thread stays on the GPU's socket (best effort)
+            from .sharder import bind_to_gpu_numa
+            self._bound[r] = bind_to_gpu_numa(self.models[r].dev_index)
         return self._replicas[r].run(arrays, self._pinned_results)
 
     def close(self):

@@ -51,3 +51,31 @@ def sum_over_ranks(value: float, device="cpu") -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin the calling thread to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root).
+    The end-to-end path moves 0.5 - 2 GB of results per step and GPU through pinned host buffers and stages pageable inputs with
+    host memcpys; with eight ranks on a two-socket box, unpinned ranks allocate and copy across the socket interconnect.
+    Best effort: returns False (and changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:  # noqa: BLE001 - an optimisation only
+        return False
