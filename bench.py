@@ -89,17 +89,19 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, watts = [], None, set(), []
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
+                watts.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": float(np.median(watts)) if watts else None}       # the sustained step sits at the board's power cap
 
 
 def kernel_family(label: str) -> str:
