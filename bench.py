@@ -700,7 +700,7 @@ def main():
     numa_bound = sharder.bind_to_gpu_numa(local_rank) if (args.numa_bind and world > 1) else False
     line = run_b200(args, rank, local_rank, world)
     if rank == 0:
-        line["config"]["numa_bound"] = bool(numa_bound)
+        line["numa_bound"] = bool(numa_bound)           # (not part of `config`: both arms quote the same config dict)
     if rank == 0:
         api_first = line.pop("_api_first")
         if world == 1 and args.gpu_baseline and args.model == "dinob":
