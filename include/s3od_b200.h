@@ -205,6 +205,7 @@ int s3od_ddp_fused_adamw_step(const float* const* d_grads, float* const* d_param
 int s3od_train_transpose(const void* d_in, int in_is_f32, void* d_out, int batch, int rows, int cols, int rows_padded, long long in_batch_stride,
                          int in_row_stride, float scale, s3od_stream stream);
 int s3od_train_scale_cast(const float* d_in, const float* d_colscale, void* d_out, long long n, int cols, s3od_stream stream);
+int s3od_train_cast_bf16_f32(const void* d_in, float* d_out, long long n, s3od_stream stream);       /* bf16 -> fp32 */
 int s3od_train_residual_scale_add(const float* d_x, const float* d_y, const float* d_lambda, float* d_out, long long n, int cols, s3od_stream stream);
 int s3od_train_add_bias(float* d_a, const float* d_bias, long long n, int cols, s3od_stream stream);
 size_t s3od_train_colsum_workspace_bytes(int rows, int cols);

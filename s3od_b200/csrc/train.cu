@@ -160,6 +160,12 @@ int s3od_train_scale_cast(const float* d_in, const float* d_colscale, void* d_ou
   S3OD_TRAIN_DONE("scale_cast_kernel");
 }
 
+int s3od_train_cast_bf16_f32(const void* d_in, float* d_out, long long n, s3od_stream stream) {
+  if (d_in == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_cast_bf16_f32");
+  cast_bf16_f32_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(d_in), d_out, n);
+  S3OD_TRAIN_DONE("cast_bf16_f32_kernel");
+}
+
 int s3od_train_residual_scale_add(const float* d_x, const float* d_y, const float* d_lambda, float* d_out, long long n, int cols, s3od_stream stream) {
   if (d_x == nullptr || d_y == nullptr || d_lambda == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_residual_scale_add");
   residual_scale_add_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, d_lambda, d_out, n, cols);

@@ -46,6 +46,10 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict
     out[i] = __float2bfloat16_rn(in[i] * (colscale != nullptr ? colscale[i % C] : 1.0f));
 }
 
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16_t* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) out[i] = __bfloat162float(in[i]);
+}
+
 // x_out = x + lambda[c] * y   (LayerScale + residual, fp32)
 __global__ void __launch_bounds__(256) residual_scale_add_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                                  const float* __restrict__ lambda, float* __restrict__ out, long long n, int C) {

@@ -42,6 +42,7 @@ def _bind_head(lib):
         lib.s3od_train_upsample2x_backward.argtypes = [vp, vp, ci, ci, ci, ci, vp]
         lib.s3od_train_small_linear.argtypes = [vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
         lib.s3od_train_small_linear_backward.argtypes = [vp, vp, vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
+        lib.s3od_train_cast_bf16_f32.argtypes = [vp, vp, ll, vp]
         lib._head_bound = True
     return lib
 
@@ -82,6 +83,22 @@ class _Ops:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=self.dev)
         self.ck(self.lib.s3od_train_scale_cast(x.data_ptr(), None, out.data_ptr(), x.numel(), x.shape[-1], self.st()), "s3od_train_scale_cast")
         return out
+
+    def to_f32(self, xb):
+        out = torch.empty(xb.shape, dtype=torch.float32, device=self.dev)
+        self.ck(self.lib.s3od_train_cast_bf16_f32(xb.data_ptr(), out.data_ptr(), xb.numel(), self.st()), "s3od_train_cast_bf16_f32")
+        return out
+
+    def conv3x3(self, xb, w_mat, bias, B, H, W, cin, cout):
+        """The inference path's implicit-GEMM convolution (TMA im2col, no materialised columns): bf16 NHWC in / out."""
+        yb = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device=self.dev)
+        if cin == 64 and cout == 64:
+            self.ck(self.lib.s3od_op_conv3x3_rows(xb.data_ptr(), w_mat.data_ptr(), bias.data_ptr() if bias is not None else None, yb.data_ptr(),
+                                                  B, H, W, 0, self.st()), "s3od_op_conv3x3_rows")
+        else:
+            self.ck(self.lib.s3od_op_conv3x3(xb.data_ptr(), w_mat.data_ptr(), bias.data_ptr() if bias is not None else None, yb.data_ptr(),
+                                             B, H, W, cin, cout, 0, self.st()), "s3od_op_conv3x3")
+        return yb
 
     def colsum(self, a, b=None):
         M, C = a.shape
@@ -134,6 +151,21 @@ class _Conv:
         self.wt = torch.zeros(self.Kp, self.Kc, dtype=torch.bfloat16, device=dev)
         self.wt[:self.K, :self.cout] = wm.t().to(torch.bfloat16)         # dgrad B operand [K (padded), cout (padded)]
         self.bias = b.detach().to(dev, torch.float32).contiguous() if b is not None else None
+        # Fast paths on the inference kernels (implicit GEMM through TMA, nothing materialised) for 3x3 / stride 1 / pad 1:
+        #   forward when cout % 256 == 0 (or the 64 -> 64 row kernel), dgrad = the same convolution of dy with the flipped,
+        #   transposed weights when the ORIGINAL cin % 256 == 0 (its output channels) - the bf16 results are widened back to fp32.
+        s3 = self.k == 3 and stride == 1 and pad == 1 and self.cin % 64 == 0
+        self.rows64 = s3 and self.cin == 64 and self.cout == 64               # needs W % 128 == 0 at run time
+        self.fast_fwd = s3 and self.cout % 256 == 0
+        self.fast_dgrad = s3 and self.cin % 256 == 0 and self.cout % 64 == 0
+        if self.fast_dgrad or self.rows64:                                    # w_d[ci][(ky', kx') * cout + co] = w[co][ci][2 - ky'][2 - kx']
+            self.wd = w.detach().to(dev, torch.float32).flip(2, 3).permute(1, 2, 3, 0).reshape(self.cin, 9 * self.cout).to(torch.bfloat16).contiguous()
+
+    def _cols(self, x, B, H, W, P):
+        o = self.ops
+        cols = torch.empty(P, self.K, dtype=torch.bfloat16, device=o.dev)
+        o.ck(o.lib.s3od_train_im2col(x.data_ptr(), cols.data_ptr(), B, H, W, self.cin, self.k, self.stride, self.pad, o.st()), "s3od_train_im2col")
+        return cols
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         o = self.ops
@@ -141,17 +173,23 @@ class _Conv:
         assert C == self.cin
         OH, OW = (H + 2 * self.pad - self.k) // self.stride + 1, (W + 2 * self.pad - self.k) // self.stride + 1
         P = B * OH * OW
-        cols = torch.empty(P, self.K, dtype=torch.bfloat16, device=o.dev)
-        o.ck(o.lib.s3od_train_im2col(x.data_ptr(), cols.data_ptr(), B, H, W, C, self.k, self.stride, self.pad, o.st()), "s3od_train_im2col")
+        x = x.contiguous()
+        if self.fast_fwd or (self.rows64 and W % 128 == 0):
+            yb = o.conv3x3(o.cast(x), self.wf[:self.cout], self.bias, B, H, W, self.cin, self.cout)
+            self.ctx = (None, x, (B, H, W), (OH, OW))                        # the wgrad builds its columns when it needs them
+            return o.to_f32(yb)
+        cols = self._cols(x, B, H, W, P)
         out = o.gemm(cols, self.wf, P, self.Np, self.K)
         y = o.copy_cols(out, P, self.cout, self.Np, self.bias)
-        self.ctx = (cols, (B, H, W), (OH, OW))
+        self.ctx = (cols, None, (B, H, W), (OH, OW))
         return y.view(B, OH, OW, self.cout)
 
     def backward(self, dy: torch.Tensor, emit: Emit, need_dx: bool = True) -> Optional[torch.Tensor]:
         o = self.ops
-        cols, (B, H, W), (OH, OW) = self.ctx
+        cols, x_saved, (B, H, W), (OH, OW) = self.ctx
         P = B * OH * OW
+        if cols is None:
+            cols = self._cols(x_saved, B, H, W, P)
         dy = dy.reshape(P, self.cout).contiguous()
         if self.bias is not None:
             emit(self.name + ".bias", o.colsum(dy))
@@ -162,6 +200,9 @@ class _Conv:
         emit(self.name + ".weight", dW.view(self.cout, self.k, self.k, self.cin).permute(0, 3, 1, 2).contiguous())
         if not need_dx:
             return None
+        if self.fast_dgrad or (self.rows64 and W % 128 == 0):
+            dxb = o.conv3x3(o.cast(dy).view(B, H, W, self.cout), self.wd, None, B, H, W, self.cout, self.cin)
+            return o.to_f32(dxb)
         dyb = torch.zeros(P, self.Kc, dtype=torch.bfloat16, device=o.dev)
         dyb[:, :self.cout] = o.cast(dy)                                                  # zero padded to the 64-granular contraction
         dcols = o.gemm(dyb, self.wt, P, self.Kp, self.Kc)
