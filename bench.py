@@ -679,6 +679,7 @@ def main():
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the short cfg3 (2048^2 sources) / cfg5 (ViT-L) legs")
     ap.add_argument("--no-gpu-baseline", dest="gpu_baseline", action="store_false", help="skip the PyTorch-on-this-GPU baseline leg")
     ap.add_argument("--gpu-baseline-batch", type=int, default=8)
+    ap.add_argument("--config", default="infer", choices=["infer", "train"], help="train = the optimisation step of BASELINE.json configs[3] as the headline")
     ap.add_argument("--no-numa-bind", dest="numa_bind", action="store_false", help="do not pin the rank to the GPU's local CPU cores")
     ap.add_argument("--model", default="dinob", choices=["dinob", "dinol"], help="dinol = ViT-L backbone, one mask (BASELINE.json configs[4])")
     ap.add_argument("--dump-profile", default=None, help="write the per-kernel CUDA-event table (label, launches, images, ms) here")
@@ -696,6 +697,23 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     rank, local_rank, world = sharder.init_from_env("nccl")
+    if args.config == "train":
+        # BASELINE.json configs[3] as the headline of this invocation: the whole optimisation step, weak scaling
+        dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(dev)
+        ent = training_slice_leg(rank, world, dev)
+        if rank == 0:
+            tsr = ent.get("train_step") or {}
+            print(json.dumps({"metric": "images/sec (dinob training step: forward + loss + backward + gradient all-reduce + AdamW)",
+                              "value": tsr.get("images_per_s"), "unit": UNIT, "n_gpus": world, "steps": 2, "warmup": 1,
+                              "ms_per_step": tsr.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "bf16 operands, fp32 accumulation / master weights", "data": "synthetic",
+                              "config": {"workload": "dinob training step, 1 synthetic 1024x1024 image per GPU, image_size 1024, seeded random weights",
+                                         "batch_per_gpu": 1, "image_size": 1024}, "detail": ent}), flush=True)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
     # N > 1: host staging / pinned result buffers stay on the GPU's socket (at N = 1 the CPU-baseline leg wants every core)
     numa_bound = sharder.bind_to_gpu_numa(local_rank) if (args.numa_bind and world > 1) else False
     line = run_b200(args, rank, local_rank, world)
