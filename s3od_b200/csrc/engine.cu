@@ -268,7 +268,11 @@ T* aptr(s3od_ctx* c, const std::string& name) {
 using bf16 = __nv_bfloat16;
 
 // ---- plan builders -----------------------------------------------------------------------------------------------
-template <int BN, class Epi, int EW>
+// kSmallN > 0: a second, one-CTA configuration with 128 x kSmallN tiles for the same GEMM, chosen at launch time when it fills the
+// SMs better than the 256 x 256 CTA-pair tiles.  With M = 4101 rows (one image) and N = 768 the pair kernel has 17 x 3 = 51 work items
+// for 74 SM pairs; 128 x 192 tiles give 33 x 4 = 132 tiles for 148 SMs in ONE round of 3/4-size tiles.  Per-element arithmetic does
+// not depend on the tile shape (same k-block order), so results stay bit-identical across batch sizes.
+template <int BN, class Epi, int EW, int kSmallN = 0>
 bool add_linear(s3od_ctx* c, const std::string& label, const void* a, uint64_t a_rows_total, int rows_per_image, int Kdim,
                 const void* bw, int N, typename Epi::Params ep, bool a_is_batch_window = false, bool per_image_tiles = false,
                 std::function<void(typename Epi::Params&, int, int, float*, float*)> patch = nullptr) {
@@ -284,6 +288,15 @@ bool add_linear(s3od_ctx* c, const std::string& label, const void* a, uint64_t a
   p.b_row_offset = 0;
   p.a_row_offset = 0;
   p.epi = ep;
+  GemmParams<Epi> ps = p;                           // the small-tile configuration (only used when kSmallN > 0)
+  bool have_small = false;
+  if constexpr (kSmallN > 0) {
+    if (N % kSmallN == 0 && !per_image_tiles) {
+      if (!tmap_matrix(&ps.tma_b, bw, N, Kdim, kSmallN)) return false;
+      ps.n_tiles = N / kSmallN;
+      have_small = true;
+    }
+  }
   const int sms = c->num_sms;
   c->plan.emplace_back(label, [=](int nb, int b0, float* mo, float* io, cudaStream_t st) mutable -> cudaError_t {
     GemmParams<Epi> q = p;
@@ -296,6 +309,21 @@ bool add_linear(s3od_ctx* c, const std::string& label, const void* a, uint64_t a
     }
     q.a_row_offset = a_is_batch_window ? b0 * rows_per_image : 0;
     if (patch) patch(q.epi, nb, b0, mo, io);
+    if constexpr (kSmallN > 0) {
+      if (have_small) {
+        // rounds x relative tile size of the two configurations
+        const int items_pair = ((q.m_tiles + 1) / 2) * q.n_tiles, pairs = sms / 2;
+        const int tiles_small = q.m_tiles * ps.n_tiles;
+        const double t_pair = static_cast<double>((items_pair + pairs - 1) / pairs);
+        // a pair item keeps each of its two SMs busy with 128 x BN of output; a small tile is 128 x kSmallN on one SM
+        const double t_small = static_cast<double>((tiles_small + sms - 1) / sms) * (static_cast<double>(kSmallN) / BN);
+        if (t_small < 0.9 * t_pair) {
+          GemmParams<Epi> r = ps;
+          r.M = q.M; r.m_tiles = q.m_tiles; r.a_row_offset = q.a_row_offset; r.epi = q.epi;
+          return launch_gemm<kSmallN, A_LINEAR, Epi, EW>(r, sms, st);
+        }
+      }
+    }
     return launch_gemm<BN, A_LINEAR, Epi, EW>(q, sms, st);
   });
   return true;
@@ -507,8 +535,8 @@ bool build_plan(s3od_ctx* c) {
       EpiResidual::Params e{dx, wptr<float>(c, pre + "o.b"), wptr<float>(c, pre + "ls1"), ntok, D};
       // flat M tiling (S3OD_FLAT_TILES): dx is a plain [nb * ntok, D] matrix, so the tiles may straddle images - per-image
       // tiling spends one tile in 33 on the 5-row remainder of every image (ntok = 4101 = 32 * 128 + 5)
-      if (!add_linear<256, EpiResidual, 8>(c, pre + "o_proj", actx, MT, ntok, D, wptr<bf16>(c, pre + "o.w"), D, e, false, !kFlatTiles,
-                                           flat_residual)) return false;
+      if (!add_linear<256, EpiResidual, 8, 192>(c, pre + "o_proj", actx, MT, ntok, D, wptr<bf16>(c, pre + "o.w"), D, e, false, !kFlatTiles,
+                                                flat_residual)) return false;
     }
     c->plan.emplace_back(pre + "ln2", [=](int nb, int, float*, float*, cudaStream_t st) {
       return launch_layernorm(x, dx, ln2w, ln2b, xn, nullptr, nb * ntok, ntok, D, 1e-5f, st);
@@ -520,8 +548,8 @@ bool build_plan(s3od_ctx* c) {
     }
     {
       EpiResidual::Params e{dx, wptr<float>(c, pre + "down.b"), wptr<float>(c, pre + "ls2"), ntok, D};
-      if (!add_linear<256, EpiResidual, 8>(c, pre + "down_proj", hmid, MT, ntok, I, wptr<bf16>(c, pre + "down.w"), D, e, false, !kFlatTiles,
-                                           flat_residual)) return false;
+      if (!add_linear<256, EpiResidual, 8, 192>(c, pre + "down_proj", hmid, MT, ntok, I, wptr<bf16>(c, pre + "down.w"), D, e, false, !kFlatTiles,
+                                                flat_residual)) return false;
     }
   }
 
