@@ -221,6 +221,21 @@ int s3od_train_qkv_split_rope(const float* d_qkv, const float* d_cos, const floa
 int s3od_train_qkv_merge_rope_backward(const float* d_dqT, const float* d_dkT, const float* d_dvT, const float* d_cos, const float* d_sin, void* d_dqkv,
                                        float* d_dqkv_f32, int batch, int ntok, int ntok_padded, int heads, int n_prefix, float qgrad_scale,
                                        float kgrad_scale, s3od_stream stream);
+/* the same merge for ROW-major gradients dq, dk, dv fp32 [B*heads, ntok_padded, 64] (what s3od_train_attention_backward writes) */
+int s3od_train_qkv_merge_rope_backward_rows(const float* d_dq, const float* d_dk, const float* d_dv, const float* d_cos, const float* d_sin,
+                                            void* d_dqkv, float* d_dqkv_f32, int batch, int ntok, int ntok_padded, int heads, int n_prefix,
+                                            float qgrad_scale, float kgrad_scale, s3od_stream stream);
+/* Fused attention of the training step (csrc/attention.cuh + attention_bwd.cuh; autograd of DINOv3ViTAttention.forward HF:316-329).
+ * q (pre-scaled by log2e/8), k, v, dout: bf16 [B*heads, ntok_padded, 64], rows >= ntok zero; ntok_padded % 384 == 0.
+ * forward : out bf16 [B*ntok, heads*64]; lse fp32 [B*heads, ntok_padded] receives the base-2 log-sum-exp of every score row
+ *           (the caller fills it with +inf first: rows >= ntok must read +inf in the backward).
+ * backward: delta fp32 [B*heads, ntok_padded] = rowsum(dout * out) (s3od_train_rowdot64); writes fp32 [B*heads, ntok_padded, 64]
+ *           dq = dA K, dk = dA^T q, dv = P^T dout with dA = P * (dout v^T - delta): the gradients w.r.t. the PRE-SCALED q and
+ *           base-2 scores' natural-log counterpart, i.e. multiply dq by 1/8 and dk by 1/log2e (s3od_train_qkv_merge_rope_backward_rows does). */
+int s3od_train_attention_forward(const void* d_q, const void* d_k, const void* d_v, void* d_out, float* d_lse, int batch, int heads, int ntok,
+                                 int ntok_padded, s3od_stream stream);
+int s3od_train_attention_backward(const void* d_q, const void* d_k, const void* d_v, const void* d_dout, const float* d_lse, const float* d_delta,
+                                  float* d_dq, float* d_dk, float* d_dv, int batch, int heads, int ntok_padded, s3od_stream stream);
 int s3od_train_split_heads(const void* d_in, int in_is_f32, void* d_out, int batch, int ntok, int ntok_padded, int heads, s3od_stream stream);
 int s3od_train_rowdot64(const void* d_a, const void* d_b, float* d_out, long long rows, s3od_stream stream);
 int s3od_train_softmax2_rows(const float* d_scores, void* d_probs, int ntok, int ntok_padded, s3od_stream stream);

@@ -296,7 +296,7 @@ S3OD_DEVICE float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-template <int kStreams, int kStages>
+template <int kStreams, int kStages, bool kLse = false>      // kLse: also write the log-sum-exp of every score row (training forward)
 __global__ void __launch_bounds__(kStreams == 2 ? kAttnThreads : kAttnThreads1, 1)
     attention_kernel_t(const __grid_constant__ AttnParams p) {
   constexpr int kAttnStages = kStages;               // shadows the namespace constant: ring depth of THIS instantiation
@@ -563,8 +563,14 @@ __global__ void __launch_bounds__(kStreams == 2 ? kAttnThreads : kAttnThreads1, 
     // ---- epilogue: O / l -> bf16 [B*ntok, heads*64]
     mbar_wait(&p_empty[(T - 1) & 1], ((T - 1) >> 1) & 1);
     tc_fence_after();
-    const float inv_a = 1.0f / (quad_sum(la) * kTruncGain), inv_b = 1.0f / (quad_sum(lb) * kTruncGain);
+    const float sum_a = quad_sum(la), sum_b = quad_sum(lb);
+    const float inv_a = 1.0f / (sum_a * kTruncGain), inv_b = 1.0f / (sum_b * kTruncGain);
     const int ta = (q_tile0 + sidx) * kAttnTile + row_a, tb = ta + 8;
+    if (kLse && (lane & 3) == 0) {                    // training: what the fused backward (attention_bwd.cuh) recomputes P from
+      float* l = p.lse + static_cast<size_t>(bh) * p.lse_stride;
+      if (ta < p.ntok) l[ta] = ma + log2f(sum_a);
+      if (tb < p.ntok) l[tb] = mb + log2f(sum_b);
+    }
     const int b = bh / p.heads, head = bh % p.heads;
     __nv_bfloat16* base = p.out + static_cast<size_t>(b) * p.ntok * (p.heads * 64) + head * 64 + q2;
     uint32_t* dst_a = reinterpret_cast<uint32_t*>(base + static_cast<size_t>(ta) * (p.heads * 64));

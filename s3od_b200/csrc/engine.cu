@@ -1139,6 +1139,53 @@ int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d
   return S3OD_OK;
 }
 
+int s3od_train_attention_forward(const void* d_q, const void* d_k, const void* d_v, void* d_out, float* d_lse, int batch, int heads, int ntok,
+                                 int ntok_padded, s3od_stream stream) {
+  if (d_q == nullptr || d_k == nullptr || d_v == nullptr || d_out == nullptr || d_lse == nullptr || batch < 1 || heads < 1 || ntok < 1 ||
+      ntok_padded < ntok || ntok_padded % 384 != 0)
+    return fail(S3OD_ERR_ARG, "bad argument to s3od_train_attention_forward (ntok_padded must be a multiple of 384)");
+  AttnParams ap{};
+  const uint64_t BH = static_cast<uint64_t>(batch) * heads;
+  const uint64_t dq[3] = {64, (uint64_t)ntok, BH};                 // rows >= ntok of a box are zero-filled by the TMA unit
+  const uint64_t sq[2] = {128, (uint64_t)ntok_padded * 128};
+  const uint32_t bq[3] = {64, kAttnTile, 1}, bkv[3] = {64, kAttnKvTile, 1};
+  if (!make_tmap(&ap.tma_q, d_q, 3, dq, sq, bq)) return S3OD_ERR_CUDA;
+  if (!make_tmap(&ap.tma_k, d_k, 3, dq, sq, bkv)) return S3OD_ERR_CUDA;
+  if (!make_tmap(&ap.tma_v, d_v, 3, dq, sq, bkv)) return S3OD_ERR_CUDA;
+  ap.out = static_cast<bf16*>(d_out);
+  ap.ntok = ntok; ap.heads = heads; ap.kv_tiles = (ntok + kAttnKvTile - 1) / kAttnKvTile;
+  ap.lse = d_lse; ap.lse_stride = ntok_padded;
+  CK(launch_attention(ap, (ntok + kAttnTile - 1) / kAttnTile, static_cast<int>(BH), static_cast<cudaStream_t>(stream)));
+  return S3OD_OK;
+}
+
+int s3od_train_attention_backward(const void* d_q, const void* d_k, const void* d_v, const void* d_dout, const float* d_lse, const float* d_delta,
+                                  float* d_dq, float* d_dk, float* d_dv, int batch, int heads, int ntok_padded, s3od_stream stream) {
+  if (d_q == nullptr || d_k == nullptr || d_v == nullptr || d_dout == nullptr || d_lse == nullptr || d_delta == nullptr || d_dq == nullptr ||
+      d_dk == nullptr || d_dv == nullptr || batch < 1 || heads < 1 || ntok_padded < 384 || ntok_padded % 384 != 0)
+    return fail(S3OD_ERR_ARG, "bad argument to s3od_train_attention_backward (ntok_padded must be a multiple of 384)");
+  const uint64_t BH = static_cast<uint64_t>(batch) * heads;
+  const uint64_t dq[3] = {64, (uint64_t)ntok_padded, BH};
+  const uint64_t sq[2] = {128, (uint64_t)ntok_padded * 128};
+  const uint32_t b128[3] = {64, kAttnTile, 1}, b96[3] = {64, kAttnKvTile, 1};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AttnBwdParams p{};
+  p.lse = d_lse; p.delta = d_delta; p.npad = ntok_padded; p.scale_ds = 1.0f;
+  // dQ: the CTA owns 128 query rows and walks the keys
+  if (!make_tmap(&p.tma_x, d_q, 3, dq, sq, b128) || !make_tmap(&p.tma_y, d_dout, 3, dq, sq, b128) || !make_tmap(&p.tma_u, d_k, 3, dq, sq, b96) ||
+      !make_tmap(&p.tma_w, d_v, 3, dq, sq, b96))
+    return S3OD_ERR_CUDA;
+  p.out_ds = d_dq; p.out_p = nullptr;
+  CK(launch_attention_backward(p, false, static_cast<int>(BH), st));
+  // dK, dV: the CTA owns 128 key rows and walks the queries (the transposed problem)
+  if (!make_tmap(&p.tma_x, d_k, 3, dq, sq, b128) || !make_tmap(&p.tma_y, d_v, 3, dq, sq, b128) || !make_tmap(&p.tma_u, d_q, 3, dq, sq, b96) ||
+      !make_tmap(&p.tma_w, d_dout, 3, dq, sq, b96))
+    return S3OD_ERR_CUDA;
+  p.out_ds = d_dk; p.out_p = d_dv;
+  CK(launch_attention_backward(p, true, static_cast<int>(BH), st));
+  return S3OD_OK;
+}
+
 int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin, int cout,
                     int relu, s3od_stream stream) {
   if (cin % 64 != 0 || cout % 256 != 0) return fail(S3OD_ERR_ARG, "s3od_op_conv3x3 needs cin % 64 == 0 and cout % 256 == 0");

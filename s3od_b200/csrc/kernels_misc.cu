@@ -1,6 +1,7 @@
 // Attention and bandwidth-bound kernel launchers.
 #include "attention.cuh"
 #include "attention_persist.cuh"
+#include "attention_bwd.cuh"
 #include "elementwise.cuh"
 #include "visualize.cuh"
 #include "metrics.cuh"
@@ -34,6 +35,7 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
   q.bh_total = bh;
   static SmemOptIn configured;
 #if S3OD_ATTN_PERSIST
+  if (q.lse != nullptr) return cudaErrorNotSupported;      // the persistent form has no log-sum-exp output
   {
     // persistent form: one CTA per SM walks the item list (attention_persist.cuh)
     if (cudaError_t e = configured.ensure(attention_persist_kernel, kAttnPSmemBytes); e != cudaSuccess) return e;
@@ -44,14 +46,34 @@ cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStrea
     return launch_pdl(attention_persist_kernel, dim3(items < sms ? items : sms), dim3(kAttnThreads), kAttnPSmemBytes, stream, q);
   }
 #elif S3OD_ATTN_ONE_STREAM
+  if (q.lse != nullptr) return cudaErrorNotSupported;
   auto kern = attention_kernel_t<1, kAttnStages1>;
   if (cudaError_t e = configured.ensure(kern, kAttnSmemBytes1); e != cudaSuccess) return e;
   return launch_pdl(kern, dim3(q_tiles * bh), dim3(kAttnThreads1), kAttnSmemBytes1, stream, q);
 #else
+  if (q.lse != nullptr) {                          // training forward: the same kernel with the log-sum-exp output compiled in
+    static SmemOptIn configured_lse;
+    auto kern_lse = attention_kernel_t<2, kAttnStages, true>;
+    if (cudaError_t e = configured_lse.ensure(kern_lse, kAttnSmemBytes); e != cudaSuccess) return e;
+    return launch_pdl(kern_lse, dim3(((q_tiles + 1) / 2) * bh), dim3(kAttnThreads), kAttnSmemBytes, stream, q);
+  }
   auto kern = attention_kernel_t<2, kAttnStages>;
   if (cudaError_t e = configured.ensure(kern, kAttnSmemBytes); e != cudaSuccess) return e;
   return launch_pdl(kern, dim3(((q_tiles + 1) / 2) * bh), dim3(kAttnThreads), kAttnSmemBytes, stream, q);   // two query tiles per CTA, 1-D grid
 #endif
+}
+
+cudaError_t launch_attention_backward(const AttnBwdParams& p, bool col_stats, int bh, cudaStream_t stream) {
+  static SmemOptIn cfg_rows, cfg_cols;
+  const dim3 grid((p.npad / kAttnTile) * bh);
+  if (col_stats) {
+    if (cudaError_t e = cfg_cols.ensure(attention_bwd_kernel<true>, kAttnBwdSmemBytes); e != cudaSuccess) return e;
+    attention_bwd_kernel<true><<<grid, kAttnBwdThreads, kAttnBwdSmemBytes, stream>>>(p);
+  } else {
+    if (cudaError_t e = cfg_rows.ensure(attention_bwd_kernel<false>, kAttnBwdSmemBytes); e != cudaSuccess) return e;
+    attention_bwd_kernel<false><<<grid, kAttnBwdThreads, kAttnBwdSmemBytes, stream>>>(p);
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,

@@ -254,6 +254,18 @@ int s3od_train_qkv_merge_rope_backward(const float* d_dqT, const float* d_dkT, c
   S3OD_TRAIN_DONE("qkv_merge_rope_bwd_kernel");
 }
 
+int s3od_train_qkv_merge_rope_backward_rows(const float* d_dq, const float* d_dk, const float* d_dv, const float* d_cos, const float* d_sin,
+                                            void* d_dqkv, float* d_dqkv_f32, int batch, int ntok, int ntok_padded, int heads, int n_prefix,
+                                            float qgrad_scale, float kgrad_scale, s3od_stream stream) {
+  if (d_dq == nullptr || d_dk == nullptr || d_dv == nullptr || d_dqkv == nullptr || d_dqkv_f32 == nullptr || ntok_padded < ntok)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_qkv_merge_rope_backward_rows");
+  const long long n = static_cast<long long>(batch) * heads * ntok * 32;
+  qkv_merge_rope_bwd_rows_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dq, d_dk, d_dv, d_cos, d_sin, static_cast<bf16_t*>(d_dqkv),
+                                                                                             d_dqkv_f32, batch, ntok, ntok_padded, heads, n_prefix,
+                                                                                             qgrad_scale, kgrad_scale);
+  S3OD_TRAIN_DONE("qkv_merge_rope_bwd_rows_kernel");
+}
+
 int s3od_train_split_heads(const void* d_in, int in_is_f32, void* d_out, int batch, int ntok, int ntok_padded, int heads, s3od_stream stream) {
   if (d_in == nullptr || d_out == nullptr || ntok_padded < ntok) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_split_heads");
   const long long n = static_cast<long long>(batch) * heads * ntok_padded * 64;

@@ -254,6 +254,40 @@ __global__ void __launch_bounds__(256) qkv_merge_rope_bwd_kernel(const float* __
   }
 }
 
+// the same merge for row-major gradients dq, dk, dv fp32 [B, H, Npad, 64] (fused attention backward): d fastest, so both sides coalesce
+__global__ void __launch_bounds__(256) qkv_merge_rope_bwd_rows_kernel(const float* __restrict__ dq, const float* __restrict__ dk, const float* __restrict__ dv,
+                                                                      const float* __restrict__ cosb, const float* __restrict__ sinb, bf16_t* __restrict__ dqkv,
+                                                                      float* __restrict__ dqkv_f32, int B, int N, int Npad, int H, int n_prefix,
+                                                                      float qgrad_scale, float kgrad_scale) {
+  const int D = H * 64;
+  const long long total = static_cast<long long>(B) * N * H * 32;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int d = static_cast<int>(i % 32);
+    long long r = i / 32;
+    const int h = static_cast<int>(r % H);
+    r /= H;
+    const int t = static_cast<int>(r % N), b = static_cast<int>(r / N);
+    const long long base = ((static_cast<long long>(b) * H + h) * Npad + t) * 64 + d;
+    float q0 = dq[base] * qgrad_scale, q1 = dq[base + 32] * qgrad_scale;
+    float k0 = dk[base] * kgrad_scale, k1 = dk[base + 32] * kgrad_scale;
+    const float v0 = dv[base], v1 = dv[base + 32];
+    if (t >= n_prefix) {                                  // transpose of the rotation, as in qkv_merge_rope_bwd_kernel
+      const float c = cosb[(t - n_prefix) * 32 + d], s = sinb[(t - n_prefix) * 32 + d];
+      const float a0 = q0 * c + q1 * s, a1 = q1 * c - q0 * s;
+      const float b0 = k0 * c + k1 * s, b1 = k1 * c - k0 * s;
+      q0 = a0; q1 = a1; k0 = b0; k1 = b1;
+    }
+    const long long o = (static_cast<long long>(b) * N + t) * 3 * D + h * 64 + d;
+    const float vals[6] = {q0, q1, k0, k1, v0, v1};
+    const long long offs[6] = {o, o + 32, o + D, o + D + 32, o + 2 * D, o + 2 * D + 32};
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      dqkv[offs[j]] = __float2bfloat16_rn(vals[j]);
+      dqkv_f32[offs[j]] = vals[j];
+    }
+  }
+}
+
 // token-major [B*N, H*64] (fp32 or bf16) -> head-major bf16 [B, H, Npad, 64], rows >= N zero
 template <class TIn>
 __global__ void __launch_bounds__(256) split_heads_kernel(const TIn* __restrict__ in, bf16_t* __restrict__ out, int B, int N, int Npad, int H) {

@@ -41,6 +41,22 @@ struct AttnParams {
   int bh_total;                // images * heads of this launch
   int trace_bh;         // debug: which blockIdx.y is traced
   long long* trace;     // debug: per-tile clock64() stamps of CTA (5, 0) (8 slots per tile: 0-4 softmax warp, 5-7 MMA thread)
+  float* lse;           // training only (else nullptr): base-2 log-sum-exp of every score row, [B*H, lse_stride]
+  int lse_stride;
+};
+
+// fused attention backward (attention_bwd.cuh): one launch with row statistics (dQ), one with column statistics (dK, dV)
+struct AttnBwdParams {
+  CUtensorMap tma_x;      // stationary operand of the score MMA, box (64, 128, 1):    dQ: Q'    dK/dV: K
+  CUtensorMap tma_y;      // stationary operand of the dP MMA,    box (64, 128, 1):    dQ: dO    dK/dV: V
+  CUtensorMap tma_u;      // streamed, box (64, 96, 1):                                 dQ: K     dK/dV: Q'
+  CUtensorMap tma_w;      // streamed, box (64, 96, 1):                                 dQ: V     dK/dV: dO
+  const float* lse;       // [B*H, npad] base-2 log-sum-exp of the score rows, +inf behind the sequence
+  const float* delta;     // [B*H, npad] rowsum(dO * O)
+  float* out_ds;          // fp32 [B*H, npad, 64]: dQ (row statistics) or dK (column statistics), times scale_ds
+  float* out_p;           // fp32 [B*H, npad, 64]: dV (column statistics only)
+  int npad;               // padded sequence length (multiple of 384)
+  float scale_ds;
 };
 
 }  // namespace s3od

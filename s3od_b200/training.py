@@ -451,6 +451,9 @@ def _bind_block(lib):
         lib.s3od_train_gelu_backward.argtypes = [vp, vp, vp, vp, ll, vp]
         lib.s3od_train_qkv_split_rope.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, vp]
         lib.s3od_train_qkv_merge_rope_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, cf, vp]
+        lib.s3od_train_qkv_merge_rope_backward_rows.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, cf, cf, vp]
+        lib.s3od_train_attention_forward.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
+        lib.s3od_train_attention_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]
         lib.s3od_train_split_heads.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp]
         lib.s3od_train_rowdot64.argtypes = [vp, vp, vp, ll, vp]
         lib.s3od_train_softmax2_rows.argtypes = [vp, vp, ci, ci, vp]
@@ -461,11 +464,12 @@ def _bind_block(lib):
 
 class EncoderBlockStep:
     """Forward (with saved activations) and backward of ONE encoder block - DINOv3ViTLayer.forward, HF modeling_dinov3_vit.py:424-450
-    with the attention of HF:294-334 - on the CUDA library: every contraction (the four linears and their dgrad / wgrad, Q K^T,
-    dO V^T, dS K, dS^T Q, P^T dO) is a tcgen05 GEMM (`s3od_op_gemm_f32`: fp32 C = bf16 A x bf16 B^T), the forward attention is the
-    fused flash kernel (`s3od_op_attention`), everything between them is a kernel of csrc/train_block.cuh.  dgrad reads the
-    transposed weights, wgrad contracts over the tokens (dY^T and X^T, zero-padded to a multiple of 64 rows), the attention
-    backward re-materialises S and P per (image, head).  A first, correctness-first form: unfused, O(N^2) scratch per head.
+    with the attention of HF:294-334 - on the CUDA library: the four linears and their dgrad / wgrad are tcgen05 GEMMs
+    (`s3od_op_gemm_f32`: fp32 C = bf16 A x bf16 B^T; dgrad reads the transposed weights, wgrad contracts over the tokens with dY^T
+    and X^T zero-padded to a multiple of 64 rows), the attention is the fused flash kernel forward (`s3od_train_attention_forward`,
+    which also writes the log-sum-exp of every score row) and the fused flash backward (`s3od_train_attention_backward`,
+    csrc/attention_bwd.cuh: P and dA recomputed tile by tile, no N x N scratch), everything between them is a kernel of
+    csrc/train_block.cuh.
 
     Precision: bf16 operands / fp32 accumulation in every GEMM (the reference trains with float32_matmul_precision "medium",
     train.py:74), fp32 LayerNorm / GELU / softmax / reductions; the gradients that feed a GEMM are rounded to bf16 once."""
@@ -479,7 +483,7 @@ class EncoderBlockStep:
         self.D, self.H, self.I = arch.hidden, arch.heads, arch.mlp
         g = image_size // arch.patch
         self.N = g * g + arch.n_prefix
-        self.Npad = (self.N + 127) // 128 * 128
+        self.Npad = (self.N + 383) // 384 * 384          # a whole number of 128-row and of 96-row tiles (fused attention backward)
         f = lambda t: t.detach().to(self.dev, torch.float32).contiguous()           # noqa: E731
         a = layer_prefix + "attention."
         D = self.D
@@ -583,10 +587,11 @@ class EncoderBlockStep:
         with torch.cuda.device(self.dev):
             xn1 = self._layernorm(x0, w["ln1.w"], w["ln1.b"])
             qkv = self._add_bias(self._gemm(xn1, wb["qkv.w"], M, 3 * D, D), w["qkv.b"])
-            qu, ku, vu = self._split_rope(qkv, B, N)                       # dense [B, H, N, 64] for the fused attention kernel
-            q, k, v = self._split_rope(qkv, B, self.Npad)                   # zero-padded rows for the backward GEMMs
+            q, k, v = self._split_rope(qkv, B, self.Npad)                   # [B, H, Npad, 64] bf16, zero rows behind the sequence
             ctx = torch.empty(M, D, dtype=torch.bfloat16, device=self.dev)
-            self._ck(self.lib.s3od_op_attention(qu.data_ptr(), ku.data_ptr(), vu.data_ptr(), ctx.data_ptr(), B, H, N, self._st()), "s3od_op_attention")
+            lse = torch.full((B * H, self.Npad), float("inf"), dtype=torch.float32, device=self.dev)
+            self._ck(self.lib.s3od_train_attention_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, H, N, self.Npad,
+                                                           self._st()), "s3od_train_attention_forward")
             o = self._add_bias(self._gemm(ctx, wb["o.w"], M, D, D), w["o.b"])
             x1 = self._residual(x0, o, w["ls1"])
             xn2 = self._layernorm(x1, w["ln2.w"], w["ln2.b"])
@@ -595,7 +600,7 @@ class EncoderBlockStep:
             self._ck(self.lib.s3od_train_gelu_forward(hpre.data_ptr(), hmid.data_ptr(), hpre.numel(), self._st()), "s3od_train_gelu_forward")
             y = self._add_bias(self._gemm(hmid, wb["down.w"], M, D, I), w["down.b"])
             x2 = self._residual(x1, y, w["ls2"])
-        self.saved = dict(B=B, x0=x0, xn1=xn1, q=q, k=k, v=v, ctx=ctx, o=o, x1=x1, xn2=xn2, hpre=hpre, hmid=hmid, y=y)
+        self.saved = dict(B=B, x0=x0, xn1=xn1, q=q, k=k, v=v, lse=lse, ctx=ctx, o=o, x1=x1, xn2=xn2, hpre=hpre, hmid=hmid, y=y)
         return x2.view(B, N, D)
 
     # ---- backward -----------------------------------------------------------------------------------------------
@@ -636,31 +641,18 @@ class EncoderBlockStep:
             BH = B * H
             Dvec = torch.empty(BH * Npad, dtype=torch.float32, device=self.dev)
             self._ck(self.lib.s3od_train_rowdot64(dO.data_ptr(), Oh.data_ptr(), Dvec.data_ptr(), BH * Npad, st), "s3od_train_rowdot64")
-            kT = self._transpose(s["k"], BH, Npad, 64, Npad)                                # [BH][64][Npad]
-            qT = self._transpose(s["q"], BH, Npad, 64, Npad)
-            dOT = self._transpose(dO, BH, Npad, 64, Npad)
-            dqT = torch.empty(BH, 64, Npad, dtype=torch.float32, device=self.dev)
-            dkT, dvT = torch.empty_like(dqT), torch.empty_like(dqT)
-            q, k, v = s["q"].view(BH, Npad, 64), s["k"].view(BH, Npad, 64), s["v"].view(BH, Npad, 64)
-            dOv = dO.view(BH, Npad, 64)
-            P = torch.empty(Npad, Npad, dtype=torch.bfloat16, device=self.dev)
-            dS = torch.empty_like(P)
-            for bh in range(BH):
-                S = self._gemm(q[bh], k[bh], Npad, Npad, 64)                                # base-2 scores (q carries log2e / 8)
-                self._ck(self.lib.s3od_train_softmax2_rows(S.data_ptr(), P.data_ptr(), N, Npad, st), "s3od_train_softmax2_rows")
-                dP = self._gemm(dOv[bh], v[bh], Npad, Npad, 64)
-                self._ck(self.lib.s3od_train_softmax_backward(P.data_ptr(), dP.data_ptr(), Dvec[bh * Npad:].data_ptr(), dS.data_ptr(), N, Npad, st),
-                         "s3od_train_softmax_backward")
-                dST = self._transpose(dS, 1, Npad, Npad, Npad).view(Npad, Npad)
-                PT = self._transpose(P, 1, Npad, Npad, Npad).view(Npad, Npad)
-                dqT[bh].copy_(self._gemm(kT[bh], dS, 64, Npad, Npad))                       # (dS K)^T
-                dkT[bh].copy_(self._gemm(qT[bh], dST, 64, Npad, Npad))                      # (dS^T Q')^T
-                dvT[bh].copy_(self._gemm(dOT[bh], PT, 64, Npad, Npad))                      # (P^T dO)^T
+            # fused flash backward (csrc/attention_bwd.cuh): P and dA are recomputed tile by tile from q, k, v and the forward's
+            # log-sum-exp; nothing of size N x N touches HBM
+            dq = torch.empty(BH, Npad, 64, dtype=torch.float32, device=self.dev)
+            dk, dv = torch.empty_like(dq), torch.empty_like(dq)
+            self._ck(self.lib.s3od_train_attention_backward(s["q"].data_ptr(), s["k"].data_ptr(), s["v"].data_ptr(), dO.data_ptr(), s["lse"].data_ptr(),
+                                                            Dvec.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, Npad, st),
+                     "s3od_train_attention_backward")
             dqkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=self.dev)
             dqkv32 = torch.empty(M, 3 * D, dtype=torch.float32, device=self.dev)
-            self._ck(self.lib.s3od_train_qkv_merge_rope_backward(dqT.data_ptr(), dkT.data_ptr(), dvT.data_ptr(), self.cos.data_ptr(), self.sin.data_ptr(),
-                                                                 dqkv.data_ptr(), dqkv32.data_ptr(), B, N, Npad, H, self.arch.n_prefix, 1.0 / 8.0,
-                                                                 1.0 / self.LOG2E, st), "s3od_train_qkv_merge_rope_backward")
+            self._ck(self.lib.s3od_train_qkv_merge_rope_backward_rows(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), self.cos.data_ptr(), self.sin.data_ptr(),
+                                                                      dqkv.data_ptr(), dqkv32.data_ptr(), B, N, Npad, H, self.arch.n_prefix, 1.0 / 8.0,
+                                                                      1.0 / self.LOG2E, st), "s3od_train_qkv_merge_rope_backward_rows")
             bq = self._colsum(dqkv32)
             grads["attention.q_proj.bias"], grads["attention.v_proj.bias"] = bq[:D].clone(), bq[2 * D:].clone()      # k_proj has no bias
             dxn1 = self._gemm(dqkv, wt["qkv.w"], M, D, 3 * D)

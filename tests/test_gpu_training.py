@@ -4,6 +4,7 @@
   * fused AdamW against the golden torch.optim.AdamW steps and against torch.optim.AdamW itself on the full 107.8 M layout.
 Tolerances: fp32 arithmetic with fast-math exp / log1p in the kernels - loss values 2e-6 relative, gradients 1e-5 relative to
 the largest gradient, AdamW 2e-7 absolute per step (one fp32 ulp of the update)."""
+import math
 import os
 
 import numpy as np
@@ -155,6 +156,58 @@ def test_fused_exchange_and_adamw_over_emulated_ranks(world):
         assert float((opt.param(0)[e0:e1] - rp_enc.detach()).abs().max()) <= 3e-7
     finally:
         opt.close()
+
+
+@pytest.mark.parametrize("B,H,N", [(1, 2, 261), (2, 3, 389), (1, 1, 4101), (1, 12, 1029)])
+def test_fused_attention_forward_backward_matches_autograd(capsys, B, H, N):
+    """csrc/attention.cuh (log-sum-exp output) + csrc/attention_bwd.cuh against torch.autograd of softmax(Q K^T) V in fp32 on the
+    SAME bf16 q, k, v, dO (HF:316-329).  Tolerance: P, dA and the operands are bf16 (2^-9 relative each) and the sums run over
+    up to 4101 keys, so every gradient is bounded relative to its own largest entry: 2e-2."""
+    import ctypes
+    from s3od_b200.training import _bind_block, _lib
+    lib = _bind_block(_lib())
+    npad = (N + 383) // 384 * 384
+    g = torch.Generator(device="cuda").manual_seed(N + H)
+    def padded(scale):
+        t = torch.zeros(B * H, npad, 64, dtype=torch.bfloat16, device="cuda")
+        t[:, :N] = (scale * torch.randn(B * H, N, 64, device="cuda", generator=g)).to(torch.bfloat16)
+        return t
+    q, k, v, do = padded(1.3), padded(1.0), padded(1.0), padded(1.0)          # q carries log2e / 8: base-2 scores of spread ~10
+    out = torch.empty(B * N, H * 64, dtype=torch.bfloat16, device="cuda")
+    lse = torch.full((B * H, npad), float("inf"), device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.s3od_train_attention_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, N, npad, st) == 0
+    # fp32 reference and its autograd
+    qf, kf, vf = (t[:, :N].float().requires_grad_(True) for t in (q, k, v))
+    s2 = qf @ kf.transpose(1, 2)                                                 # base-2 scores
+    ref_lse = torch.logsumexp(s2 * math.log(2.0), dim=-1) / math.log(2.0)
+    o_ref = torch.softmax(s2 * math.log(2.0), dim=-1) @ vf
+    (o_ref * do[:, :N].float()).sum().backward()
+    o_head = out.view(B, N, H, 64).permute(0, 2, 1, 3).reshape(B * H, N, 64).float()
+    assert float((o_head - o_ref.detach()).abs().max()) <= 2e-2 * float(o_ref.detach().abs().max())
+    assert float((lse[:, :N] - ref_lse.detach()).abs().max()) <= 1e-3 and bool(torch.isinf(lse[:, N:]).all())
+    # delta = rowsum(dO * O) from the kernel's own bf16 output, as the block step computes it
+    o_pad = torch.zeros_like(q)
+    o_pad[:, :N] = o_head.to(torch.bfloat16)
+    delta = torch.empty(B * H * npad, device="cuda")
+    assert lib.s3od_train_rowdot64(do.data_ptr(), o_pad.data_ptr(), delta.data_ptr(), B * H * npad, st) == 0
+    dq, dk, dv = (torch.full((B * H, npad, 64), float("nan"), device="cuda") for _ in range(3))
+    assert lib.s3od_train_attention_backward(q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                             dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, npad, st) == 0
+    torch.cuda.synchronize()
+    ln2 = math.log(2.0)                                                          # the kernel differentiates w.r.t. natural-log scores
+    errs = {}
+    for name, got, ref in (("dq", dq[:, :N] * ln2, qf.grad), ("dk", dk[:, :N] * ln2, kf.grad), ("dv", dv[:, :N], vf.grad)):
+        assert bool(torch.isfinite(got).all()), name
+        errs[name] = float((got - ref).abs().max()) / float(ref.abs().max())
+        assert errs[name] <= 2e-2, (name, errs[name])
+    assert float(dq[:, N:].abs().max()) == 0.0                                   # padding queries: P is exactly 0
+    with capsys.disabled():
+        print(f"\n[fused attention B={B} H={H} N={N}] max-abs error / largest entry: " + ", ".join(f"{k_} {e:.2e}" for k_, e in errs.items()))
+    # argument checks
+    assert lib.s3od_train_attention_backward(q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                             dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, H, npad - 128, st) != 0
+    assert lib.s3od_train_attention_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), None, B, H, N, npad, st) != 0
 
 
 @pytest.mark.parametrize("S,B,layer", [(224, 2, 3), (96, 3, 0), (1024, 1, 7)])
