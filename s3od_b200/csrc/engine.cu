@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -1113,6 +1114,45 @@ int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N,
     return S3OD_OK;
   }
   CK((launch_gemm<128, A_LINEAR, EpiStoreF32, 8>(p, sms, static_cast<cudaStream_t>(stream))));
+  return S3OD_OK;
+}
+
+// c[i] = sum over z of partial[z][i]   (the k-splits of s3od_op_gemm_f32_splitk; n a multiple of 4, 16-byte aligned)
+__global__ void __launch_bounds__(256) sum_k_splits_kernel(const float4* __restrict__ partial, int splits, long long n4, float4* __restrict__ c) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    float4 acc = partial[i];
+    for (int z = 1; z < splits; ++z) {
+      const float4 v = partial[z * n4 + i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    c[i] = acc;
+  }
+}
+
+int s3od_op_gemm_f32_splitk(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, int splits, float* d_workspace, s3od_stream stream) {
+  if (splits <= 1) return s3od_op_gemm_f32(d_a, d_b, d_c, M, N, K, stream);
+  if (!use_pair_kernel()) return fail(S3OD_ERR_ARG, "s3od_op_gemm_f32_splitk needs the CTA-pair GEMM (library built with S3OD_PAIR=0)");
+  if (N % 128 != 0 || M < 1 || splits > 64 || K % (64 * splits) != 0 || d_workspace == nullptr || (reinterpret_cast<uintptr_t>(d_c) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(d_workspace) & 15) != 0)
+    return fail(S3OD_ERR_ARG, "s3od_op_gemm_f32_splitk needs N % 128 == 0, K % (64 * splits) == 0, splits <= 64 and a 16-byte aligned workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GemmParams<EpiStoreF32> p{};
+  const bool wide = N % 256 == 0;
+  if (!tmap_matrix(&p.tma_a, d_a, M, K, kBM)) return S3OD_ERR_CUDA;
+  if (!tmap_matrix(&p.tma_b, d_b, N, K, wide ? b_box_rows<256>() : b_box_rows<128>())) return S3OD_ERR_CUDA;
+  p.M = M; p.m_tiles = (M + kBM - 1) / kBM; p.n_tiles = N / (wide ? 256 : 128);
+  p.num_k_blocks = K / 64 / splits;
+  p.k_splits = splits;
+  p.epi = EpiStoreF32::Params{d_workspace, N, static_cast<long long>(M) * N};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (wide) CK((launch_gemm<256, A_LINEAR, EpiStoreF32, 8>(p, sms, st)));
+  else CK((launch_gemm<128, A_LINEAR, EpiStoreF32, 8>(p, sms, st)));
+  const long long n4 = static_cast<long long>(M) * N / 4;
+  const int grid = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148LL * 8));
+  sum_k_splits_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_workspace), splits, n4, reinterpret_cast<float4*>(d_c));
+  CK(cudaGetLastError());
   return S3OD_OK;
 }
 

@@ -59,6 +59,8 @@ struct GemmParams {
   int tiles_per_image;
   ConvGeom geom;
   typename Epi::Params epi;
+  int k_splits;          // > 1 (CTA-pair kernel, A_LINEAR, EpiStoreF32 only): split z works on k-blocks [z, z + 1) * num_k_blocks and
+                         // hands z to the epilogue as RowInfo.b - wgrad GEMMs whose output has far fewer tiles than the GPU has SMs
 };
 
 template <int BN, int EPI_WARPS = 8>
@@ -617,10 +619,11 @@ struct EpiStoreF32 {
   struct Params {
     float* out;
     int ld;
+    long long split_stride = 0;      // elements between the partial outputs of two k-splits (GemmParams::k_splits)
   };
   template <int NCOLS>
   static S3OD_DEVICE void run(const Params& e, const RowInfo& ri, int n0, uint32_t taddr, const WarpStage& stg) {
-    float* dst = e.out + static_cast<size_t>(ri.gm) * e.ld + n0;
+    float* dst = e.out + static_cast<size_t>(ri.b) * e.split_stride + static_cast<size_t>(ri.gm) * e.ld + n0;
 #pragma unroll 1
     for (int c = 0; c < NCOLS; c += 32) {
       float v[32];

@@ -140,10 +140,11 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams<Epi> p) {
   pdl_wait();                                     // the previous kernel's outputs are complete and visible from here on
 
   const int m_pairs = (p.m_tiles + 1) / 2;
-  const int total_items = m_pairs * p.n_tiles;
+  const int items_per_split = m_pairs * p.n_tiles;
+  const int total_items = items_per_split * (p.k_splits > 1 ? p.k_splits : 1);      // split-major: item = (k-split, M-tile pair, N tile)
   const int first = blockIdx.x >> 1, step = gridDim.x >> 1;
   // own M tile of a work item (clamped for loads when the pair's second tile is past the end)
-  auto m_of = [&](int item) { return 2 * (item / p.n_tiles) + rank; };
+  auto m_of = [&](int item) { return 2 * ((item % items_per_split) / p.n_tiles) + rank; };
 
   if (warp == kWarpTma) {
     if (lane == 0) {
@@ -153,7 +154,8 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams<Epi> p) {
       for (int item = first; item < total_items; item += step) {
         int m_blk = m_of(item);
         if (m_blk >= p.m_tiles) m_blk = p.m_tiles - 1;
-        const int n_blk = item % p.n_tiles;
+        const int n_blk = (item % items_per_split) % p.n_tiles;
+        const int kb0 = (item / items_per_split) * p.num_k_blocks;          // first k-block of this item's k-split
         int cb = 0, h0 = 0, w0 = 0;
         if (AMODE == A_CONV) {
           const int per_img = p.geom.tiles_h * p.geom.tiles_w;
@@ -170,7 +172,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams<Epi> p) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
           if (AMODE == A_LINEAR) {
-            tma_load_2d_pair(sA + stage * Cfg::kABytes, &p.tma_a, &full[stage], kb * kBK, a_row0);
+            tma_load_2d_pair(sA + stage * Cfg::kABytes, &p.tma_a, &full[stage], (kb0 + kb) * kBK, a_row0);
           } else {
             tma_load_5d_pair(sA + stage * Cfg::kABytes, &p.tma_a, &full[stage], p.geom.dc[tap] + cblk * kBK, w0 + p.geom.dw[tap],
                              p.geom.dp[tap], h0 + p.geom.dh[tap], cb);
@@ -179,7 +181,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams<Epi> p) {
               ++tap;
             }
           }
-          tma_load_2d_pair(sB + stage * Cfg::kBBytes, &p.tma_b, &full[stage], kb * kBK, p.b_row_offset + n_blk * BN + rank * (BN / 2));
+          tma_load_2d_pair(sB + stage * Cfg::kBBytes, &p.tma_b, &full[stage], (kb0 + kb) * kBK, p.b_row_offset + n_blk * BN + rank * (BN / 2));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -234,7 +236,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams<Epi> p) {
     uint32_t acc_phase = 0;
     for (int item = first; item < total_items; item += step) {
       const int m_blk = m_of(item);
-      const int n_blk = item % p.n_tiles;
+      const int n_blk = (item % items_per_split) % p.n_tiles;
       RowInfo ri;
       if (AMODE == A_LINEAR) {
         ri.h = ri.w = 0;
@@ -245,7 +247,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams<Epi> p) {
           ri.valid = ri.t < p.rows_per_image;
         } else {
           ri.gm = m_blk * kBM + row;
-          ri.b = 0;
+          ri.b = item / items_per_split;             // k-split (0 without splitting)
           ri.t = ri.gm;
           ri.valid = ri.gm < p.M;
         }

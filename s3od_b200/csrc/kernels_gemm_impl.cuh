@@ -15,7 +15,7 @@ cudaError_t launch_gemm(const GemmParams<Epi>& p, int num_sms, cudaStream_t stre
       auto kern2 = gemm_tc2_kernel<BN, AMODE, Epi, EPI_WARPS>;
       static SmemOptIn configured2;
       if (cudaError_t e = configured2.ensure(kern2, Cfg2::kSmemBytes); e != cudaSuccess) return e;
-      const int items = ((p.m_tiles + 1) / 2) * p.n_tiles;            // (M-tile pair, N tile) work items
+      const int items = ((p.m_tiles + 1) / 2) * p.n_tiles * (p.k_splits > 1 ? p.k_splits : 1);      // (k-split, M-tile pair, N tile) work items
       const int pairs = items < num_sms / 2 ? items : num_sms / 2;
       return launch_pdl(kern2, dim3(2 * pairs), dim3(128 + 32 * EPI_WARPS), Cfg2::kSmemBytes, stream, p);
     }

@@ -458,8 +458,19 @@ def _bind_block(lib):
         lib.s3od_train_rowdot64.argtypes = [vp, vp, vp, ll, vp]
         lib.s3od_train_softmax2_rows.argtypes = [vp, vp, ci, ci, vp]
         lib.s3od_train_softmax_backward.argtypes = [vp, vp, vp, vp, ci, ci, vp]
+        lib.s3od_op_gemm_f32_splitk.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
         lib._block_bound = True
     return lib
+
+
+def wgrad_plan(n_out: int, n_in: int, rows: int, sms: int = 148):
+    """(k-splits, padded contraction length) of a weight-gradient GEMM dW[n_out, n_in] = dY^T X over `rows` tokens.  The output has
+    only ceil(n_out / 256) * (n_in / 256 or 128) CTA-pair tiles - 9 for a 768 x 768 projection, 3 for a 64-channel convolution - so
+    the contraction is split until the tiles fill the SM pairs once (s3od_op_gemm_f32_splitk), keeping >= 8 k-blocks per split."""
+    tiles = ((n_out + 127) // 128 + 1) // 2 * (n_in // (256 if n_in % 256 == 0 else 128))
+    splits = max(1, min(32, (sms // 2) // max(tiles, 1), rows // 512))
+    kpad = (rows + 64 * splits - 1) // (64 * splits) * (64 * splits)
+    return splits, kpad
 
 
 class EncoderBlockStep:
@@ -480,6 +491,7 @@ class EncoderBlockStep:
         from .weights import rope_tables
         self.lib = _bind_block(_lib())
         self.arch, self.dev = arch, torch.device(device)
+        self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         self.D, self.H, self.I = arch.hidden, arch.heads, arch.mlp
         g = image_size // arch.patch
         self.N = g * g + arch.n_prefix
@@ -513,6 +525,18 @@ class EncoderBlockStep:
     def _gemm(self, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
         c = torch.empty(M, N, dtype=torch.float32, device=self.dev)
         self._ck(self.lib.s3od_op_gemm_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, self._st()), "s3od_op_gemm_f32")
+        return c
+
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, n_in: int) -> torch.Tensor:
+        """dW fp32 [n_out, n_in] = dy[rows, n_out]^T x[rows, n_in]: both operands transposed (tokens become the zero-padded contraction
+        dimension) and the contraction split across the SMs (`wgrad_plan`)."""
+        splits, kpad = wgrad_plan(n_out, n_in, rows, self.sms)
+        a = self._transpose(dy, 1, rows, n_out, kpad)
+        b = self._transpose(x, 1, rows, n_in, kpad)
+        c = torch.empty(n_out, n_in, dtype=torch.float32, device=self.dev)
+        ws = torch.empty(splits * n_out * n_in, dtype=torch.float32, device=self.dev) if splits > 1 else None
+        self._ck(self.lib.s3od_op_gemm_f32_splitk(a.data_ptr(), b.data_ptr(), c.data_ptr(), n_out, n_in, kpad, splits,
+                                                  ws.data_ptr() if ws is not None else None, self._st()), "s3od_op_gemm_f32_splitk")
         return c
 
     def _transpose(self, t: torch.Tensor, batch: int, rows: int, cols: int, rows_padded: int, scale: float = 1.0) -> torch.Tensor:
@@ -610,32 +634,30 @@ class EncoderBlockStep:
         s, w, wt = self.saved, self.w, self.wt
         B, N, Npad, D, I, H = s["B"], self.N, self.Npad, self.D, self.I, self.H
         M = B * N
-        Mpad = (M + 63) // 64 * 64
         grads: Dict[str, torch.Tensor] = {}
         dx2 = dx2.to(self.dev, torch.float32).contiguous().view(M, D)
         with torch.cuda.device(self.dev):
             st = self._st()
-            T = lambda t, rows, cols: self._transpose(t, 1, rows, cols, Mpad).view(cols, Mpad)       # noqa: E731  tokens become the K dimension
             # ---- MLP branch: x2 = x1 + ls2 * (down(gelu(up(LN2(x1)))))
             grads["layer_scale2.lambda1"] = self._colsum(dx2, s["y"])
             grads["mlp.down_proj.bias"] = self._colsum(dx2, None, w["ls2"])
             dy = self._scale_cast(dx2, w["ls2"])
             dhmid = self._gemm(dy, wt["down.w"], M, I, D)                                   # dgrad: dY W
-            grads["mlp.down_proj.weight"] = self._gemm(T(dy, M, D), T(s["hmid"], M, I), D, I, Mpad)      # wgrad: dY^T X
+            grads["mlp.down_proj.weight"] = self._wgrad(dy, s["hmid"], M, D, I)                        # wgrad: dY^T X
             dhpre = torch.empty(M, I, dtype=torch.bfloat16, device=self.dev)
             dhpre32 = torch.empty(M, I, dtype=torch.float32, device=self.dev)
             self._ck(self.lib.s3od_train_gelu_backward(s["hpre"].data_ptr(), dhmid.data_ptr(), dhpre.data_ptr(), dhpre32.data_ptr(), dhmid.numel(), st),
                      "s3od_train_gelu_backward")
             grads["mlp.up_proj.bias"] = self._colsum(dhpre32)
             dxn2 = self._gemm(dhpre, wt["up.w"], M, D, I)
-            grads["mlp.up_proj.weight"] = self._gemm(T(dhpre, M, I), T(s["xn2"], M, D), I, D, Mpad)
+            grads["mlp.up_proj.weight"] = self._wgrad(dhpre, s["xn2"], M, I, D)
             dx1, grads["norm2.weight"], grads["norm2.bias"] = self._ln_backward(s["x1"], w["ln2.w"], dxn2, dx2)
             # ---- attention branch: x1 = x0 + ls1 * o_proj(attn(LN1(x0)))
             grads["layer_scale1.lambda1"] = self._colsum(dx1, s["o"])
             grads["attention.o_proj.bias"] = self._colsum(dx1, None, w["ls1"])
             do = self._scale_cast(dx1, w["ls1"])
             dctx = self._gemm(do, wt["o.w"], M, D, D)
-            grads["attention.o_proj.weight"] = self._gemm(T(do, M, D), T(s["ctx"], M, D), D, D, Mpad)
+            grads["attention.o_proj.weight"] = self._wgrad(do, s["ctx"], M, D, D)
             dO = self._split_heads(dctx, B)                                                 # [B, H, Npad, 64] bf16
             Oh = self._split_heads(s["ctx"], B)
             BH = B * H
@@ -656,7 +678,7 @@ class EncoderBlockStep:
             bq = self._colsum(dqkv32)
             grads["attention.q_proj.bias"], grads["attention.v_proj.bias"] = bq[:D].clone(), bq[2 * D:].clone()      # k_proj has no bias
             dxn1 = self._gemm(dqkv, wt["qkv.w"], M, D, 3 * D)
-            dW = self._gemm(T(dqkv, M, 3 * D), T(s["xn1"], M, D), 3 * D, D, Mpad)
+            dW = self._wgrad(dqkv, s["xn1"], M, 3 * D, D)
             grads["attention.q_proj.weight"], grads["attention.k_proj.weight"], grads["attention.v_proj.weight"] = dW[:D], dW[D:2 * D], dW[2 * D:]
             dx0, grads["norm1.weight"], grads["norm1.bias"] = self._ln_backward(s["x0"], w["ln1.w"], dxn1, dx1)
         return dx0.view(B, N, D), grads
@@ -741,12 +763,9 @@ class EncoderTrainer:
                     emit(f"{self.prefix}{i}.{name}", g[name])
             # embeddings: patch rows -> conv weight / bias (wgrad with the patches as K), prefix rows -> cls / register tokens
             dtok = dh[:, npre:].reshape(B * P, D).contiguous()
-            Mpad = (B * P + 63) // 64 * 64
-            dtok_T = b0._transpose(dtok, 1, B * P, D, Mpad).view(D, Mpad)
-            cols_T = b0._transpose(cols, 1, B * P, cols.shape[1], Mpad).view(cols.shape[1], Mpad)
             e = "encoder.embeddings."
             emit(e + "patch_embeddings.bias", b0._colsum(dtok))
-            emit(e + "patch_embeddings.weight", b0._gemm(dtok_T, cols_T, D, cols.shape[1], Mpad).view(D, 3, self.arch.patch, self.arch.patch))
+            emit(e + "patch_embeddings.weight", b0._wgrad(dtok, cols, B * P, D, cols.shape[1]).view(D, 3, self.arch.patch, self.arch.patch))
             dpre = b0._colsum(dh[:, :npre].reshape(B, npre * D).contiguous()).view(npre, D)      # summed over the batch
             emit(e + "register_tokens", dpre[1:].reshape(1, npre - 1, D).clone())
             emit(e + "cls_token", dpre[:1].reshape(1, 1, D).clone())

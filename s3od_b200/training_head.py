@@ -20,7 +20,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import torch
 
 from .arch import ArchSpec
-from .training import _bind_block, _check, _lib
+from .training import _bind_block, _check, _lib, wgrad_plan
 
 
 def _bind_head(lib):
@@ -57,6 +57,7 @@ class _Ops:
     def __init__(self, device):
         self.lib = _bind_head(_bind_block(_lib()))
         self.dev = torch.device(device)
+        self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
 
     def st(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
@@ -70,6 +71,18 @@ class _Ops:
     def gemm(self, a, b, M, N, K):
         c = self.f32(M, N)
         self.ck(self.lib.s3od_op_gemm_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, self.st()), "s3od_op_gemm_f32")
+        return c
+
+    def wgrad(self, dy, x, rows, n_out, n_in, n_in_padded):
+        """dW fp32 [n_out, n_in_padded] = dy[rows, n_out]^T x[rows, n_in] with the contraction over the rows (pixels) split across the
+        SMs (`training.wgrad_plan`); columns >= n_in are zero."""
+        splits, kpad = wgrad_plan(n_out, n_in_padded, rows, self.sms)
+        a = self.transpose_into(dy, rows, n_out, n_out, kpad)
+        b = self.transpose_into(x, rows, n_in, n_in_padded, kpad)
+        c = self.f32(n_out, n_in_padded)
+        ws = self.f32(splits * n_out * n_in_padded) if splits > 1 else None
+        self.ck(self.lib.s3od_op_gemm_f32_splitk(a.data_ptr(), b.data_ptr(), c.data_ptr(), n_out, n_in_padded, kpad, splits,
+                                                 ws.data_ptr() if ws is not None else None, self.st()), "s3od_op_gemm_f32_splitk")
         return c
 
     def transpose_into(self, t, rows, cols, out_rows, rows_padded):
@@ -193,10 +206,7 @@ class _Conv:
         dy = dy.reshape(P, self.cout).contiguous()
         if self.bias is not None:
             emit(self.name + ".bias", o.colsum(dy))
-        Ppad = _up(P, 64)
-        dyT = o.transpose_into(dy, P, self.cout, self.cout, Ppad)                        # [cout][Ppad]
-        colsT = o.transpose_into(cols, P, self.K, self.Kp, Ppad)                         # [K padded to 128 rows][Ppad]
-        dW = o.copy_cols(o.gemm(dyT, colsT, self.cout, self.Kp, Ppad), self.cout, self.K, self.Kp)
+        dW = o.copy_cols(o.wgrad(dy, cols, P, self.cout, self.K, self.Kp), self.cout, self.K, self.Kp)      # dY^T cols, pixels as the contraction
         emit(self.name + ".weight", dW.view(self.cout, self.k, self.k, self.cin).permute(0, 3, 1, 2).contiguous())
         if not need_dx:
             return None
@@ -249,8 +259,7 @@ class _ConvT:
         o.ck(o.lib.s3od_train_convt_unfold(dy.data_ptr(), dcols.data_ptr(), B, H, W, self.cout, self.k, self.stride, self.pad, o.st()),
              "s3od_train_convt_unfold")
         dx = o.gemm(dcols, self.wt, P, self.cin, self.N)
-        Ppad = _up(P, 64)
-        dW = o.gemm(o.transpose_into(dcols, P, self.N, self.N, Ppad), o.transpose_into(xb, P, self.cin, self.cin, Ppad), self.N, self.cin, Ppad)
+        dW = o.wgrad(dcols, xb, P, self.N, self.cin, self.cin)
         emit(self.name + ".weight", dW.view(self.k, self.k, self.cout, self.cin).permute(3, 2, 0, 1).contiguous())
         return dx.view(B, H, W, self.cin)
 

@@ -4,7 +4,7 @@ from s3od_b200.arch import VITB
 from s3od_b200.synth import synth_state_dict
 from s3od_b200.training_head import TrainStep
 sd = synth_state_dict(VITB, 0)
-for S, B in ((224, 8), (1024, 1), (1024, 2)):
+for S, B in ((224, 8), (1024, 1), (1024, 2), (1024, 4), (1024, 8)):
     ts = TrainStep(sd, VITB, S, "cuda:0", lr=1e-5)
     g = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(B, 3, S, S, device="cuda", generator=g)
