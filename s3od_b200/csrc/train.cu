@@ -143,8 +143,20 @@ int s3od_train_transpose(const void* d_in, int in_is_f32, void* d_out, int batch
   if (d_in == nullptr || d_out == nullptr || batch < 1 || rows < 1 || cols < 1 || rows_padded < rows)
     return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_transpose");
   if ((cols + 31) / 32 > 65535 || batch > 65535) return train_fail(S3OD_ERR_ARG, "s3od_train_transpose: more than 2 M columns or 65535 batches");
-  const dim3 grid((rows_padded + 31) / 32, (cols + 31) / 32, batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vec = in_is_f32 ? 4 : 8;                 // elements per 16-byte load
+  if (rows_padded % 8 == 0 && (reinterpret_cast<uintptr_t>(d_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
+      in_row_stride % vec == 0 && in_batch_stride % vec == 0 && (static_cast<long long>(cols) * rows_padded) % 8 == 0) {
+    const dim3 grid64((rows_padded + 63) / 64, (cols + 63) / 64, batch);          // 64 x 64 tiles, 16-byte accesses
+    if (in_is_f32)
+      transpose_pad64_kernel<float><<<grid64, 256, 0, st>>>(static_cast<const float*>(d_in), static_cast<bf16_t*>(d_out), rows, cols, rows_padded,
+                                                            in_batch_stride, in_row_stride, scale);
+    else
+      transpose_pad64_kernel<bf16_t><<<grid64, 256, 0, st>>>(static_cast<const bf16_t*>(d_in), static_cast<bf16_t*>(d_out), rows, cols, rows_padded,
+                                                             in_batch_stride, in_row_stride, scale);
+    S3OD_TRAIN_DONE("transpose_pad64_kernel");
+  }
+  const dim3 grid((rows_padded + 31) / 32, (cols + 31) / 32, batch);
   if (in_is_f32)
     transpose_pad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(d_in), static_cast<bf16_t*>(d_out), rows, cols, rows_padded,
                                                       in_batch_stride, in_row_stride, scale);
@@ -192,11 +204,14 @@ size_t s3od_train_colsum_workspace_bytes(int rows, int cols) {
 int s3od_train_colsum(const float* d_a, const float* d_b, int rows, int cols, const float* d_colscale, float* d_out, int accumulate,
                       void* d_workspace, s3od_stream stream) {
   if (d_a == nullptr || d_out == nullptr || d_workspace == nullptr || rows < 1 || cols < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_colsum");
+  const bool vec = cols % 4 == 0 && (reinterpret_cast<uintptr_t>(d_a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_b) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_workspace) & 15) == 0;
   const int rpb = colsum_rows_per_block(rows);
   const int nblk = (rows + rpb - 1) / rpb;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  colsum_partial_kernel<<<dim3((cols + 255) / 256, nblk), 256, 0, st>>>(d_a, d_b, rows, cols, rpb, static_cast<float*>(d_workspace));
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(static_cast<const float*>(d_workspace), nblk, cols, d_colscale, d_out, accumulate);
+  if (vec) colsum_partial_kernel<<<dim3((cols + 255) / 256, nblk), 256, 0, st>>>(d_a, d_b, rows, cols, rpb, static_cast<float*>(d_workspace));
+  else colsum_partial_scalar_kernel<<<dim3((cols + 255) / 256, nblk), 256, 0, st>>>(d_a, d_b, rows, cols, rpb, static_cast<float*>(d_workspace));
+  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(static_cast<const float*>(d_workspace), nblk, cols, d_colscale, d_out, accumulate);
   S3OD_TRAIN_DONE("colsum kernels");
 }
 
@@ -216,8 +231,8 @@ int s3od_train_ln_backward(const float* d_x, const float* d_gamma, const float* 
     ln_backward_kernel<1024><<<nblk, 256, 0, st>>>(d_x, d_gamma, d_dy, d_dres, d_dx, rows, eps, pg, pb);
   else
     return train_fail(S3OD_ERR_ARG, "s3od_train_ln_backward: hidden size must be 768 or 1024");
-  colsum_final_kernel<<<(dim + 255) / 256, 256, 0, st>>>(pg, nblk, dim, nullptr, d_dgamma, 0);
-  colsum_final_kernel<<<(dim + 255) / 256, 256, 0, st>>>(pb, nblk, dim, nullptr, d_dbeta, 0);
+  colsum_final_kernel<<<(dim + 31) / 32, 256, 0, st>>>(pg, nblk, dim, nullptr, d_dgamma, 0);
+  colsum_final_kernel<<<(dim + 31) / 32, 256, 0, st>>>(pb, nblk, dim, nullptr, d_dbeta, 0);
   S3OD_TRAIN_DONE("ln_backward kernels");
 }
 

@@ -39,6 +39,65 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const TIn* __restric
   }
 }
 
+// The same transposition with 64 x 64 tiles and 16-byte global accesses on both sides (the 32 x 32 form above moves 64-byte row
+// pieces and reaches a quarter of the HBM bandwidth): needs Rpad % 8 == 0, 16-byte aligned `in` / `out`, and row / batch strides
+// of `in` that are multiples of one 16-byte vector.  The tile is kept transposed in shared memory as bf16 [c][r] with a pitch of
+// 33 words: the scattered 2-byte stores of the load phase are 2-way conflicted, the 4-byte reads of the store phase conflict-free.
+template <class TIn>
+__global__ void __launch_bounds__(256) transpose_pad64_kernel(const TIn* __restrict__ in, bf16_t* __restrict__ out, int R, int C, int Rpad,
+                                                              long long in_batch_stride, int in_row_stride, float scale) {
+  constexpr int kPitch = 66;                                        // halfwords
+  __shared__ __align__(16) unsigned short tile[64 * kPitch];
+  constexpr int kVec = 16 / static_cast<int>(sizeof(TIn));          // elements per 16-byte load: 8 bf16 or 4 fp32
+  constexpr int kThreadsPerRow = 64 / kVec;
+  constexpr int kRowsPerPass = 256 / kThreadsPerRow;
+  const int b = blockIdx.z;
+  const TIn* ib = in + static_cast<long long>(b) * in_batch_stride;
+  bf16_t* ob = out + static_cast<long long>(b) * C * Rpad;
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+#pragma unroll
+  for (int pass = 0; pass < 64 / kRowsPerPass; ++pass) {
+    const int rl = pass * kRowsPerPass + static_cast<int>(threadIdx.x) / kThreadsPerRow;
+    const int cl = (static_cast<int>(threadIdx.x) % kThreadsPerRow) * kVec;
+    const int r = r0 + rl, c = c0 + cl;
+    float v[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) v[j] = 0.0f;
+    if (r < R && c < C) {
+      const TIn* src = ib + static_cast<long long>(r) * in_row_stride + c;
+      if (c + kVec <= C) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+        if constexpr (sizeof(TIn) == 4) {
+          v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+        } else {
+          const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[2 * j] = __uint_as_float(w[j] << 16);
+            v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j)
+          if (c + j < C) v[j] = ldf(src + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) tile[(cl + j) * kPitch + rl] = __bfloat16_as_ushort(__float2bfloat16_rn(v[j] * scale));
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int cl = pass * 32 + static_cast<int>(threadIdx.x) / 8, rl = (static_cast<int>(threadIdx.x) % 8) * 8;
+    const int c = c0 + cl, r = r0 + rl;
+    if (c < C && r < Rpad) {                                        // Rpad % 8 == 0: the 8 rows are all inside or all outside
+      const unsigned* t = reinterpret_cast<const unsigned*>(tile + cl * kPitch + rl);
+      *reinterpret_cast<uint4*>(ob + static_cast<long long>(c) * Rpad + r) = make_uint4(t[0], t[1], t[2], t[3]);
+    }
+  }
+}
+
 // out_bf16[r][c] = in[r][c] * colscale[c] (colscale may be null); optional fp32 copy of the same product
 __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ in, const float* __restrict__ colscale, bf16_t* __restrict__ out,
                                                          long long n, int C) {
@@ -62,9 +121,39 @@ __global__ void __launch_bounds__(256) add_bias_kernel(float* __restrict__ a, co
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) a[i] += bias[i % C];
 }
 
-// partial[blk][c] = sum over the block's rows of a[r][c] * (b ? b[r][c] : 1);  out[c] = sum of partials (second launch)
+// partial[blk][c] = sum over the block's rows of a[r][c] * (b ? b[r][c] : 1);  out[c] = sum of partials (second launch).
+// Block = 64 column quads (256 columns, 16-byte loads) x 4 row lanes; the lanes are combined through shared memory.  C % 4 == 0.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int M, int C,
                                                              int rows_per_block, float* __restrict__ partial) {
+  __shared__ float4 red[4][64];
+  const int cq = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int c = blockIdx.x * 256 + 4 * cq;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (c < C) {
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 4) {
+      const long long i = static_cast<long long>(r) * C + c;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a + i));
+      if (b != nullptr) {
+        const float4 y = __ldg(reinterpret_cast<const float4*>(b + i));
+        s.x += x.x * y.x; s.y += x.y * y.y; s.z += x.z * y.z; s.w += x.w * y.w;
+      } else {
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+      }
+    }
+  }
+  red[rl][cq] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    const float4 t1 = red[1][cq], t2 = red[2][cq], t3 = red[3][cq];
+    s.x += t1.x + t2.x + t3.x; s.y += t1.y + t2.y + t3.y; s.z += t1.z + t2.z + t3.z; s.w += t1.w + t2.w + t3.w;
+    *reinterpret_cast<float4*>(partial + static_cast<long long>(blockIdx.y) * C + c) = s;
+  }
+}
+// any column count / alignment: one thread per column
+__global__ void __launch_bounds__(256) colsum_partial_scalar_kernel(const float* __restrict__ a, const float* __restrict__ b, int M, int C,
+                                                                    int rows_per_block, float* __restrict__ partial) {
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
@@ -75,14 +164,23 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   }
   partial[static_cast<long long>(blockIdx.y) * C + c] = s;
 }
+// block = 32 columns x 8 partial-row lanes
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nblk, int C, const float* __restrict__ colscale,
                                                            float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, jl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.0f;
-  for (int j = 0; j < nblk; ++j) s += partial[static_cast<long long>(j) * C + c];
-  if (colscale != nullptr) s *= colscale[c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < C)
+    for (int j = jl; j < nblk; j += 8) s += partial[static_cast<long long>(j) * C + c];
+  red[jl][cl] = s;
+  __syncthreads();
+  if (jl == 0 && c < C) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) s += red[j][cl];
+    if (colscale != nullptr) s *= colscale[c];
+    out[c] = accumulate ? out[c] + s : s;
+  }
 }
 
 // LayerNorm backward, one warp per row:  xhat = (x - mean) rstd;  g = dy * gamma;

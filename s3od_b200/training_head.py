@@ -87,7 +87,9 @@ class _Ops:
 
     def transpose_into(self, t, rows, cols, out_rows, rows_padded):
         """t [rows][cols] (fp32 or bf16, dense) -> zeroed bf16 [out_rows >= cols][rows_padded] holding t^T in its first `cols` rows."""
-        out = torch.zeros(out_rows, rows_padded, dtype=torch.bfloat16, device=self.dev)
+        out = torch.empty(out_rows, rows_padded, dtype=torch.bfloat16, device=self.dev)      # the kernel writes (and zero-pads) rows < cols
+        if out_rows > cols:
+            out[cols:].zero_()
         self.ck(self.lib.s3od_train_transpose(t.data_ptr(), 1 if t.dtype == torch.float32 else 0, out.data_ptr(), 1, rows, cols, rows_padded,
                                               rows * cols, cols, 1.0, self.st()), "s3od_train_transpose")
         return out

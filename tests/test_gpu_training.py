@@ -158,6 +158,33 @@ def test_fused_exchange_and_adamw_over_emulated_ranks(world):
         opt.close()
 
 
+def test_training_glue_kernels_transpose_colsum_splitk(vitb_sd):
+    """The glue of the block step on ragged shapes: transposition (64 x 64 vector form and the scalar fallback, fp32 and bf16 input,
+    batched, zero padding) is exact; column sums and the split-K GEMM agree with torch to fp32 summation-order accuracy."""
+    from s3od_b200.training import EncoderBlockStep
+    blk = EncoderBlockStep(vitb_sd, "encoder.model.layer.0.", VITB, 64, "cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for dtype in (torch.float32, torch.bfloat16):
+        for batch, rows, cols, rpad in ((1, 1000, 200, 1024), (3, 70, 96, 128), (1, 333, 77, 333), (2, 64, 64, 72), (1, 4101, 768, 4608)):
+            t = torch.randn(batch, rows, cols, device="cuda", generator=g).to(dtype)
+            out = blk._transpose(t, batch, rows, cols, rpad, scale=0.5)
+            ref = torch.zeros(batch, cols, rpad, dtype=torch.bfloat16, device="cuda")
+            ref[:, :, :rows] = (t.float() * 0.5).to(torch.bfloat16).transpose(1, 2)
+            assert torch.equal(out, ref), (dtype, batch, rows, cols, rpad)
+    for rows, cols in ((4101, 768), (1000, 96), (37, 3072), (513, 6)):
+        a = torch.randn(rows, cols, device="cuda", generator=g)
+        b = torch.randn(rows, cols, device="cuda", generator=g)
+        sc = torch.randn(cols, device="cuda", generator=g)
+        assert float((blk._colsum(a) - a.double().sum(0).float()).abs().max()) <= 1e-4 * math.sqrt(rows)
+        assert float((blk._colsum(a, b, sc) - ((a.double() * b.double()).sum(0) * sc.double()).float()).abs().max()) <= 3e-4 * math.sqrt(rows)
+    for rows, n_out, n_in in ((4101, 768, 768), (9000, 64, 640), (700, 256, 128)):
+        dy = torch.randn(rows, n_out, device="cuda", generator=g).to(torch.bfloat16)
+        x = torch.randn(rows, n_in, device="cuda", generator=g).to(torch.bfloat16)
+        ref = dy.float().t() @ x.float()
+        got = blk._wgrad(dy, x, rows, n_out, n_in)
+        assert float((got - ref).abs().max()) <= 2e-3 * math.sqrt(rows), (rows, n_out, n_in)
+
+
 @pytest.mark.parametrize("B,H,N", [(1, 2, 261), (2, 3, 389), (1, 1, 4101), (1, 12, 1029)])
 def test_fused_attention_forward_backward_matches_autograd(capsys, B, H, N):
     """csrc/attention.cuh (log-sum-exp output) + csrc/attention_bwd.cuh against torch.autograd of softmax(Q K^T) V in fp32 on the
