@@ -276,6 +276,8 @@ int s3od_train_small_linear_backward(const float* d_dout, const float* d_a, cons
 /* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
 /* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */
 int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream);
+/* the same with bias[N] (fp32, 16-byte aligned, may be NULL) added to every row in the epilogue */
+int s3od_op_gemm_f32_bias(const void* d_a, const void* d_b, const float* d_bias, float* d_c, int M, int N, int K, s3od_stream stream);
 /* the same GEMM with the contraction split `splits` ways across the SMs (weight-gradient GEMMs: an M x N output of a few tiles and a
    K of 10^4..10^6 tokens): every split writes its partial M x N product into d_workspace (splits * M * N floats), a second kernel sums
    them into d_c.  K % (64 * splits) == 0, splits <= 64; splits <= 1 is s3od_op_gemm_f32. */

@@ -1098,12 +1098,17 @@ void s3od_destroy(s3od_ctx* c) {
 
 // ------------------------------------------------------------------------------------------ kernel-level entry points
 int s3od_op_gemm_f32(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, s3od_stream stream) {
+  return s3od_op_gemm_f32_bias(d_a, d_b, nullptr, d_c, M, N, K, stream);
+}
+
+int s3od_op_gemm_f32_bias(const void* d_a, const void* d_b, const float* d_bias, float* d_c, int M, int N, int K, s3od_stream stream) {
   if (N % 128 != 0 || K % 64 != 0 || M < 1) return fail(S3OD_ERR_ARG, "s3od_op_gemm_f32 needs N % 128 == 0 and K % 64 == 0");
+  if ((reinterpret_cast<uintptr_t>(d_bias) & 15) != 0) return fail(S3OD_ERR_ARG, "s3od_op_gemm_f32_bias needs a 16-byte aligned bias");
   GemmParams<EpiStoreF32> p{};
   if (!tmap_matrix(&p.tma_a, d_a, M, K, kBM)) return S3OD_ERR_CUDA;
   if (!tmap_matrix(&p.tma_b, d_b, N, K, b_box_rows<128>())) return S3OD_ERR_CUDA;
   p.M = M; p.m_tiles = (M + kBM - 1) / kBM; p.n_tiles = N / 128; p.num_k_blocks = K / 64;
-  p.epi = EpiStoreF32::Params{d_c, N};
+  p.epi = EpiStoreF32::Params{d_c, N, 0, d_bias};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

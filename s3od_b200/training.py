@@ -458,6 +458,7 @@ def _bind_block(lib):
         lib.s3od_train_rowdot64.argtypes = [vp, vp, vp, ll, vp]
         lib.s3od_train_softmax2_rows.argtypes = [vp, vp, ci, ci, vp]
         lib.s3od_train_softmax_backward.argtypes = [vp, vp, vp, vp, ci, ci, vp]
+        lib.s3od_op_gemm_f32_bias.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
         lib.s3od_op_gemm_f32_splitk.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
         lib._block_bound = True
     return lib
@@ -522,9 +523,10 @@ class EncoderBlockStep:
     def _ck(self, rc, what):
         _check(self.lib, rc, what)
 
-    def _gemm(self, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
+    def _gemm(self, a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
         c = torch.empty(M, N, dtype=torch.float32, device=self.dev)
-        self._ck(self.lib.s3od_op_gemm_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), M, N, K, self._st()), "s3od_op_gemm_f32")
+        self._ck(self.lib.s3od_op_gemm_f32_bias(a.data_ptr(), b.data_ptr(), bias.data_ptr() if bias is not None else None, c.data_ptr(), M, N, K,
+                                                self._st()), "s3od_op_gemm_f32_bias")
         return c
 
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, n_in: int) -> torch.Tensor:
@@ -610,19 +612,19 @@ class EncoderBlockStep:
         x0 = x.to(self.dev, torch.float32).contiguous().view(M, D)
         with torch.cuda.device(self.dev):
             xn1 = self._layernorm(x0, w["ln1.w"], w["ln1.b"])
-            qkv = self._add_bias(self._gemm(xn1, wb["qkv.w"], M, 3 * D, D), w["qkv.b"])
+            qkv = self._gemm(xn1, wb["qkv.w"], M, 3 * D, D, w["qkv.b"])
             q, k, v = self._split_rope(qkv, B, self.Npad)                   # [B, H, Npad, 64] bf16, zero rows behind the sequence
             ctx = torch.empty(M, D, dtype=torch.bfloat16, device=self.dev)
             lse = torch.full((B * H, self.Npad), float("inf"), dtype=torch.float32, device=self.dev)
             self._ck(self.lib.s3od_train_attention_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), ctx.data_ptr(), lse.data_ptr(), B, H, N, self.Npad,
                                                            self._st()), "s3od_train_attention_forward")
-            o = self._add_bias(self._gemm(ctx, wb["o.w"], M, D, D), w["o.b"])
+            o = self._gemm(ctx, wb["o.w"], M, D, D, w["o.b"])
             x1 = self._residual(x0, o, w["ls1"])
             xn2 = self._layernorm(x1, w["ln2.w"], w["ln2.b"])
-            hpre = self._add_bias(self._gemm(xn2, wb["up.w"], M, I, D), w["up.b"])
+            hpre = self._gemm(xn2, wb["up.w"], M, I, D, w["up.b"])
             hmid = torch.empty(M, I, dtype=torch.bfloat16, device=self.dev)
             self._ck(self.lib.s3od_train_gelu_forward(hpre.data_ptr(), hmid.data_ptr(), hpre.numel(), self._st()), "s3od_train_gelu_forward")
-            y = self._add_bias(self._gemm(hmid, wb["down.w"], M, D, I), w["down.b"])
+            y = self._gemm(hmid, wb["down.w"], M, D, I, w["down.b"])
             x2 = self._residual(x1, y, w["ls2"])
         self.saved = dict(B=B, x0=x0, xn1=xn1, q=q, k=k, v=v, lse=lse, ctx=ctx, o=o, x1=x1, xn2=xn2, hpre=hpre, hmid=hmid, y=y)
         return x2.view(B, N, D)
@@ -721,7 +723,7 @@ class EncoderTrainer:
         P = (self.S // self.arch.patch) ** 2
         with torch.cuda.device(self.dev):
             cols = self._im2col(x)
-            tok = b0._add_bias(b0._gemm(cols, self.patch_wb, B * P, D, cols.shape[1]), self.patch_b)
+            tok = b0._gemm(cols, self.patch_wb, B * P, D, cols.shape[1], self.patch_b)
             h = torch.empty(B, P + npre, D, dtype=torch.float32, device=self.dev)
             h[:, :npre] = self.prefix_tokens
             h[:, npre:] = tok.view(B, P, D)
