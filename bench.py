@@ -26,6 +26,7 @@ from s3od_b200.synth import save_checkpoint, synth_noise_image, synth_state_dict
 
 METRIC = "images/sec (dinob, device-timed)"
 UNIT = "images/s"
+TRAIN_BATCH = 4            # images per GPU and step of the training legs (train_batch_size of the reference's model_training/config/dataset/synth.yaml:6)
 # algorithmic FLOPs of the needed layers, dinob @ 1024^2 = 2276.8 GF as written; the plan runs the four
 # fusion-block out_convs (1x1) BEFORE the 2x interpolation (engine.cu, "out_conv commuted"), which removes 34.2 GF of them
 # ("if used, subtract 34.2 GF") - the work actually executed is what the roofline is computed from.
@@ -271,7 +272,7 @@ def gpu_baseline(S, batch, dev):
         sd_bf["_dtype"] = torch.bfloat16
         run("bf16_weights", False, True, sd_bf)          # + autocast: the fp32 RoPE tables / LayerNorm outputs meet bf16 operands
         # the training step of config 4 the same way: oracle arithmetic (train-mode head) + loss restatement under autocast(bf16),
-        # torch.autograd, torch.optim.AdamW with the reference's two groups; batch 2 at 1024^2
+        # torch.autograd, torch.optim.AdamW with the reference's two groups; batch TRAIN_BATCH at 1024^2
         try:
             from oracle import loss as ol
             sd_t = {k: v.detach().clone() for k, v in sd_dev.items()}
@@ -280,8 +281,8 @@ def gpu_baseline(S, batch, dev):
                 sd_t[k].requires_grad_(True)
             opt = torch.optim.AdamW([{"params": [sd_t[k] for k in names if k.startswith("encoder.")], "lr": 1e-5},
                                      {"params": [sd_t[k] for k in names if k.startswith("seg_head.")], "lr": 1e-4}], weight_decay=0.05)
-            xt = torch.randn(2, 3, S, S, device=dev)
-            mt = (torch.rand(2, S, S, device=dev) > 0.5).float()
+            xt = torch.randn(TRAIN_BATCH, 3, S, S, device=dev)
+            mt = (torch.rand(TRAIN_BATCH, S, S, device=dev) > 0.5).float()
 
             def train_step():
                 opt.zero_grad(set_to_none=True)
@@ -300,7 +301,8 @@ def gpu_baseline(S, batch, dev):
                 train_step()
             e1.record()
             torch.cuda.synchronize(dev)
-            res["train_step_bf16_autocast"] = round(3 * 2 / (e0.elapsed_time(e1) / 1e3), 2)
+            res["train_step_bf16_autocast"] = round(3 * TRAIN_BATCH / (e0.elapsed_time(e1) / 1e3), 2)
+            res["train_step_batch"] = TRAIN_BATCH
         except Exception as e:  # noqa: BLE001
             res["train_step_bf16_autocast"] = None
             res["train_step_error"] = repr(e)[:200]
@@ -453,13 +455,13 @@ def training_slice_leg(rank, world, dev):
         del blk, xb, gb
         torch.cuda.empty_cache()
         # the whole optimisation step of config 4 (train-mode forward, loss, backward, gradient exchange over the process group,
-        # fused AdamW) at one 1024^2 image per GPU: correctness-first kernels, but a REAL step with a REAL
-        # collective, so the N = 1, 2, 4, 8 records show how the exchange scales
+        # fused AdamW) at config/dataset/synth.yaml's batch of four 1024^2 images per GPU: a REAL step with a
+        # REAL collective, so the N = 1, 2, 4, 8 records show how the exchange scales
         from s3od_b200.training_head import TrainStep
         ts = TrainStep(synth_state_dict(VITB, 0), VITB, 1024, dev, lr=1e-5)
         g2 = torch.Generator(device=dev).manual_seed(11 + rank)
-        xi = torch.randn(1, 3, 1024, 1024, device=dev, generator=g2)
-        mi = (torch.rand(1, 1024, 1024, device=dev, generator=g2) > 0.5).float()
+        xi = torch.randn(TRAIN_BATCH, 3, 1024, 1024, device=dev, generator=g2)
+        mi = (torch.rand(TRAIN_BATCH, 1024, 1024, device=dev, generator=g2) > 0.5).float()
         ts.step(xi, mi)
         torch.cuda.synchronize(dev)
         sharder.barrier()
@@ -471,7 +473,8 @@ def training_slice_leg(rank, world, dev):
         b.record()
         torch.cuda.synchronize(dev)
         tstep = sharder.max_over_ranks(a.elapsed_time(b), device=dev) / nst
-        ent["train_step"] = {"batch_per_gpu": 1, "image_size": 1024, "ms_per_step": round(tstep, 1), "images_per_s": round(world * 1e3 / tstep, 2),
+        ent["train_step"] = {"batch_per_gpu": TRAIN_BATCH, "image_size": 1024, "ms_per_step": round(tstep, 1),
+                             "images_per_s": round(world * TRAIN_BATCH * 1e3 / tstep, 2),
                              "loss": round(float(lossv), 4), "allreduce_buckets": ts.layout.num_buckets,
                              "what": "TrainStep.step: encoder + head forward (train mode), loss fwd+bwd, full backward, bucketed all-reduce, fused AdamW"}
         del ts
@@ -708,8 +711,8 @@ def main():
                               "value": tsr.get("images_per_s"), "unit": UNIT, "n_gpus": world, "steps": 2, "warmup": 1,
                               "ms_per_step": tsr.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                               "dtype": "bf16 operands, fp32 accumulation / master weights", "data": "synthetic",
-                              "config": {"workload": "dinob training step, 1 synthetic 1024x1024 image per GPU, image_size 1024, seeded random weights",
-                                         "batch_per_gpu": 1, "image_size": 1024}, "detail": ent}), flush=True)
+                              "config": {"workload": f"dinob training step, {TRAIN_BATCH} synthetic 1024x1024 images per GPU, image_size 1024, seeded random weights",
+                                         "batch_per_gpu": TRAIN_BATCH, "image_size": 1024}, "detail": ent}), flush=True)
         if world > 1:
             torch.distributed.barrier()
             torch.distributed.destroy_process_group()
