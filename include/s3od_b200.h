@@ -283,6 +283,12 @@ int s3od_op_gemm_f32_bias(const void* d_a, const void* d_b, const float* d_bias,
    them into d_c.  K % (64 * splits) == 0, splits <= 64; splits <= 1 is s3od_op_gemm_f32. */
 int s3od_op_gemm_f32_splitk(const void* d_a, const void* d_b, float* d_c, int M, int N, int K, int splits, float* d_workspace,
                             s3od_stream stream);
+/* Weight-gradient GEMM without transposes (csrc/gemm_tn.cuh): C[M,N] fp32 = sum_k A[k,m] * B[k,n]; A bf16 [K rows, pitch lda >= M],
+   B bf16 [K rows, pitch ldb >= N] - one row per token / pixel, channels contiguous, exactly as dY and X lie in memory.  M % 64 == 0,
+   N % 64 == 0, pitches multiples of 8; any K.  The contraction is split `splits` ways (clamped to the number of 64-row blocks);
+   splits > 1 need d_workspace of splits * M * N floats. */
+int s3od_op_wgrad_gemm_f32(const void* d_a, int lda, const void* d_b, int ldb, float* d_c, int M, int N, int K, int splits, float* d_workspace,
+                           s3od_stream stream);
 /* y bf16 = LayerNorm(x fp32) */
 int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void* d_y, int M, int D, float eps,
                       s3od_stream stream);

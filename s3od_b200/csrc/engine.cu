@@ -1161,6 +1161,41 @@ int s3od_op_gemm_f32_splitk(const void* d_a, const void* d_b, float* d_c, int M,
   return S3OD_OK;
 }
 
+int s3od_op_wgrad_gemm_f32(const void* d_a, int lda, const void* d_b, int ldb, float* d_c, int M, int N, int K, int splits, float* d_workspace,
+                           s3od_stream stream) {
+  if (d_a == nullptr || d_b == nullptr || d_c == nullptr || M < 64 || N < 64 || K < 1 || M % 64 != 0 || N % 64 != 0 || lda < M || ldb < N || lda % 8 != 0 ||
+      ldb % 8 != 0 || (reinterpret_cast<uintptr_t>(d_a) & 15) != 0 || (reinterpret_cast<uintptr_t>(d_b) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(d_c) & 15) != 0)
+    return fail(S3OD_ERR_ARG, "s3od_op_wgrad_gemm_f32 needs M % 64 == 0, N % 64 == 0, row pitches that are multiples of 8 elements and 16-byte aligned buffers");
+  GemmTnParams p{};
+  p.M = M; p.N = N;
+  p.m_tiles = (M + 127) / 128; p.n_tiles = (N + 255) / 256;
+  p.k_blocks = (K + 63) / 64;
+  if (splits < 1) splits = 1;
+  if (splits > p.k_blocks) splits = p.k_blocks;
+  p.k_blocks_per_split = (p.k_blocks + splits - 1) / splits;
+  p.splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;          // no split without a k-block
+  if (p.splits > 1 && (d_workspace == nullptr || (reinterpret_cast<uintptr_t>(d_workspace) & 15) != 0))
+    return fail(S3OD_ERR_ARG, "s3od_op_wgrad_gemm_f32: splits > 1 need a 16-byte aligned workspace of splits * M * N floats");
+  p.out = p.splits > 1 ? d_workspace : d_c;
+  const uint64_t da[3] = {64, (uint64_t)K, (uint64_t)(M / 64)}, sa[2] = {(uint64_t)lda * 2, 128};
+  const uint64_t db[3] = {64, (uint64_t)K, (uint64_t)(N / 64)}, sb[2] = {(uint64_t)ldb * 2, 128};
+  const uint32_t ba[3] = {64, 64, 2}, bb[3] = {64, 64, 4};
+  if (!make_tmap(&p.tma_a, d_a, 3, da, sa, ba) || !make_tmap(&p.tma_b, d_b, 3, db, sb, bb)) return S3OD_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(launch_gemm_tn(p, sms, st));
+  if (p.splits > 1) {
+    const long long n4 = static_cast<long long>(M) * N / 4;
+    const int grid = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148LL * 8));
+    sum_k_splits_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_workspace), p.splits, n4, reinterpret_cast<float4*>(d_c));
+    CK(cudaGetLastError());
+  }
+  return S3OD_OK;
+}
+
 int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void* d_y, int M, int D, float eps, s3od_stream stream) {
   CK(launch_layernorm(const_cast<float*>(d_x), nullptr, d_w, d_b, static_cast<bf16*>(d_y), nullptr, M, M, D, eps,
                       static_cast<cudaStream_t>(stream)));

@@ -2,6 +2,7 @@
 #include "attention.cuh"
 #include "attention_persist.cuh"
 #include "attention_bwd.cuh"
+#include "gemm_tn.cuh"
 #include "elementwise.cuh"
 #include "visualize.cuh"
 #include "metrics.cuh"
@@ -73,6 +74,14 @@ cudaError_t launch_attention_backward(const AttnBwdParams& p, bool col_stats, in
     if (cudaError_t e = cfg_rows.ensure(attention_bwd_kernel<false>, kAttnBwdSmemBytes); e != cudaSuccess) return e;
     attention_bwd_kernel<false><<<grid, kAttnBwdThreads, kAttnBwdSmemBytes, stream>>>(p);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tn(const GemmTnParams& p, int num_sms, cudaStream_t stream) {
+  static SmemOptIn configured;
+  if (cudaError_t e = configured.ensure(gemm_tn_kernel, kTnSmemBytes); e != cudaSuccess) return e;
+  const int items = p.m_tiles * p.n_tiles * p.splits;
+  gemm_tn_kernel<<<items < num_sms ? items : num_sms, kTnThreads, kTnSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -69,6 +69,7 @@ cudaError_t launch_convt_rows(const ConvTRowParams& p, int num_sms, cudaStream_t
 cudaError_t launch_conv_swap128(const ConvSwapParams& p, int num_sms, cudaStream_t stream);
 
 cudaError_t launch_attention(const AttnParams& p, int q_tiles, int bh, cudaStream_t stream);
+cudaError_t launch_gemm_tn(const GemmTnParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_attention_backward(const AttnBwdParams& p, bool col_stats, int bh, cudaStream_t stream);
 // x += dx (optional), tap = bf16(x) on patch rows (optional), y = LayerNorm(x) (optional)
 cudaError_t launch_layernorm(float* x, const __nv_bfloat16* dx, const float* w, const float* b, __nv_bfloat16* y, __nv_bfloat16* tap, int M,

@@ -59,4 +59,16 @@ struct AttnBwdParams {
   float scale_ds;
 };
 
+// weight-gradient GEMM with token-major operands (gemm_tn.cuh)
+struct GemmTnParams {
+  CUtensorMap tma_a;       // (64 channels, K rows, M / 64 atoms), box (64, 64, 2)
+  CUtensorMap tma_b;       // (64 channels, K rows, N / 64 atoms), box (64, 64, 4)
+  float* out;              // [splits][M][N]
+  int M, N;
+  int m_tiles, n_tiles;    // ceil(M / 128), ceil(N / 256)
+  int k_blocks;            // ceil(K / 64)
+  int k_blocks_per_split;
+  int splits;
+};
+
 }  // namespace s3od

@@ -459,6 +459,7 @@ def _bind_block(lib):
         lib.s3od_train_softmax2_rows.argtypes = [vp, vp, ci, ci, vp]
         lib.s3od_train_softmax_backward.argtypes = [vp, vp, vp, vp, ci, ci, vp]
         lib.s3od_op_gemm_f32_bias.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
+        lib.s3od_op_wgrad_gemm_f32.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, ci, vp, vp]
         lib.s3od_op_gemm_f32_splitk.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
         lib._block_bound = True
     return lib
@@ -472,6 +473,25 @@ def wgrad_plan(n_out: int, n_in: int, rows: int, sms: int = 148):
     splits = max(1, min(32, (sms // 2) // max(tiles, 1), rows // 512))
     kpad = (rows + 64 * splits - 1) // (64 * splits) * (64 * splits)
     return splits, kpad
+
+
+def wgrad_plan_tn(n_out: int, n_in: int, rows: int, sms: int = 148) -> int:
+    """k-splits of the transpose-free weight-gradient GEMM (csrc/gemm_tn.cuh, 128 x 256 output tiles, one CTA each): enough that the
+    (split, tile) items fill the SMs once, at least 4 blocks of 64 rows per split."""
+    tiles = ((n_out + 127) // 128) * ((n_in + 255) // 256)
+    return max(1, min(64, sms // max(tiles, 1), rows // 256))
+
+
+def wgrad_tn(lib, check, dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, n_in: int, sms: int, stream) -> torch.Tensor:
+    """dW fp32 [n_out, n_in] = dy[rows, n_out]^T x[rows, n_in] on `s3od_op_wgrad_gemm_f32`: bf16 operands exactly as they lie in memory
+    (one row per token / pixel), nothing transposed.  n_out % 64 == 0 and n_in % 64 == 0."""
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
+    splits = wgrad_plan_tn(n_out, n_in, rows, sms)
+    c = torch.empty(n_out, n_in, dtype=torch.float32, device=dy.device)
+    ws = torch.empty(splits * n_out * n_in, dtype=torch.float32, device=dy.device) if splits > 1 else None
+    check(lib.s3od_op_wgrad_gemm_f32(dy.data_ptr(), n_out, x.data_ptr(), n_in, c.data_ptr(), n_out, n_in, rows, splits,
+                                     ws.data_ptr() if ws is not None else None, stream), "s3od_op_wgrad_gemm_f32")
+    return c
 
 
 class EncoderBlockStep:
@@ -530,8 +550,14 @@ class EncoderBlockStep:
         return c
 
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, rows: int, n_out: int, n_in: int) -> torch.Tensor:
-        """dW fp32 [n_out, n_in] = dy[rows, n_out]^T x[rows, n_in]: both operands transposed (tokens become the zero-padded contraction
-        dimension) and the contraction split across the SMs (`wgrad_plan`)."""
+        """dW fp32 [n_out, n_in] = dy[rows, n_out]^T x[rows, n_in] with the contraction split across the SMs: on the transpose-free
+        kernel (`wgrad_tn`) when both widths are multiples of 64, else through transposed, zero-padded copies (`wgrad_plan`)."""
+        if n_out % 64 == 0 and n_in % 64 == 0:
+            if dy.dtype != torch.bfloat16:
+                dy = self._scale_cast(dy)
+            if x.dtype != torch.bfloat16:
+                x = self._scale_cast(x)
+            return wgrad_tn(self.lib, self._ck, dy.contiguous(), x.contiguous(), rows, n_out, n_in, self.sms, self._st())
         splits, kpad = wgrad_plan(n_out, n_in, rows, self.sms)
         a = self._transpose(dy, 1, rows, n_out, kpad)
         b = self._transpose(x, 1, rows, n_in, kpad)

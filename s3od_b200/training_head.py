@@ -20,7 +20,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import torch
 
 from .arch import ArchSpec
-from .training import _bind_block, _check, _lib, wgrad_plan
+from .training import _bind_block, _check, _lib, wgrad_plan, wgrad_tn
 
 
 def _bind_head(lib):
@@ -74,8 +74,12 @@ class _Ops:
         return c
 
     def wgrad(self, dy, x, rows, n_out, n_in, n_in_padded):
-        """dW fp32 [n_out, n_in_padded] = dy[rows, n_out]^T x[rows, n_in] with the contraction over the rows (pixels) split across the
-        SMs (`training.wgrad_plan`); columns >= n_in are zero."""
+        """dW fp32 [n_out, n_in] = dy[rows, n_out]^T x[rows, n_in] with the contraction over the rows (pixels) split across the SMs: the
+        transpose-free kernel (`training.wgrad_tn`) when both widths are multiples of 64, else transposed zero-padded copies."""
+        if n_out % 64 == 0 and n_in % 64 == 0:
+            dyb = dy if dy.dtype == torch.bfloat16 else self.cast(dy)
+            xb = x if x.dtype == torch.bfloat16 else self.cast(x)
+            return wgrad_tn(self.lib, self.ck, dyb.contiguous(), xb.contiguous(), rows, n_out, n_in, self.sms, self.st())
         splits, kpad = wgrad_plan(n_out, n_in_padded, rows, self.sms)
         a = self.transpose_into(dy, rows, n_out, n_out, kpad)
         b = self.transpose_into(x, rows, n_in, n_in_padded, kpad)
@@ -83,7 +87,7 @@ class _Ops:
         ws = self.f32(splits * n_out * n_in_padded) if splits > 1 else None
         self.ck(self.lib.s3od_op_gemm_f32_splitk(a.data_ptr(), b.data_ptr(), c.data_ptr(), n_out, n_in_padded, kpad, splits,
                                                  ws.data_ptr() if ws is not None else None, self.st()), "s3od_op_gemm_f32_splitk")
-        return c
+        return self.copy_cols(c, n_out, n_in, n_in_padded) if n_in_padded != n_in else c
 
     def transpose_into(self, t, rows, cols, out_rows, rows_padded):
         """t [rows][cols] (fp32 or bf16, dense) -> zeroed bf16 [out_rows >= cols][rows_padded] holding t^T in its first `cols` rows."""
@@ -208,7 +212,7 @@ class _Conv:
         dy = dy.reshape(P, self.cout).contiguous()
         if self.bias is not None:
             emit(self.name + ".bias", o.colsum(dy))
-        dW = o.copy_cols(o.wgrad(dy, cols, P, self.cout, self.K, self.Kp), self.cout, self.K, self.Kp)      # dY^T cols, pixels as the contraction
+        dW = o.wgrad(dy, cols, P, self.cout, self.K, self.Kp)                          # dY^T cols, pixels as the contraction
         emit(self.name + ".weight", dW.view(self.cout, self.k, self.k, self.cin).permute(0, 3, 1, 2).contiguous())
         if not need_dx:
             return None
