@@ -272,6 +272,11 @@ int s3od_train_small_linear(const float* d_a, const float* d_w, const float* d_b
                             s3od_stream stream);
 int s3od_train_small_linear_backward(const float* d_dout, const float* d_a, const float* d_w, float* d_da, float* d_dw, float* d_dbias, long long m, int n,
                                      int k, int lda, int group_step, s3od_stream stream);
+/* the same with a workspace of s3od_train_small_linear_workspace_bytes(m, n, k): the grouped mask heads at full resolution (k = 32,
+   n = 1 or 3, m >= 32768 rows) then take a two-stage weight gradient (whole-row loads, per-block partial sums, fixed-order final sum) */
+size_t s3od_train_small_linear_workspace_bytes(long long m, int n, int k);
+int s3od_train_small_linear_backward_ws(const float* d_dout, const float* d_a, const float* d_w, float* d_da, float* d_dw, float* d_dbias, long long m,
+                                        int n, int k, int lda, int group_step, void* d_workspace, s3od_stream stream);
 
 /* ---- kernel-level entry points used by tests/ and profiles/ (same kernels the forward pass launches) ---------- */
 /* C[M,N] fp32 = A[M,K] bf16 * B[N,K]^T bf16 */

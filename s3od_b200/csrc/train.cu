@@ -426,11 +426,33 @@ int s3od_train_small_linear(const float* d_a, const float* d_w, const float* d_b
   small_linear_kernel<<<grid_for(m * n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, d_w, d_bias, d_out, m, n, k, lda, group_step);
   S3OD_TRAIN_DONE("small_linear_kernel");
 }
+static constexpr int kSmallWgradRows = 8192;        // rows per block of the two-stage weight gradient
+static bool small_wgrad_two_stage(long long m, int n, int k, int lda, int group_step) {
+  return m >= 4 * kSmallWgradRows && k == 32 && (n == 3 || n == 1) && group_step == k && lda % 4 == 0;
+}
+size_t s3od_train_small_linear_workspace_bytes(long long m, int n, int k) {
+  return static_cast<size_t>((m + kSmallWgradRows - 1) / kSmallWgradRows) * n * (k + 1) * sizeof(float);
+}
+
 int s3od_train_small_linear_backward(const float* d_dout, const float* d_a, const float* d_w, float* d_da, float* d_dw, float* d_dbias, long long m, int n,
                                      int k, int lda, int group_step, s3od_stream stream) {
+  return s3od_train_small_linear_backward_ws(d_dout, d_a, d_w, d_da, d_dw, d_dbias, m, n, k, lda, group_step, nullptr, stream);
+}
+
+int s3od_train_small_linear_backward_ws(const float* d_dout, const float* d_a, const float* d_w, float* d_da, float* d_dw, float* d_dbias, long long m,
+                                        int n, int k, int lda, int group_step, void* d_workspace, s3od_stream stream) {
   if (d_dout == nullptr || d_a == nullptr || d_w == nullptr || d_da == nullptr || d_dw == nullptr) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_small_linear_backward");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   small_linear_dgrad_kernel<<<grid_for(m * (group_step ? static_cast<long long>(n) * k : k)), 256, 0, st>>>(d_dout, d_w, d_da, m, n, k, lda, group_step);
+  if (d_workspace != nullptr && small_wgrad_two_stage(m, n, k, lda, group_step) && (reinterpret_cast<uintptr_t>(d_a) & 15) == 0) {
+    // grouped mask heads at full resolution: whole-row loads, per-block partial sums, fixed-order final reduce
+    const int nblk = static_cast<int>((m + kSmallWgradRows - 1) / kSmallWgradRows);
+    float* part = static_cast<float*>(d_workspace);
+    if (n == 3) small_linear_wgrad_rows_kernel<3, 32><<<nblk, 256, 0, st>>>(d_dout, d_a, part, m, lda, kSmallWgradRows);
+    else small_linear_wgrad_rows_kernel<1, 32><<<nblk, 256, 0, st>>>(d_dout, d_a, part, m, lda, kSmallWgradRows);
+    small_linear_wgrad_final_kernel<<<(n * (k + 1) + 31) / 32, 256, 0, st>>>(part, nblk, n, k, d_dw, d_dbias);
+    S3OD_TRAIN_DONE("small_linear backward kernels (two-stage weight gradient)");
+  }
   small_linear_wgrad_kernel<<<n * (k + 1), 256, 0, st>>>(d_dout, d_a, d_dw, d_dbias, m, n, k, lda, group_step);
   S3OD_TRAIN_DONE("small_linear backward kernels");
 }

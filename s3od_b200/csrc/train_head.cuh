@@ -283,4 +283,71 @@ __global__ void __launch_bounds__(256) small_linear_wgrad_kernel(const float* __
   }
 }
 
+// The same weight / bias gradient for the grouped mask heads at full resolution (M = millions of pixels, NN masks x KK channels,
+// a[m][n * KK + k]): the kernel above walks all M rows once per (n, k) with 4-byte strided loads; here every thread reads whole
+// rows (16-byte loads) and keeps all NN * (KK + 1) sums in registers, a block covers `rows_per_block` rows and writes its partial
+// sums, and a second kernel adds the partials in a fixed order.
+template <int NN, int KK>
+__global__ void __launch_bounds__(256) small_linear_wgrad_rows_kernel(const float* __restrict__ dout, const float* __restrict__ a,
+                                                                      float* __restrict__ partial, long long M, int lda, int rows_per_block) {
+  constexpr int C = NN * (KK + 1);
+  __shared__ float red[8][C];
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  for (long long m = r0 + threadIdx.x; m < r1; m += 256) {
+    const float4* ar = reinterpret_cast<const float4*>(a + m * lda);
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+      const float d = dout[m * NN + n];
+#pragma unroll
+      for (int k4 = 0; k4 < KK / 4; ++k4) {
+        const float4 v = __ldg(ar + n * (KK / 4) + k4);
+        acc[n * (KK + 1) + 4 * k4 + 0] += d * v.x;
+        acc[n * (KK + 1) + 4 * k4 + 1] += d * v.y;
+        acc[n * (KK + 1) + 4 * k4 + 2] += d * v.z;
+        acc[n * (KK + 1) + 4 * k4 + 3] += d * v.w;
+      }
+      acc[n * (KK + 1) + KK] += d;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    partial[static_cast<long long>(blockIdx.x) * C + threadIdx.x] = v;
+  }
+}
+// sums the partials (column c = n * (K + 1) + k; k == K is the bias gradient); block = 32 columns x 8 partial lanes
+__global__ void __launch_bounds__(256) small_linear_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int N, int K, float* __restrict__ dw,
+                                                                       float* __restrict__ dbias) {
+  __shared__ float red[8][33];
+  const int C = N * (K + 1);
+  const int cl = threadIdx.x & 31, jl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.0f;
+  if (c < C)
+    for (int j = jl; j < nblk; j += 8) s += partial[static_cast<long long>(j) * C + c];
+  red[jl][cl] = s;
+  __syncthreads();
+  if (jl == 0 && c < C) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) s += red[j][cl];
+    const int n = c / (K + 1), k = c % (K + 1);
+    if (k < K) dw[static_cast<long long>(n) * K + k] = s;
+    else if (dbias != nullptr) dbias[n] = s;
+  }
+}
+
 }  // namespace s3od

@@ -42,6 +42,9 @@ def _bind_head(lib):
         lib.s3od_train_upsample2x_backward.argtypes = [vp, vp, ci, ci, ci, ci, vp]
         lib.s3od_train_small_linear.argtypes = [vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
         lib.s3od_train_small_linear_backward.argtypes = [vp, vp, vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
+        lib.s3od_train_small_linear_backward_ws.argtypes = [vp, vp, vp, vp, vp, vp, ll, ci, ci, ci, ci, vp, vp]
+        lib.s3od_train_small_linear_workspace_bytes.argtypes = [ll, ci, ci]
+        lib.s3od_train_small_linear_workspace_bytes.restype = ctypes.c_size_t
         lib.s3od_train_cast_bf16_f32.argtypes = [vp, vp, ll, vp]
         lib._head_bound = True
     return lib
@@ -453,8 +456,10 @@ class HeadTrainer:
             dlog = d_masks.to(o.dev, torch.float32).permute(0, 2, 3, 1).contiguous().view(P, K)
             dr = o.f32(P, K * self.inter)
             dw2, db2 = o.f32(K, self.inter), o.f32(K)
-            o.ck(o.lib.s3od_train_small_linear_backward(dlog.data_ptr(), s["r"].data_ptr(), self.w2.data_ptr(), dr.data_ptr(), dw2.data_ptr(), db2.data_ptr(),
-                                                        P, K, self.inter, K * self.inter, self.inter, o.st()), "s3od_train_small_linear_backward")
+            ws = torch.empty(o.lib.s3od_train_small_linear_workspace_bytes(P, K, self.inter), dtype=torch.uint8, device=o.dev)
+            o.ck(o.lib.s3od_train_small_linear_backward_ws(dlog.data_ptr(), s["r"].data_ptr(), self.w2.data_ptr(), dr.data_ptr(), dw2.data_ptr(), db2.data_ptr(),
+                                                           P, K, self.inter, K * self.inter, self.inter, ws.data_ptr(), o.st()),
+                 "s3od_train_small_linear_backward_ws")
             m = self.mask_prefix
             for k in range(K):
                 em(m + f"mask_heads.{k}.2.bias", db2[k:k + 1].clone())

@@ -185,6 +185,34 @@ def test_training_glue_kernels_transpose_colsum_splitk(vitb_sd):
         assert float((got - ref).abs().max()) <= 2e-3 * math.sqrt(rows), (rows, n_out, n_in)
 
 
+@pytest.mark.parametrize("n", [3, 1])
+def test_grouped_mask_head_backward_two_stage(n):
+    """s3od_train_small_linear_backward_ws at a full-resolution row count (two-stage weight gradient) against torch and against
+    the one-stage kernel (no workspace): logits[m][j] = sum_k r[m][j*32 + k] w[j][k] + b[j]  (mask_heads, model.py:421-467)."""
+    import ctypes
+    from s3od_b200.training_head import _Ops
+    o = _Ops("cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(3 + n)
+    m, k = 70001, 32
+    r = torch.randn(m, n * k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g)
+    dlog = torch.randn(m, n, device="cuda", generator=g)
+    outs = []
+    for use_ws in (True, False):
+        dr, dw, db = torch.empty_like(r), torch.empty_like(w), torch.empty(n, device="cuda")
+        ws = torch.empty(o.lib.s3od_train_small_linear_workspace_bytes(m, n, k), dtype=torch.uint8, device="cuda") if use_ws else None
+        o.ck(o.lib.s3od_train_small_linear_backward_ws(dlog.data_ptr(), r.data_ptr(), w.data_ptr(), dr.data_ptr(), dw.data_ptr(), db.data_ptr(), m, n, k,
+                                                       n * k, k, ws.data_ptr() if use_ws else None, o.st()), "small_linear_backward_ws")
+        outs.append((dr, dw, db))
+    ref_dw = torch.einsum("mj,mjk->jk", dlog.double(), r.view(m, n, k).double()).float()
+    ref_db = dlog.double().sum(0).float()
+    ref_dr = (dlog.unsqueeze(2) * w.unsqueeze(0)).reshape(m, n * k)
+    for dr, dw, db in outs:
+        assert float((dw - ref_dw).abs().max()) <= 2e-4 * math.sqrt(m)
+        assert float((db - ref_db).abs().max()) <= 2e-4 * math.sqrt(m)
+        assert torch.equal(dr, ref_dr)
+
+
 @pytest.mark.parametrize("B,H,N", [(1, 2, 261), (2, 3, 389), (1, 1, 4101), (1, 12, 1029)])
 def test_fused_attention_forward_backward_matches_autograd(capsys, B, H, N):
     """csrc/attention.cuh (log-sum-exp output) + csrc/attention_bwd.cuh against torch.autograd of softmax(Q K^T) V in fp32 on the
