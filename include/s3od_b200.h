@@ -294,6 +294,12 @@ int s3od_op_gemm_f32_splitk(const void* d_a, const void* d_b, float* d_c, int M,
    splits > 1 need d_workspace of splits * M * N floats. */
 int s3od_op_wgrad_gemm_f32(const void* d_a, int lda, const void* d_b, int ldb, float* d_c, int M, int N, int K, int splits, float* d_workspace,
                            s3od_stream stream);
+/* Weight gradient of a 3x3 / stride 1 / pad 1 convolution straight from the NHWC tensors (the same kernel with its B operand loaded
+   as the nine shifted windows of x - no im2col matrix): dw fp32 [cout][(ky*3 + kx)*cin + ci] = sum over pixels of
+   dy[b,y,x,co] * x[b,y+ky-1,x+kx-1,ci]; dy bf16 (batch,h,w,cout), x bf16 (batch,h,w,cin); cin % 64 == 0, cout % 64 == 0.
+   splits > 1 need d_workspace of splits * cout * 9 * cin floats. */
+int s3od_op_conv3x3_wgrad_f32(const void* d_dy, const void* d_x, float* d_dw, int batch, int h, int w, int cin, int cout, int splits,
+                              float* d_workspace, s3od_stream stream);
 /* y bf16 = LayerNorm(x fp32) */
 int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void* d_y, int M, int D, float eps,
                       s3od_stream stream);

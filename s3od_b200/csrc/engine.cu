@@ -1196,6 +1196,46 @@ int s3od_op_wgrad_gemm_f32(const void* d_a, int lda, const void* d_b, int ldb, f
   return S3OD_OK;
 }
 
+int s3od_op_conv3x3_wgrad_f32(const void* d_dy, const void* d_x, float* d_dw, int batch, int h, int w, int cin, int cout, int splits,
+                              float* d_workspace, s3od_stream stream) {
+  if (d_dy == nullptr || d_x == nullptr || d_dw == nullptr || batch < 1 || h < 1 || w < 1 || cin < 64 || cout < 64 || cin % 64 != 0 || cout % 64 != 0 ||
+      (reinterpret_cast<uintptr_t>(d_dy) & 15) != 0 || (reinterpret_cast<uintptr_t>(d_x) & 15) != 0 || (reinterpret_cast<uintptr_t>(d_dw) & 15) != 0)
+    return fail(S3OD_ERR_ARG, "s3od_op_conv3x3_wgrad_f32 needs cin % 64 == 0, cout % 64 == 0 and 16-byte aligned buffers");
+  GemmTnParams p{};
+  p.conv = 1;
+  p.M = cout; p.N = 9 * cin;
+  p.m_tiles = (p.M + 127) / 128; p.n_tiles = (p.N + 255) / 256;
+  p.patches_w = (w + 15) / 16; p.patches_h = (h + 3) / 4; p.cin_blocks = cin / 64;
+  p.k_blocks = batch * p.patches_h * p.patches_w;
+  if (splits < 1) splits = 1;
+  if (splits > p.k_blocks) splits = p.k_blocks;
+  p.k_blocks_per_split = (p.k_blocks + splits - 1) / splits;
+  p.splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  if (p.splits > 1 && (d_workspace == nullptr || (reinterpret_cast<uintptr_t>(d_workspace) & 15) != 0))
+    return fail(S3OD_ERR_ARG, "s3od_op_conv3x3_wgrad_f32: splits > 1 need a 16-byte aligned workspace of splits * cout * 9 * cin floats");
+  p.out = p.splits > 1 ? d_workspace : d_dw;
+  const uint64_t W = w, H = h, B = batch;
+  const uint64_t da[5] = {64, W, H, B, (uint64_t)(cout / 64)};
+  const uint64_t sa[4] = {(uint64_t)cout * 2, W * cout * 2, H * W * cout * 2, 128};
+  const uint32_t ba[5] = {64, 16, 4, 1, 2};
+  const uint64_t db[4] = {(uint64_t)cin, W, H, B};
+  const uint64_t sb[3] = {(uint64_t)cin * 2, W * cin * 2, H * W * cin * 2};
+  const uint32_t bb[4] = {64, 16, 4, 1};
+  if (!make_tmap(&p.tma_a, d_dy, 5, da, sa, ba) || !make_tmap(&p.tma_b, d_x, 4, db, sb, bb)) return S3OD_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(launch_gemm_tn(p, sms, st));
+  if (p.splits > 1) {
+    const long long n4 = static_cast<long long>(p.M) * p.N / 4;
+    const int grid = static_cast<int>(std::min<long long>((n4 + 255) / 256, 148LL * 8));
+    sum_k_splits_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(d_workspace), p.splits, n4, reinterpret_cast<float4*>(d_dw));
+    CK(cudaGetLastError());
+  }
+  return S3OD_OK;
+}
+
 int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void* d_y, int M, int D, float eps, s3od_stream stream) {
   CK(launch_layernorm(const_cast<float*>(d_x), nullptr, d_w, d_b, static_cast<bf16*>(d_y), nullptr, M, M, D, eps,
                       static_cast<cudaStream_t>(stream)));

@@ -83,9 +83,23 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
         k_range(item, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], kTnABytes + kTnBBytes);
-          tma_load_3d(sA + stage * kTnABytes, &p.tma_a, &full[stage], 0, kb * 64, m_atom0);
-          tma_load_3d(sB + stage * kTnBBytes, &p.tma_b, &full[stage], 0, kb * 64, n_atom0);
+          if (p.conv == 0) {
+            mbar_arrive_expect_tx(&full[stage], kTnABytes + kTnBBytes);
+            tma_load_3d(sA + stage * kTnABytes, &p.tma_a, &full[stage], 0, kb * 64, m_atom0);
+            tma_load_3d(sB + stage * kTnBBytes, &p.tma_b, &full[stage], 0, kb * 64, n_atom0);
+          } else {
+            // k-block = the 4 x 16 pixel patch (h0, w0) of image b; B atom j = (tap, 64-channel block) of the 3x3 window
+            const int per_img = p.patches_h * p.patches_w;
+            const int b = kb / per_img, r = kb % per_img;
+            const int h0 = (r / p.patches_w) * 4, w0 = (r % p.patches_w) * 16;
+            const int n_atoms = min(4, 9 * p.cin_blocks - n_atom0);       // atoms past N stay stale: their columns are never stored
+            mbar_arrive_expect_tx(&full[stage], kTnABytes + n_atoms * 8192);
+            tma_load_5d(sA + stage * kTnABytes, &p.tma_a, &full[stage], 0, w0, h0, b, m_atom0);
+            for (int j = 0; j < n_atoms; ++j) {
+              const int tap = (n_atom0 + j) / p.cin_blocks, cb = (n_atom0 + j) % p.cin_blocks;
+              tma_load_4d(sB + stage * kTnBBytes + j * 8192, &p.tma_b, &full[stage], cb * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, b);
+            }
+          }
           if (++stage == kTnStages) {
             stage = 0;
             phase ^= 1;

@@ -69,6 +69,12 @@ struct GemmTnParams {
   int k_blocks;            // ceil(K / 64)
   int k_blocks_per_split;
   int splits;
+  // conv = 1: weight gradient of a 3x3 / stride 1 / pad 1 convolution straight from the NHWC tensors (no im2col): a k-block is a
+  // 4 x 16 pixel patch; tma_a = dY as (64 channels, W, H, B, cout / 64) box (64, 16, 4, 1, 2); tma_b = X as (cin, W, H, B) box
+  // (64, 16, 4, 1), loaded once per atom at the tap's shifted coordinates (the TMA unit zero-fills outside the image);
+  // N = 9 * cin, column n = tap * cin + ci.
+  int conv;
+  int patches_w, patches_h, cin_blocks;
 };
 
 }  // namespace s3od

@@ -20,7 +20,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import torch
 
 from .arch import ArchSpec
-from .training import _bind_block, _check, _lib, wgrad_plan, wgrad_tn
+from .training import _bind_block, _check, _lib, wgrad_plan, wgrad_plan_tn, wgrad_tn
 
 
 def _bind_head(lib):
@@ -42,6 +42,7 @@ def _bind_head(lib):
         lib.s3od_train_upsample2x_backward.argtypes = [vp, vp, ci, ci, ci, ci, vp]
         lib.s3od_train_small_linear.argtypes = [vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
         lib.s3od_train_small_linear_backward.argtypes = [vp, vp, vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
+        lib.s3od_op_conv3x3_wgrad_f32.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
         lib.s3od_train_small_linear_backward_ws.argtypes = [vp, vp, vp, vp, vp, vp, ll, ci, ci, ci, ci, vp, vp]
         lib.s3od_train_small_linear_workspace_bytes.argtypes = [ll, ci, ci]
         lib.s3od_train_small_linear_workspace_bytes.restype = ctypes.c_size_t
@@ -91,6 +92,15 @@ class _Ops:
         self.ck(self.lib.s3od_op_gemm_f32_splitk(a.data_ptr(), b.data_ptr(), c.data_ptr(), n_out, n_in_padded, kpad, splits,
                                                  ws.data_ptr() if ws is not None else None, self.st()), "s3od_op_gemm_f32_splitk")
         return self.copy_cols(c, n_out, n_in, n_in_padded) if n_in_padded != n_in else c
+
+    def conv3x3_wgrad(self, dyb, xb, B, H, W, cin, cout):
+        """dW fp32 [cout, 9 * cin] (tap-major) of a 3x3 / stride 1 / pad 1 convolution from bf16 NHWC dy and x (`s3od_op_conv3x3_wgrad_f32`)."""
+        splits = wgrad_plan_tn(cout, 9 * cin, B * H * W, self.sms)
+        dw = self.f32(cout, 9 * cin)
+        ws = self.f32(splits * cout * 9 * cin) if splits > 1 else None
+        self.ck(self.lib.s3od_op_conv3x3_wgrad_f32(dyb.data_ptr(), xb.data_ptr(), dw.data_ptr(), B, H, W, cin, cout, splits,
+                                                   ws.data_ptr() if ws is not None else None, self.st()), "s3od_op_conv3x3_wgrad_f32")
+        return dw
 
     def transpose_into(self, t, rows, cols, out_rows, rows_padded):
         """t [rows][cols] (fp32 or bf16, dense) -> zeroed bf16 [out_rows >= cols][rows_padded] holding t^T in its first `cols` rows."""
@@ -180,6 +190,7 @@ class _Conv:
         self.rows64 = s3 and self.cin == 64 and self.cout == 64               # needs W % 128 == 0 at run time
         self.fast_fwd = s3 and self.cout % 256 == 0
         self.fast_dgrad = s3 and self.cin % 256 == 0 and self.cout % 64 == 0
+        self.implicit_wgrad = s3 and self.cout % 64 == 0                      # s3od_op_conv3x3_wgrad_f32: no im2col matrix for the weight gradient
         if self.fast_dgrad or self.rows64:                                    # w_d[ci][(ky', kx') * cout + co] = w[co][ci][2 - ky'][2 - kx']
             self.wd = w.detach().to(dev, torch.float32).flip(2, 3).permute(1, 2, 3, 0).reshape(self.cin, 9 * self.cout).to(torch.bfloat16).contiguous()
 
@@ -203,24 +214,29 @@ class _Conv:
         cols = self._cols(x, B, H, W, P)
         out = o.gemm(cols, self.wf, P, self.Np, self.K)
         y = o.copy_cols(out, P, self.cout, self.Np, self.bias)
-        self.ctx = (cols, None, (B, H, W), (OH, OW))
+        self.ctx = (None, x, (B, H, W), (OH, OW)) if self.implicit_wgrad else (cols, None, (B, H, W), (OH, OW))
         return y.view(B, OH, OW, self.cout)
 
     def backward(self, dy: torch.Tensor, emit: Emit, need_dx: bool = True) -> Optional[torch.Tensor]:
         o = self.ops
         cols, x_saved, (B, H, W), (OH, OW) = self.ctx
         P = B * OH * OW
-        if cols is None:
-            cols = self._cols(x_saved, B, H, W, P)
         dy = dy.reshape(P, self.cout).contiguous()
         if self.bias is not None:
             emit(self.name + ".bias", o.colsum(dy))
-        dW = o.wgrad(dy, cols, P, self.cout, self.K, self.Kp)                          # dY^T cols, pixels as the contraction
+        dyb = None
+        if self.implicit_wgrad:
+            dyb = o.cast(dy)
+            dW = o.conv3x3_wgrad(dyb, o.cast(x_saved), B, H, W, self.cin, self.cout)     # the nine shifted windows of x are read by TMA
+        else:
+            if cols is None:
+                cols = self._cols(x_saved, B, H, W, P)
+            dW = o.wgrad(dy, cols, P, self.cout, self.K, self.Kp)                      # dY^T cols, pixels as the contraction
         emit(self.name + ".weight", dW.view(self.cout, self.k, self.k, self.cin).permute(0, 3, 1, 2).contiguous())
         if not need_dx:
             return None
         if self.fast_dgrad or (self.rows64 and W % 128 == 0):
-            dxb = o.conv3x3(o.cast(dy).view(B, H, W, self.cout), self.wd, None, B, H, W, self.cout, self.cin)
+            dxb = o.conv3x3((dyb if dyb is not None else o.cast(dy)).view(B, H, W, self.cout), self.wd, None, B, H, W, self.cout, self.cin)
             return o.to_f32(dxb)
         dyb = torch.zeros(P, self.Kc, dtype=torch.bfloat16, device=o.dev)
         dyb[:, :self.cout] = o.cast(dy)                                                  # zero padded to the 64-granular contraction

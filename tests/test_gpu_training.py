@@ -185,6 +185,30 @@ def test_training_glue_kernels_transpose_colsum_splitk(vitb_sd):
         assert float((got - ref).abs().max()) <= 2e-3 * math.sqrt(rows), (rows, n_out, n_in)
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 8, 8, 64, 64), (1, 37, 50, 128, 64), (2, 64, 64, 256, 128), (1, 5, 3, 64, 192), (1, 128, 128, 64, 64)])
+def test_implicit_conv_weight_gradient(B, H, W, cin, cout):
+    """s3od_op_conv3x3_wgrad_f32 (no im2col: TMA reads the nine shifted windows of x) against torch's conv2d weight gradient in
+    fp32 on the same bf16-rounded dy and x; ragged maps exercise the zero fill at the image border and in partial 4 x 16 patches."""
+    from s3od_b200.training_head import _Ops
+    o = _Ops("cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(B * H + cin)
+    x = torch.randn(B, H, W, cin, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(B, H, W, cout, device="cuda", generator=g).to(torch.bfloat16)
+    dw = o.conv3x3_wgrad(dy, x, B, H, W, cin, cout)                                   # [cout][(ky*3 + kx)*cin + ci]
+    xr = x.float().permute(0, 3, 1, 2).contiguous()
+    w0 = torch.zeros(cout, cin, 3, 3, device="cuda", requires_grad=True)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        y = torch.nn.functional.conv2d(xr, w0, padding=1)
+        (y * dy.float().permute(0, 3, 1, 2)).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    ref = w0.grad.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    err = float((dw - ref).abs().max())
+    assert err <= 2e-3 * math.sqrt(B * H * W), (err, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("n", [3, 1])
 def test_grouped_mask_head_backward_two_stage(n):
     """s3od_train_small_linear_backward_ws at a full-resolution row count (two-stage weight gradient) against torch and against
