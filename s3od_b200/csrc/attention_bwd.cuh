@@ -14,8 +14,10 @@
 //                               S^T = X U^T, dP^T = Y W^T, L / Delta per COLUMN; acc_p += P^T W -> dV,  acc_ds += dA^T U -> dK
 // so the second launch works on the transposed problem and nothing is ever transposed through shared memory.  S and dP are
 // computed twice (7 instead of 5 MMAs per tile pair) - the price of two kernels without atomics on dQ.
-// Warps 0..7: 16 rows of a TMEM lane quarter each (four threads share a row, 24 of the 96 columns each - the tcgen05.ld
-// .16x256b layout of the forward kernel); warp 8: MMA issuer; warp 9: TMA producer (X, Y once; U, W through a ring).
+// Warps 0..15: 16 rows of a TMEM lane quarter and one half (48) of the step's 96 columns each (four threads share a row, 12 columns
+// each - the tcgen05.ld .16x256b layout of the forward kernel; with 8 warps = one per 16 rows the exponential phase of a step took 2.3 x
+// its SFU time, the one CTA per SM has nothing else to hide latency with); warp 16: MMA issuer; warp 17: TMA producer (X, Y once;
+// U, W through a ring).
 // Tensor memory (512 columns): S 0..95 | dP 96..191 | P buffers 192, 240 | dA buffers 288, 336 | acc_ds 384..447 | acc_p 448..511.
 // All operands are [B*H, npad, 64] bf16 with npad % 384 == 0 and zero rows behind the sequence; L is +inf there, which makes
 // P (and with it dA) exactly 0 for padding queries; padding keys have K = 0 rows, so whatever dA holds there adds nothing to dQ,
@@ -25,12 +27,36 @@
 
 namespace s3od {
 
-constexpr int kAttnBwdThreads = 320;
+constexpr int kAttnBwdSoftmaxWarps = 16;
+constexpr int kAttnBwdThreads = 32 * (kAttnBwdSoftmaxWarps + 2);
 constexpr int kAttnBwdStages = 4;
 constexpr int kAttnBwdXBytes = 128 * 128;          // 128 rows x 64 bf16
 constexpr int kAttnBwdUBytes = kAttnKvTile * 128;  // 96 rows x 64 bf16
 constexpr int kAttnBwdSmemBytes = 2 * kAttnBwdXBytes + kAttnBwdStages * 2 * kAttnBwdUBytes + 256 + 1024;
 static_assert(kAttnBwdSmemBytes + 1024 <= 227 * 1024, "attention backward shared memory");
+
+// 16-column (x2) forms of the forward kernel's tcgen05.ld / st helpers
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_ld_16x256_x2(uint32_t taddr, uint32_t (&r)[NR]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]), "=r"(r[OFF + 6]),
+                 "=r"(r[OFF + 7])
+               : "r"(taddr));
+}
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_st_16x128_x2(uint32_t taddr, const uint32_t (&r)[NR]) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[OFF + 0]), "r"(r[OFF + 1]), "r"(r[OFF + 2]),
+               "r"(r[OFF + 3])
+               : "memory");
+}
+template <int OFF, int NR>
+S3OD_DEVICE void tmem_ld_wait8(uint32_t (&r)[NR]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[OFF + 0]), "+r"(r[OFF + 1]), "+r"(r[OFF + 2]), "+r"(r[OFF + 3]), "+r"(r[OFF + 4]), "+r"(r[OFF + 5]), "+r"(r[OFF + 6]),
+                 "+r"(r[OFF + 7])
+               :
+               : "memory");
+}
 
 template <bool kColStats>
 __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
@@ -44,14 +70,14 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
   uint64_t* u_full = bars + 1;                        // kAttnBwdStages
   uint64_t* u_empty = u_full + kAttnBwdStages;        // the accumulate MMAs that read the stage have completed
   uint64_t* s_full = u_empty + kAttnBwdStages;        // S and dP of the step are in TMEM
-  uint64_t* s_empty = s_full + 1;                     // 256 arrivals: both are in registers
-  uint64_t* p_full = s_empty + 1;                     // [2] 256 arrivals: P / dA buffer j & 1 written
+  uint64_t* s_empty = s_full + 1;                     // one arrival per softmax thread: both are in registers
+  uint64_t* p_full = s_empty + 1;                     // [2] one arrival per softmax thread: P / dA buffer j & 1 written
   uint64_t* p_empty = p_full + 2;                     // [2] the accumulate MMAs of the step have completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kWarpMma = 8, kWarpTma = 9;
+  constexpr int kWarpMma = kAttnBwdSoftmaxWarps, kWarpTma = kAttnBwdSoftmaxWarps + 1;
   const int tiles = p.npad / kAttnTile;
   const int tile = static_cast<int>(blockIdx.x) % tiles;           // tiles of one (image, head) adjacent: they share U / W in L2
   const int bh = static_cast<int>(blockIdx.x) / tiles;
@@ -71,9 +97,9 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
         mbar_init(&u_empty[i], 1);
       }
       mbar_init(s_full, 1);
-      mbar_init(s_empty, 256);
-      mbar_init(&p_full[0], 256);
-      mbar_init(&p_full[1], 256);
+      mbar_init(s_empty, 32 * kAttnBwdSoftmaxWarps);
+      mbar_init(&p_full[0], 32 * kAttnBwdSoftmaxWarps);
+      mbar_init(&p_full[1], 32 * kAttnBwdSoftmaxWarps);
       mbar_init(&p_empty[0], 1);
       mbar_init(&p_empty[1], 1);
       fence_barrier_init();
@@ -160,9 +186,12 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
   } else {
     // ===================== P = exp2(S - L), dA = P (dP - Delta) =====================
     const int lane_base = (warp & 3) * 32 + ((warp >> 2) & 1) * 16;
+    const int col_half = warp >> 3;                    // this warp's 48 of the step's 96 columns
     const int row_a = lane_base + (lane >> 2);         // second row: row_a + 8
     const int q2 = 2 * (lane & 3);
     const uint32_t s_addr = tmem_base + (static_cast<uint32_t>(lane_base) << 16);
+    const uint32_t s_half = s_addr + 48 * col_half;    // fp32 columns of this warp
+    const uint32_t w_half = 24 * col_half;             // the same columns as packed bf16 pairs
     const float* lse = p.lse + static_cast<size_t>(bh) * p.npad;
     const float* delta = p.delta + static_cast<size_t>(bh) * p.npad;
     float nl_a = 0.0f, nl_b = 0.0f, nd_a = 0.0f, nd_b = 0.0f;       // row statistics (negated): rows row_a, row_a + 8 of the CTA's tile
@@ -172,35 +201,42 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
       nd_a = -delta[tile * kAttnTile + row_a];
       nd_b = -delta[tile * kAttnTile + row_a + 8];
     }
-    uint32_t rs[kAttnRegs], rd[kAttnRegs];
-    uint32_t wp[kAttnRegs / 2], wd[kAttnRegs / 2];
+    constexpr int kRegs = kAttnRegs / 2;               // 24 scores per thread and step: 2 rows x 12 columns
+    uint32_t rs[kRegs], rd[kRegs];
+    uint32_t wp[kRegs / 2], wd[kRegs / 2];
 
     for (int j = 0; j < T; ++j) {
       const uint32_t buf = (j & 1) * (kAttnKvTile / 2);
+      // column statistics of this step: issued before the wait so that their latency hides behind it
+      float2 l2[kRegs / 4], d2[kRegs / 4];
+      if (kColStats) {
+        const float2* lse_c = reinterpret_cast<const float2*>(lse + j * kAttnKvTile + 48 * col_half + q2);
+        const float2* delta_c = reinterpret_cast<const float2*>(delta + j * kAttnKvTile + 48 * col_half + q2);
+#pragma unroll
+        for (int i = 0; i < kRegs / 4; ++i) {
+          l2[i] = __ldg(lse_c + 4 * i);
+          d2[i] = __ldg(delta_c + 4 * i);
+        }
+      }
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      tmem_ld_16x256_x8<0>(s_addr, rs);
-      tmem_ld_16x256_x4<32>(s_addr + 64, rs);
-      tmem_ld_16x256_x8<0>(s_addr + kColDp, rd);
-      tmem_ld_16x256_x4<32>(s_addr + kColDp + 64, rd);
+      tmem_ld_16x256_x4<0>(s_half, rs);
+      tmem_ld_16x256_x2<16>(s_half + 32, rs);
+      tmem_ld_16x256_x4<0>(s_half + kColDp, rd);
+      tmem_ld_16x256_x2<16>(s_half + kColDp + 32, rd);
       tmem_ld_wait16<0>(rs);
-      tmem_ld_wait16<16>(rs);
-      tmem_ld_wait16<32>(rs);
+      tmem_ld_wait8<16>(rs);
       tmem_ld_wait16<0>(rd);
-      tmem_ld_wait16<16>(rd);
-      tmem_ld_wait16<32>(rd);
+      tmem_ld_wait8<16>(rd);
       tc_fence_before();
       mbar_arrive(s_empty);                            // the next S / dP may overwrite tensor memory
-      const float2* lse_c = reinterpret_cast<const float2*>(lse + j * kAttnKvTile + q2);
-      const float2* delta_c = reinterpret_cast<const float2*>(delta + j * kAttnKvTile + q2);
 #pragma unroll
-      for (int i = 0; i < kAttnRegs / 4; ++i) {
-        // this thread's columns 8 i + q2 + {0, 1} of rows a (registers 4 i, 4 i + 1) and b (4 i + 2, 4 i + 3)
+      for (int i = 0; i < kRegs / 4; ++i) {
+        // this thread's columns 48 col_half + 8 i + q2 + {0, 1} of rows a (registers 4 i, 4 i + 1) and b (4 i + 2, 4 i + 3)
         uint64_t nla, nlb, nda, ndb;
         if (kColStats) {
-          const float2 l2 = __ldg(lse_c + 4 * i), d2 = __ldg(delta_c + 4 * i);
-          nla = nlb = f2_pack(-l2.x, -l2.y);
-          nda = ndb = f2_pack(-d2.x, -d2.y);
+          nla = nlb = f2_pack(-l2[i].x, -l2[i].y);
+          nda = ndb = f2_pack(-d2[i].x, -d2[i].y);
         } else {
           nla = f2_pack(nl_a, nl_a);
           nlb = f2_pack(nl_b, nl_b);
@@ -223,13 +259,11 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
       }
       if (j >= 2) mbar_wait(&p_empty[j & 1], ((j - 2) >> 1) & 1);     // the accumulate MMAs of step j - 2 have read this buffer
       tc_fence_after();
-      tmem_st_16x128_x4<0>(s_addr + kColDs + buf, wd);
-      tmem_st_16x128_x4<8>(s_addr + kColDs + buf + 16, wd);
-      tmem_st_16x128_x4<16>(s_addr + kColDs + buf + 32, wd);
+      tmem_st_16x128_x4<0>(s_addr + kColDs + buf + w_half, wd);
+      tmem_st_16x128_x2<8>(s_addr + kColDs + buf + w_half + 16, wd);
       if (kColStats) {
-        tmem_st_16x128_x4<0>(s_addr + kColP + buf, wp);
-        tmem_st_16x128_x4<8>(s_addr + kColP + buf + 16, wp);
-        tmem_st_16x128_x4<16>(s_addr + kColP + buf + 32, wp);
+        tmem_st_16x128_x4<0>(s_addr + kColP + buf + w_half, wp);
+        tmem_st_16x128_x2<8>(s_addr + kColP + buf + w_half + 16, wp);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -240,14 +274,13 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
     mbar_wait(&p_empty[(T - 1) & 1], ((T - 1) >> 1) & 1);
     tc_fence_after();
     const size_t row0 = static_cast<size_t>(bh) * p.npad + tile * kAttnTile;
-    auto store_acc = [&](uint32_t col, float* out, float scale) {
-      float2* dst_a = reinterpret_cast<float2*>(out + (row0 + row_a) * 64 + q2);
-      float2* dst_b = reinterpret_cast<float2*>(out + (row0 + row_a + 8) * 64 + q2);
-      tmem_ld_16x256_x8<0>(s_addr + col, rs);
+    auto store_acc = [&](uint32_t col, float* out, float scale) {       // this warp: 32 of the accumulator's 64 columns
+      float2* dst_a = reinterpret_cast<float2*>(out + (row0 + row_a) * 64 + 32 * col_half + q2);
+      float2* dst_b = reinterpret_cast<float2*>(out + (row0 + row_a + 8) * 64 + 32 * col_half + q2);
+      tmem_ld_16x256_x4<0>(s_addr + col + 32 * col_half, rs);
       tmem_ld_wait16<0>(rs);
-      tmem_ld_wait16<16>(rs);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         dst_a[4 * i] = make_float2(__uint_as_float(rs[4 * i + 0]) * scale, __uint_as_float(rs[4 * i + 1]) * scale);
         dst_b[4 * i] = make_float2(__uint_as_float(rs[4 * i + 2]) * scale, __uint_as_float(rs[4 * i + 3]) * scale);
       }
