@@ -306,7 +306,7 @@ int s3od_op_layernorm(const float* d_x, const float* d_w, const float* d_b, void
 /* out[B*ntok, heads*64] bf16 = softmax(Q K^T) V ; q, k, v [B*heads, ntok, 64] bf16 (q pre-scaled by log2e/8) */
 int s3od_op_attention(const void* d_q, const void* d_k, const void* d_v, void* d_out, int batch, int heads, int ntok,
                       s3od_stream stream);
-/* NHWC bf16 3x3 / stride 1 / pad 1 convolution, weights [cout, 9*cin] bf16 (tap-major), fp32 bias or NULL */
+/* NHWC bf16 3x3 / stride 1 / pad 1 convolution, weights [cout, 9*cin] bf16 (tap-major), fp32 bias or NULL; cin % 64 == 0, cout % 128 == 0 */
 int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin,
                     int cout, int relu, s3od_stream stream);
 /* the same convolution for cin = 64, cout = 64 on the row-streaming kernel (w % 128 == 0) */

@@ -1308,19 +1308,21 @@ int s3od_train_attention_backward(const void* d_q, const void* d_k, const void* 
 
 int s3od_op_conv3x3(const void* d_in, const void* d_w, const float* d_bias, void* d_out, int batch, int h, int w, int cin, int cout,
                     int relu, s3od_stream stream) {
-  if (cin % 64 != 0 || cout % 256 != 0) return fail(S3OD_ERR_ARG, "s3od_op_conv3x3 needs cin % 64 == 0 and cout % 256 == 0");
+  if (cin % 64 != 0 || cout % 128 != 0) return fail(S3OD_ERR_ARG, "s3od_op_conv3x3 needs cin % 64 == 0 and cout % 128 == 0");
+  const bool wide = cout % 256 == 0;                 // 256-wide tiles, else the 128-wide configuration (the mask head's 256 -> 128)
   GemmParams<EpiConv> p{};
   if (!tmap_nhwc(&p.tma_a, d_in, batch, h, w, cin)) return S3OD_ERR_CUDA;
-  if (!tmap_matrix(&p.tma_b, d_w, cout, 9 * cin, b_box_rows<256>())) return S3OD_ERR_CUDA;
+  if (!tmap_matrix(&p.tma_b, d_w, cout, 9 * cin, wide ? b_box_rows<256>() : b_box_rows<128>())) return S3OD_ERR_CUDA;
   p.geom = geom_3x3(h, w, cin);
   p.m_tiles = batch * p.geom.tiles_h * p.geom.tiles_w;
-  p.n_tiles = cout / 256;
+  p.n_tiles = cout / (wide ? 256 : 128);
   p.num_k_blocks = 9 * cin / 64;
   p.epi = conv_epi(static_cast<bf16*>(d_out), nullptr, d_bias, nullptr, nullptr, relu, cout, h, w);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  CK((launch_gemm<256, A_CONV, EpiConv, 8>(p, sms, static_cast<cudaStream_t>(stream))));
+  if (wide) CK((launch_gemm<256, A_CONV, EpiConv, 8>(p, sms, static_cast<cudaStream_t>(stream))));
+  else CK((launch_gemm<128, A_CONV, EpiConv, 8>(p, sms, static_cast<cudaStream_t>(stream))));
   return S3OD_OK;
 }
 

@@ -184,11 +184,11 @@ class _Conv:
         self.wt[:self.K, :self.cout] = wm.t().to(torch.bfloat16)         # dgrad B operand [K (padded), cout (padded)]
         self.bias = b.detach().to(dev, torch.float32).contiguous() if b is not None else None
         # Fast paths on the inference kernels (implicit GEMM through TMA, nothing materialised) for 3x3 / stride 1 / pad 1:
-        #   forward when cout % 256 == 0 (or the 64 -> 64 row kernel), dgrad = the same convolution of dy with the flipped,
+        #   forward when cout % 128 == 0 (or the 64 -> 64 row kernel), dgrad = the same convolution of dy with the flipped,
         #   transposed weights when the ORIGINAL cin % 256 == 0 (its output channels) - the bf16 results are widened back to fp32.
         s3 = self.k == 3 and stride == 1 and pad == 1 and self.cin % 64 == 0
         self.rows64 = s3 and self.cin == 64 and self.cout == 64               # needs W % 128 == 0 at run time
-        self.fast_fwd = s3 and self.cout % 256 == 0
+        self.fast_fwd = s3 and self.cout % 128 == 0
         self.fast_dgrad = s3 and self.cin % 256 == 0 and self.cout % 64 == 0
         self.implicit_wgrad = s3 and self.cout % 64 == 0                      # s3od_op_conv3x3_wgrad_f32: no im2col matrix for the weight gradient
         if self.fast_dgrad or self.rows64:                                    # w_d[ci][(ky', kx') * cout + co] = w[co][ci][2 - ky'][2 - kx']
@@ -260,6 +260,11 @@ class _ConvT:
         self.wf = wm.to(torch.bfloat16).contiguous()                      # forward B operand [N, cin]
         self.wt = wm.t().to(torch.bfloat16).contiguous()                  # dgrad B operand [cin, N]
         self.bias = b.detach().to(dev, torch.float32).contiguous()
+        # the mask head's ConvTranspose2d(128 -> 64, k4, s2, p1): forward on the inference path's row-streaming kernel (conv_rows.cuh)
+        self.rows = self.cin == 128 and self.cout == 64 and self.k == 4 and stride == 2 and pad == 1
+        if self.rows:
+            from .weights import convt_rows_weights
+            self.wr = convt_rows_weights(w.detach().to(dev, torch.float32)).to(torch.bfloat16).contiguous()
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         o = self.ops
@@ -267,6 +272,11 @@ class _ConvT:
         OH, OW = (H - 1) * self.stride - 2 * self.pad + self.k, (W - 1) * self.stride - 2 * self.pad + self.k
         P = B * H * W
         xb = o.cast(x.reshape(P, C))
+        if self.rows and W % 128 == 0:
+            yb = torch.empty(B, OH, OW, self.cout, dtype=torch.bfloat16, device=o.dev)
+            o.ck(o.lib.s3od_op_convt_rows(xb.data_ptr(), self.wr.data_ptr(), self.bias.data_ptr(), yb.data_ptr(), B, H, W, 0, o.st()), "s3od_op_convt_rows")
+            self.ctx = (xb, (B, H, W))
+            return o.to_f32(yb)
         cols = o.gemm(xb, self.wf, P, self.N, C)
         y = o.f32(B, OH, OW, self.cout)
         o.ck(o.lib.s3od_train_convt_fold(cols.data_ptr(), self.bias.data_ptr(), y.data_ptr(), B, H, W, self.cout, self.k, self.stride, self.pad, self.N,

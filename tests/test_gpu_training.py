@@ -432,7 +432,7 @@ def test_whole_encoder_backward_matches_autograd(vitb_sd, capsys, S, B):
     assert float((params[e0:e1] - before[e0:e1]).abs().max()) > 0
 
 
-@pytest.mark.parametrize("S,B", [(64, 2), (128, 1)])
+@pytest.mark.parametrize("S,B", [(64, 2), (128, 1), (256, 1)])          # 256: the row-streaming kernels (maps of 128 columns) take part
 def test_head_train_forward_backward_matches_autograd(vitb_sd, loss_module, capsys, S, B):
     """The whole DPT head in TRAIN mode (batch-statistics BatchNorm, up-sampling before out_conv, nothing folded) + the loss:
     forward, and every parameter / tap gradient of the REAL training loss, against torch.autograd through the oracle's
