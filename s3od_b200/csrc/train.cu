@@ -13,6 +13,7 @@
 #include "train.cuh"
 #include "train_block.cuh"
 #include "train_head.cuh"
+#include "train_vec.cuh"
 
 using namespace s3od;
 
@@ -59,6 +60,12 @@ cudaError_t run_loss(const float* z, const float* q, const float* t, int B, int 
 }
 
 }  // namespace
+
+// every pointer 16-byte aligned (null counts as aligned: optional operands)
+template <class... P>
+static bool al16(P... ptrs) {
+  return (((reinterpret_cast<uintptr_t>(ptrs) & 15) == 0) && ...);
+}
 
 extern "C" {
 
@@ -168,18 +175,32 @@ int s3od_train_transpose(const void* d_in, int in_is_f32, void* d_out, int batch
 
 int s3od_train_scale_cast(const float* d_in, const float* d_colscale, void* d_out, long long n, int cols, s3od_stream stream) {
   if (d_in == nullptr || d_out == nullptr || n < 1 || cols < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_scale_cast");
+  if (n % 4 == 0 && cols % 4 == 0 && al16(d_in, d_colscale) && (reinterpret_cast<uintptr_t>(d_out) & 7) == 0) {
+    scale_cast4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(d_in), d_colscale,
+                                                                                         static_cast<uint2*>(d_out), n / 4, cols);
+    S3OD_TRAIN_DONE("scale_cast4_kernel");
+  }
   scale_cast_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, d_colscale, static_cast<bf16_t*>(d_out), n, cols);
   S3OD_TRAIN_DONE("scale_cast_kernel");
 }
 
 int s3od_train_cast_bf16_f32(const void* d_in, float* d_out, long long n, s3od_stream stream) {
   if (d_in == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_cast_bf16_f32");
+  if (n % 4 == 0 && al16(d_out) && (reinterpret_cast<uintptr_t>(d_in) & 7) == 0) {
+    cast_bf16_f32_4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint2*>(d_in), reinterpret_cast<float4*>(d_out), n / 4);
+    S3OD_TRAIN_DONE("cast_bf16_f32_4_kernel");
+  }
   cast_bf16_f32_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16_t*>(d_in), d_out, n);
   S3OD_TRAIN_DONE("cast_bf16_f32_kernel");
 }
 
 int s3od_train_residual_scale_add(const float* d_x, const float* d_y, const float* d_lambda, float* d_out, long long n, int cols, s3od_stream stream) {
   if (d_x == nullptr || d_y == nullptr || d_lambda == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_residual_scale_add");
+  if (n % 4 == 0 && cols % 4 == 0 && al16(d_x, d_y, d_lambda, d_out)) {
+    residual_scale_add4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(d_x), reinterpret_cast<const float4*>(d_y), d_lambda, reinterpret_cast<float4*>(d_out), n / 4, cols);
+    S3OD_TRAIN_DONE("residual_scale_add4_kernel");
+  }
   residual_scale_add_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, d_lambda, d_out, n, cols);
   S3OD_TRAIN_DONE("residual_scale_add_kernel");
 }
@@ -348,12 +369,20 @@ int s3od_train_convt_unfold(const float* d_dy, void* d_dcols, int batch, int h, 
   if (d_dy == nullptr || d_dcols == nullptr) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_convt_unfold");
   const int oh = (h - 1) * stride - 2 * pad + k, ow = (w - 1) * stride - 2 * pad + k;
   const long long n = static_cast<long long>(batch) * h * w * k * k * cout;
+  if (cout % 8 == 0 && al16(d_dy, d_dcols)) {
+    convt_unfold8_kernel<<<grid_for(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, static_cast<uint4*>(d_dcols), batch, h, w, cout, k, stride, pad, oh, ow);
+    S3OD_TRAIN_DONE("convt_unfold8_kernel");
+  }
   convt_unfold_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, static_cast<__nv_bfloat16*>(d_dcols), batch, h, w, cout, k, stride, pad, oh, ow);
   S3OD_TRAIN_DONE("convt_unfold_kernel");
 }
 
 int s3od_train_copy_cols(const float* d_in, float* d_out, long long rows, int cols, int pitch, const float* d_bias, s3od_stream stream) {
   if (d_in == nullptr || d_out == nullptr || rows < 1 || cols < 1 || pitch < cols) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_copy_cols");
+  if (cols % 4 == 0 && pitch % 4 == 0 && al16(d_in, d_out, d_bias)) {
+    copy_cols4_kernel<<<grid_for(rows * cols / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, reinterpret_cast<float4*>(d_out), rows, cols, pitch, d_bias);
+    S3OD_TRAIN_DONE("copy_cols4_kernel");
+  }
   copy_cols_kernel<<<grid_for(rows * cols), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, d_out, rows, cols, pitch, d_bias);
   S3OD_TRAIN_DONE("copy_cols_kernel");
 }
@@ -374,7 +403,11 @@ int s3od_train_bn_forward(const float* d_x, const float* d_gamma, const float* d
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bn_stats_kernel<<<(cols + 255) / 256, 256, 0, st>>>(sums, sums + cols, d_mean, d_rstd, cols, 1.0f / rows, eps);
   const long long n = static_cast<long long>(rows) * cols;
-  bn_apply_kernel<<<grid_for(n), 256, 0, st>>>(d_x, d_mean, d_rstd, d_gamma, d_beta, d_xhat, d_y, n, cols);
+  if (cols % 4 == 0 && al16(d_x, d_mean, d_rstd, d_gamma, d_beta, d_xhat, d_y))
+    bn_apply4_kernel<<<grid_for(n / 4), 256, 0, st>>>(reinterpret_cast<const float4*>(d_x), d_mean, d_rstd, d_gamma, d_beta, reinterpret_cast<float4*>(d_xhat),
+                                                      reinterpret_cast<float4*>(d_y), n / 4, cols);
+  else
+    bn_apply_kernel<<<grid_for(n), 256, 0, st>>>(d_x, d_mean, d_rstd, d_gamma, d_beta, d_xhat, d_y, n, cols);
   S3OD_TRAIN_DONE("bn forward kernels");
 }
 
@@ -389,34 +422,61 @@ int s3od_train_bn_backward(const float* d_dy, const float* d_xhat, const float* 
   rc = s3od_train_colsum(d_dy, d_xhat, rows, cols, nullptr, d_dgamma, 0, ws, stream);
   if (rc != S3OD_OK) return rc;
   const long long n = static_cast<long long>(rows) * cols;
-  bn_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, d_xhat, d_gamma, d_rstd, d_dbeta, d_dgamma, d_dx, n, cols, 1.0f / rows);
+  if (cols % 4 == 0 && al16(d_dy, d_xhat, d_gamma, d_rstd, d_dbeta, d_dgamma, d_dx))
+    bn_backward4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(d_dy), reinterpret_cast<const float4*>(d_xhat),
+                                                                                          d_gamma, d_rstd, d_dbeta, d_dgamma, reinterpret_cast<float4*>(d_dx), n / 4,
+                                                                                          cols, 1.0f / rows);
+  else
+    bn_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, d_xhat, d_gamma, d_rstd, d_dbeta, d_dgamma, d_dx, n, cols, 1.0f / rows);
   S3OD_TRAIN_DONE("bn backward kernels");
 }
 
 int s3od_train_relu(const float* d_x, float* d_y, long long n, s3od_stream stream) {
   if (d_x == nullptr || d_y == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_relu");
+  if (n % 4 == 0 && al16(d_x, d_y)) {
+    relu4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(d_x), reinterpret_cast<float4*>(d_y), n / 4);
+    S3OD_TRAIN_DONE("relu4_kernel");
+  }
   relu_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, n);
   S3OD_TRAIN_DONE("relu_kernel");
 }
 int s3od_train_relu_backward(const float* d_dy, const float* d_x, float* d_dx, long long n, s3od_stream stream) {
   if (d_dy == nullptr || d_x == nullptr || d_dx == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_relu_backward");
+  if (n % 4 == 0 && al16(d_dy, d_x, d_dx)) {
+    relu_backward4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(d_dy), reinterpret_cast<const float4*>(d_x),
+                                                                                            reinterpret_cast<float4*>(d_dx), n / 4);
+    S3OD_TRAIN_DONE("relu_backward4_kernel");
+  }
   relu_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, d_x, d_dx, n);
   S3OD_TRAIN_DONE("relu_backward_kernel");
 }
 int s3od_train_add(const float* d_a, const float* d_b, float* d_out, long long n, s3od_stream stream) {
   if (d_a == nullptr || d_b == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_add");
+  if (n % 4 == 0 && al16(d_a, d_b, d_out)) {
+    add4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(d_a), reinterpret_cast<const float4*>(d_b),
+                                                                                  reinterpret_cast<float4*>(d_out), n / 4);
+    S3OD_TRAIN_DONE("add4_kernel");
+  }
   add_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_a, d_b, d_out, n);
   S3OD_TRAIN_DONE("add_kernel");
 }
 int s3od_train_upsample2x(const float* d_x, float* d_y, int batch, int h, int w, int c, s3od_stream stream) {
   if (d_x == nullptr || d_y == nullptr || batch < 1 || h < 1 || w < 1 || c < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_upsample2x");
   const long long n = static_cast<long long>(batch) * 4 * h * w * c;
+  if (c % 4 == 0 && al16(d_x, d_y)) {
+    upsample2x4_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, reinterpret_cast<float4*>(d_y), batch, h, w, c);
+    S3OD_TRAIN_DONE("upsample2x4_kernel");
+  }
   upsample2x_f32_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, d_y, batch, h, w, c);
   S3OD_TRAIN_DONE("upsample2x_f32_kernel");
 }
 int s3od_train_upsample2x_backward(const float* d_dy, float* d_dx, int batch, int h, int w, int c, s3od_stream stream) {
   if (d_dy == nullptr || d_dx == nullptr || batch < 1 || h < 1 || w < 1 || c < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_upsample2x_backward");
   const long long n = static_cast<long long>(batch) * h * w * c;
+  if (c % 4 == 0 && al16(d_dy, d_dx)) {
+    upsample2x4_backward_kernel<<<grid_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, reinterpret_cast<float4*>(d_dx), batch, h, w, c);
+    S3OD_TRAIN_DONE("upsample2x4_backward_kernel");
+  }
   upsample2x_f32_backward_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_dy, d_dx, batch, h, w, c);
   S3OD_TRAIN_DONE("upsample2x_f32_backward_kernel");
 }
