@@ -206,6 +206,10 @@ int s3od_train_transpose(const void* d_in, int in_is_f32, void* d_out, int batch
                          int in_row_stride, float scale, s3od_stream stream);
 int s3od_train_scale_cast(const float* d_in, const float* d_colscale, void* d_out, long long n, int cols, s3od_stream stream);
 int s3od_train_cast_bf16_f32(const void* d_in, float* d_out, long long n, s3od_stream stream);       /* bf16 -> fp32 */
+/* fp32 [rows, cols] -> bf16 [rows, cols_padded] with zero columns behind `cols`, and bf16 [rows, cols_padded] -> fp32 [rows, cols]:
+   channel padding to the granularity of the tensor-core convolution kernels (column counts multiples of 4) */
+int s3od_train_cast_pad(const float* d_in, void* d_out, long long rows, int cols, int cols_padded, s3od_stream stream);
+int s3od_train_cast_slice(const void* d_in, float* d_out, long long rows, int cols, int cols_padded, s3od_stream stream);
 int s3od_train_residual_scale_add(const float* d_x, const float* d_y, const float* d_lambda, float* d_out, long long n, int cols, s3od_stream stream);
 int s3od_train_add_bias(float* d_a, const float* d_bias, long long n, int cols, s3od_stream stream);
 size_t s3od_train_colsum_workspace_bytes(int rows, int cols);

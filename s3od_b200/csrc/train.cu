@@ -194,6 +194,23 @@ int s3od_train_cast_bf16_f32(const void* d_in, float* d_out, long long n, s3od_s
   S3OD_TRAIN_DONE("cast_bf16_f32_kernel");
 }
 
+int s3od_train_cast_pad(const float* d_in, void* d_out, long long rows, int cols, int cols_padded, s3od_stream stream) {
+  if (d_in == nullptr || d_out == nullptr || rows < 1 || cols < 4 || cols % 4 != 0 || cols_padded % 4 != 0 || cols_padded < cols || !al16(d_in) ||
+      (reinterpret_cast<uintptr_t>(d_out) & 7) != 0)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_cast_pad (column counts multiples of 4, aligned buffers)");
+  cast_pad4_kernel<<<grid_for(rows * cols_padded / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, static_cast<uint2*>(d_out), rows, cols, cols_padded);
+  S3OD_TRAIN_DONE("cast_pad4_kernel");
+}
+
+int s3od_train_cast_slice(const void* d_in, float* d_out, long long rows, int cols, int cols_padded, s3od_stream stream) {
+  if (d_in == nullptr || d_out == nullptr || rows < 1 || cols < 4 || cols % 4 != 0 || cols_padded % 4 != 0 || cols_padded < cols || !al16(d_out) ||
+      (reinterpret_cast<uintptr_t>(d_in) & 7) != 0)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_cast_slice (column counts multiples of 4, aligned buffers)");
+  cast_slice4_kernel<<<grid_for(rows * cols / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(d_in), reinterpret_cast<float4*>(d_out),
+                                                                                                 rows, cols, cols_padded);
+  S3OD_TRAIN_DONE("cast_slice4_kernel");
+}
+
 int s3od_train_residual_scale_add(const float* d_x, const float* d_y, const float* d_lambda, float* d_out, long long n, int cols, s3od_stream stream) {
   if (d_x == nullptr || d_y == nullptr || d_lambda == nullptr || d_out == nullptr || n < 1) return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_residual_scale_add");
   if (n % 4 == 0 && cols % 4 == 0 && al16(d_x, d_y, d_lambda, d_out)) {

@@ -95,6 +95,33 @@ __global__ void __launch_bounds__(256) bn_backward4_kernel(const float4* __restr
                         g.z * r.z * (d.z - s1.z * inv_p - h.z * s2.z * inv_p), g.w * r.w * (d.w - s1.w * inv_p - h.w * s2.w * inv_p));
   }
 }
+// fp32 [rows, C] -> bf16 [rows, Cp] with zero columns C..Cp, and back (channel padding to the granularity of the tensor-core
+// convolution kernels); C % 4 == 0, Cp % 4 == 0
+__global__ void __launch_bounds__(256) cast_pad4_kernel(const float* __restrict__ in, uint2* __restrict__ out, long long rows, int C, int Cp) {
+  const int q = Cp / 4;
+  const long long n4 = rows * q;
+  S3OD_VEC_LOOP(i, n4) {
+    const long long r = i / q;
+    const int c = static_cast<int>(i - r * q) * 4;
+    uint2 o = make_uint2(0u, 0u);
+    if (c < C) {
+      const float4 v = *reinterpret_cast<const float4*>(in + r * C + c);
+      o = pack4_bf16(v.x, v.y, v.z, v.w);
+    }
+    out[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256) cast_slice4_kernel(const __nv_bfloat16* __restrict__ in, float4* __restrict__ out, long long rows, int C, int Cp) {
+  const int q = C / 4;
+  const long long n4 = rows * q;
+  S3OD_VEC_LOOP(i, n4) {
+    const long long r = i / q;
+    const int c = static_cast<int>(i - r * q) * 4;
+    const uint2 u = *reinterpret_cast<const uint2*>(in + r * Cp + c);
+    out[i] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+  }
+}
+
 // transposed-convolution unfold, 8 channels per thread (Cout % 8 == 0): two 16-byte loads, one 16-byte store
 __global__ void __launch_bounds__(256) convt_unfold8_kernel(const float* __restrict__ dy, uint4* __restrict__ dcols, int B, int H, int W, int Cout, int k,
                                                             int stride, int pad, int OH, int OW) {

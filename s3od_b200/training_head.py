@@ -42,6 +42,8 @@ def _bind_head(lib):
         lib.s3od_train_upsample2x_backward.argtypes = [vp, vp, ci, ci, ci, ci, vp]
         lib.s3od_train_small_linear.argtypes = [vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
         lib.s3od_train_small_linear_backward.argtypes = [vp, vp, vp, vp, vp, vp, ll, ci, ci, ci, ci, vp]
+        lib.s3od_train_cast_pad.argtypes = [vp, vp, ll, ci, ci, vp]
+        lib.s3od_train_cast_slice.argtypes = [vp, vp, ll, ci, ci, vp]
         lib.s3od_op_conv3x3_wgrad_f32.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
         lib.s3od_train_small_linear_backward_ws.argtypes = [vp, vp, vp, vp, vp, vp, ll, ci, ci, ci, ci, vp, vp]
         lib.s3od_train_small_linear_workspace_bytes.argtypes = [ll, ci, ci]
@@ -116,6 +118,22 @@ class _Ops:
         self.ck(self.lib.s3od_train_scale_cast(x.data_ptr(), None, out.data_ptr(), x.numel(), x.shape[-1], self.st()), "s3od_train_scale_cast")
         return out
 
+    def cast_pad(self, x, rows, c, cp):
+        """fp32 [rows, c] -> bf16 [rows, cp], zero columns behind c."""
+        if cp == c:
+            return self.cast(x.reshape(rows, c))
+        out = torch.empty(rows, cp, dtype=torch.bfloat16, device=self.dev)
+        self.ck(self.lib.s3od_train_cast_pad(x.data_ptr(), out.data_ptr(), rows, c, cp, self.st()), "s3od_train_cast_pad")
+        return out
+
+    def cast_slice(self, xb, rows, c, cp):
+        """bf16 [rows, cp] -> fp32 [rows, c]."""
+        if cp == c:
+            return self.to_f32(xb.reshape(rows, c))
+        out = self.f32(rows, c)
+        self.ck(self.lib.s3od_train_cast_slice(xb.data_ptr(), out.data_ptr(), rows, c, cp, self.st()), "s3od_train_cast_slice")
+        return out
+
     def to_f32(self, xb):
         out = torch.empty(xb.shape, dtype=torch.float32, device=self.dev)
         self.ck(self.lib.s3od_train_cast_bf16_f32(xb.data_ptr(), out.data_ptr(), xb.numel(), self.st()), "s3od_train_cast_bf16_f32")
@@ -183,16 +201,27 @@ class _Conv:
         self.wt = torch.zeros(self.Kp, self.Kc, dtype=torch.bfloat16, device=dev)
         self.wt[:self.K, :self.cout] = wm.t().to(torch.bfloat16)         # dgrad B operand [K (padded), cout (padded)]
         self.bias = b.detach().to(dev, torch.float32).contiguous() if b is not None else None
-        # Fast paths on the inference kernels (implicit GEMM through TMA, nothing materialised) for 3x3 / stride 1 / pad 1:
-        #   forward when cout % 128 == 0 (or the 64 -> 64 row kernel), dgrad = the same convolution of dy with the flipped,
-        #   transposed weights when the ORIGINAL cin % 256 == 0 (its output channels) - the bf16 results are widened back to fp32.
-        s3 = self.k == 3 and stride == 1 and pad == 1 and self.cin % 64 == 0
-        self.rows64 = s3 and self.cin == 64 and self.cout == 64               # needs W % 128 == 0 at run time
-        self.fast_fwd = s3 and self.cout % 128 == 0
-        self.fast_dgrad = s3 and self.cin % 256 == 0 and self.cout % 64 == 0
-        self.implicit_wgrad = s3 and self.cout % 64 == 0                      # s3od_op_conv3x3_wgrad_f32: no im2col matrix for the weight gradient
-        if self.fast_dgrad or self.rows64:                                    # w_d[ci][(ky', kx') * cout + co] = w[co][ci][2 - ky'][2 - kx']
-            self.wd = w.detach().to(dev, torch.float32).flip(2, 3).permute(1, 2, 3, 0).reshape(self.cin, 9 * self.cout).to(torch.bfloat16).contiguous()
+        # 3x3 / stride 1 / pad 1 convolutions with cin % 64 == 0 never materialise an im2col matrix: forward = the inference path's
+        # implicit-GEMM convolution (TMA im2col), dgrad = the same kernel on dy with the flipped, transposed weights, wgrad = the
+        # implicit weight-gradient kernel (s3od_op_conv3x3_wgrad_f32).  The kernels want output channels in multiples of 128, so
+        # cout (forward, and the channel count of dy) and cin (as the OUTPUT of the dgrad convolution) are zero-padded to that
+        # granularity in the packed weights and in the bf16 staging copies - the merged mask heads (64 -> 96 at 1024 x 1024) used
+        # to cost a 4.8 GB column matrix and a 10.7 GB fp32 dgrad product per batch of 4.
+        self.s3 = self.k == 3 and stride == 1 and pad == 1 and self.cin % 64 == 0 and self.cout % 4 == 0
+        self.rows64 = self.s3 and self.cin == 64 and self.cout == 64          # row-streaming kernel, needs W % 128 == 0 at run time
+        if self.s3:
+            self.cp, self.dp = _up(self.cout, 128), _up(self.cin, 128)
+            wfull = torch.zeros(self.cp, self.dp, 3, 3, dtype=torch.float32, device=dev)
+            wfull[:self.cout, :self.cin] = w.detach().to(dev, torch.float32)
+            self.wf_p = wfull[:, :self.cin].permute(0, 2, 3, 1).reshape(self.cp, self.K).to(torch.bfloat16).contiguous()      # [cp, 9 cin]
+            self.bias_p = None
+            if self.bias is not None:
+                self.bias_p = torch.zeros(self.cp, dtype=torch.float32, device=dev)
+                self.bias_p[:self.cout] = self.bias
+            # w_d[ci][(ky', kx') * cp + co] = w[co][ci][2 - ky'][2 - kx']
+            self.wd_p = wfull.flip(2, 3).permute(1, 2, 3, 0).reshape(self.dp, 9 * self.cp).to(torch.bfloat16).contiguous()
+            if self.rows64:
+                self.wd = self.wd_p[:64].reshape(64, 9, self.cp)[:, :, :64].reshape(64, 9 * 64).contiguous()
 
     def _cols(self, x, B, H, W, P):
         o = self.ops
@@ -207,14 +236,17 @@ class _Conv:
         OH, OW = (H + 2 * self.pad - self.k) // self.stride + 1, (W + 2 * self.pad - self.k) // self.stride + 1
         P = B * OH * OW
         x = x.contiguous()
-        if self.fast_fwd or (self.rows64 and W % 128 == 0):
-            yb = o.conv3x3(o.cast(x), self.wf[:self.cout], self.bias, B, H, W, self.cin, self.cout)
-            self.ctx = (None, x, (B, H, W), (OH, OW))                        # the wgrad builds its columns when it needs them
-            return o.to_f32(yb)
+        if self.s3:
+            xb = o.cast(x)
+            self.ctx = (None, xb, (B, H, W), (OH, OW))                       # bf16 x: all the weight gradient needs
+            if self.rows64 and W % 128 == 0:
+                return o.to_f32(o.conv3x3(xb, self.wf[:64], self.bias, B, H, W, 64, 64))
+            yb = o.conv3x3(xb, self.wf_p, self.bias_p, B, H, W, self.cin, self.cp)
+            return o.cast_slice(yb, P, self.cout, self.cp).view(B, OH, OW, self.cout)
         cols = self._cols(x, B, H, W, P)
         out = o.gemm(cols, self.wf, P, self.Np, self.K)
         y = o.copy_cols(out, P, self.cout, self.Np, self.bias)
-        self.ctx = (None, x, (B, H, W), (OH, OW)) if self.implicit_wgrad else (cols, None, (B, H, W), (OH, OW))
+        self.ctx = (cols, None, (B, H, W), (OH, OW))
         return y.view(B, OH, OW, self.cout)
 
     def backward(self, dy: torch.Tensor, emit: Emit, need_dx: bool = True) -> Optional[torch.Tensor]:
@@ -224,20 +256,24 @@ class _Conv:
         dy = dy.reshape(P, self.cout).contiguous()
         if self.bias is not None:
             emit(self.name + ".bias", o.colsum(dy))
-        dyb = None
-        if self.implicit_wgrad:
-            dyb = o.cast(dy)
-            dW = o.conv3x3_wgrad(dyb, o.cast(x_saved), B, H, W, self.cin, self.cout)     # the nine shifted windows of x are read by TMA
-        else:
-            if cols is None:
-                cols = self._cols(x_saved, B, H, W, P)
-            dW = o.wgrad(dy, cols, P, self.cout, self.K, self.Kp)                      # dY^T cols, pixels as the contraction
+        if self.s3:
+            use_rows = self.rows64 and W % 128 == 0
+            cp = 64 if use_rows else self.cp
+            dyb = o.cast_pad(dy, P, self.cout, cp)                                         # bf16, channels zero-padded to the kernel granularity
+            dW = o.conv3x3_wgrad(dyb, x_saved, B, H, W, self.cin, cp)[:self.cout]          # the nine shifted windows of x are read by TMA
+            emit(self.name + ".weight", dW.reshape(self.cout, self.k, self.k, self.cin).permute(0, 3, 1, 2).contiguous())
+            if not need_dx:
+                return None
+            if use_rows:
+                return o.to_f32(o.conv3x3(dyb.view(B, H, W, 64), self.wd, None, B, H, W, 64, 64))
+            dxb = o.conv3x3(dyb.view(B, H, W, self.cp), self.wd_p, None, B, H, W, self.cp, self.dp)
+            return o.cast_slice(dxb, P, self.cin, self.dp).view(B, H, W, self.cin)
+        if cols is None:
+            cols = self._cols(x_saved, B, H, W, P)
+        dW = o.wgrad(dy, cols, P, self.cout, self.K, self.Kp)                              # dY^T cols, pixels as the contraction
         emit(self.name + ".weight", dW.view(self.cout, self.k, self.k, self.cin).permute(0, 3, 1, 2).contiguous())
         if not need_dx:
             return None
-        if self.fast_dgrad or (self.rows64 and W % 128 == 0):
-            dxb = o.conv3x3((dyb if dyb is not None else o.cast(dy)).view(B, H, W, self.cout), self.wd, None, B, H, W, self.cout, self.cin)
-            return o.to_f32(dxb)
         dyb = torch.zeros(P, self.Kc, dtype=torch.bfloat16, device=o.dev)
         dyb[:, :self.cout] = o.cast(dy)                                                  # zero padded to the 64-granular contraction
         dcols = o.gemm(dyb, self.wt, P, self.Kp, self.Kc)
