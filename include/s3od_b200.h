@@ -215,6 +215,11 @@ int s3od_train_add_bias(float* d_a, const float* d_bias, long long n, int cols, 
 size_t s3od_train_colsum_workspace_bytes(int rows, int cols);
 int s3od_train_colsum(const float* d_a, const float* d_b, int rows, int cols, const float* d_colscale, float* d_out, int accumulate,
                       void* d_workspace, s3od_stream stream);
+/* two column sums in one pass over a: out_ab[c] = sum_r a[r][c] * b[r][c], out_a[c] = colscale_a[c] * sum_r a[r][c] (colscale_a may be NULL);
+   workspace of s3od_train_colsum2_workspace_bytes(rows, cols) */
+size_t s3od_train_colsum2_workspace_bytes(int rows, int cols);
+int s3od_train_colsum2(const float* d_a, const float* d_b, int rows, int cols, const float* d_colscale_a, float* d_out_ab, float* d_out_a, void* d_workspace,
+                       s3od_stream stream);
 size_t s3od_train_ln_backward_workspace_bytes(int rows, int dim);
 int s3od_train_ln_backward(const float* d_x, const float* d_gamma, const float* d_dy, const float* d_dres, float* d_dx, int rows, int dim, float eps,
                            float* d_dgamma, float* d_dbeta, void* d_workspace, s3od_stream stream);

@@ -253,6 +253,28 @@ int s3od_train_colsum(const float* d_a, const float* d_b, int rows, int cols, co
   S3OD_TRAIN_DONE("colsum kernels");
 }
 
+size_t s3od_train_colsum2_workspace_bytes(int rows, int cols) { return 2 * s3od_train_colsum_workspace_bytes(rows, cols); }
+
+int s3od_train_colsum2(const float* d_a, const float* d_b, int rows, int cols, const float* d_colscale_a, float* d_out_ab, float* d_out_a, void* d_workspace,
+                       s3od_stream stream) {
+  if (d_a == nullptr || d_b == nullptr || d_out_ab == nullptr || d_out_a == nullptr || d_workspace == nullptr || rows < 1 || cols < 1)
+    return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_colsum2");
+  const int rpb = colsum_rows_per_block(rows);
+  const int nblk = (rows + rpb - 1) / rpb;
+  float* p_ab = static_cast<float*>(d_workspace);
+  float* p_a = p_ab + static_cast<size_t>(nblk) * cols;
+  if (cols % 4 != 0 || !al16(d_a, d_b, d_workspace)) {          // odd shapes: two one-sum passes
+    int rc = s3od_train_colsum(d_a, d_b, rows, cols, nullptr, d_out_ab, 0, d_workspace, stream);
+    if (rc != S3OD_OK) return rc;
+    return s3od_train_colsum(d_a, nullptr, rows, cols, d_colscale_a, d_out_a, 0, d_workspace, stream);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  colsum2_partial_kernel<<<dim3((cols + 255) / 256, nblk), 256, 0, st>>>(d_a, d_b, rows, cols, rpb, p_ab, p_a);
+  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(p_ab, nblk, cols, nullptr, d_out_ab, 0);
+  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(p_a, nblk, cols, d_colscale_a, d_out_a, 0);
+  S3OD_TRAIN_DONE("colsum2 kernels");
+}
+
 size_t s3od_train_ln_backward_workspace_bytes(int rows, int dim) { return static_cast<size_t>(2) * ((rows + 7) / 8) * dim * sizeof(float); }
 
 int s3od_train_ln_backward(const float* d_x, const float* d_gamma, const float* d_dy, const float* d_dres, float* d_dx, int rows, int dim, float eps,
@@ -404,7 +426,7 @@ int s3od_train_copy_cols(const float* d_in, float* d_out, long long rows, int co
   S3OD_TRAIN_DONE("copy_cols_kernel");
 }
 
-size_t s3od_train_bn_workspace_bytes(int rows, int cols) { return s3od_train_colsum_workspace_bytes(rows, cols) + 4 * static_cast<size_t>(cols) * sizeof(float); }
+size_t s3od_train_bn_workspace_bytes(int rows, int cols) { return s3od_train_colsum2_workspace_bytes(rows, cols) + 4 * static_cast<size_t>(cols) * sizeof(float); }
 
 int s3od_train_bn_forward(const float* d_x, const float* d_gamma, const float* d_beta, float* d_xhat, float* d_y, float* d_mean, float* d_rstd, int rows,
                           int cols, float eps, void* d_workspace, s3od_stream stream) {
@@ -413,9 +435,7 @@ int s3od_train_bn_forward(const float* d_x, const float* d_gamma, const float* d
     return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_bn_forward");
   float* sums = static_cast<float*>(d_workspace);                           // [sum x | sum x^2 | - | -], then the column-sum partials
   void* ws = sums + 4 * static_cast<size_t>(cols);
-  int rc = s3od_train_colsum(d_x, nullptr, rows, cols, nullptr, sums, 0, ws, stream);
-  if (rc != S3OD_OK) return rc;
-  rc = s3od_train_colsum(d_x, d_x, rows, cols, nullptr, sums + cols, 0, ws, stream);
+  int rc = s3od_train_colsum2(d_x, d_x, rows, cols, nullptr, sums + cols, sums, ws, stream);      // sum x^2 and sum x in one pass
   if (rc != S3OD_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bn_stats_kernel<<<(cols + 255) / 256, 256, 0, st>>>(sums, sums + cols, d_mean, d_rstd, cols, 1.0f / rows, eps);
@@ -434,9 +454,7 @@ int s3od_train_bn_backward(const float* d_dy, const float* d_xhat, const float* 
       d_workspace == nullptr)
     return train_fail(S3OD_ERR_ARG, "bad argument to s3od_train_bn_backward");
   void* ws = static_cast<float*>(d_workspace) + 4 * static_cast<size_t>(cols);
-  int rc = s3od_train_colsum(d_dy, nullptr, rows, cols, nullptr, d_dbeta, 0, ws, stream);
-  if (rc != S3OD_OK) return rc;
-  rc = s3od_train_colsum(d_dy, d_xhat, rows, cols, nullptr, d_dgamma, 0, ws, stream);
+  int rc = s3od_train_colsum2(d_dy, d_xhat, rows, cols, nullptr, d_dgamma, d_dbeta, ws, stream);   // sum dy xhat and sum dy in one pass
   if (rc != S3OD_OK) return rc;
   const long long n = static_cast<long long>(rows) * cols;
   if (cols % 4 == 0 && al16(d_dy, d_xhat, d_gamma, d_rstd, d_dbeta, d_dgamma, d_dx))

@@ -151,6 +151,39 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     *reinterpret_cast<float4*>(partial + static_cast<long long>(blockIdx.y) * C + c) = s;
   }
 }
+// two sums in one pass over a: partial_ab[blk][c] = sum a[r][c] * b[r][c] and partial_a[blk][c] = sum a[r][c] (BatchNorm statistics:
+// a = b = x; BatchNorm backward: a = dy, b = xhat; LayerScale + bias gradient: a = d out, b = branch output)
+__global__ void __launch_bounds__(256) colsum2_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int M, int C, int rows_per_block,
+                                                              float* __restrict__ partial_ab, float* __restrict__ partial_a) {
+  __shared__ float4 red[2][4][64];
+  const int cq = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int c = blockIdx.x * 256 + 4 * cq;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t = s;
+  if (c < C) {
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 4) {
+      const long long i = static_cast<long long>(r) * C + c;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a + i));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(b + i));
+      s.x += x.x * y.x; s.y += x.y * y.y; s.z += x.z * y.z; s.w += x.w * y.w;
+      t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
+    }
+  }
+  red[0][rl][cq] = s;
+  red[1][rl][cq] = t;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+      const float4 u = red[0][j][cq], v = red[1][j][cq];
+      s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w;
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    *reinterpret_cast<float4*>(partial_ab + static_cast<long long>(blockIdx.y) * C + c) = s;
+    *reinterpret_cast<float4*>(partial_a + static_cast<long long>(blockIdx.y) * C + c) = t;
+  }
+}
 // any column count / alignment: one thread per column
 __global__ void __launch_bounds__(256) colsum_partial_scalar_kernel(const float* __restrict__ a, const float* __restrict__ b, int M, int C,
                                                                     int rows_per_block, float* __restrict__ partial) {

@@ -444,6 +444,9 @@ def _bind_block(lib):
         lib.s3od_train_colsum_workspace_bytes.argtypes = [ci, ci]
         lib.s3od_train_colsum_workspace_bytes.restype = ctypes.c_size_t
         lib.s3od_train_colsum.argtypes = [vp, vp, ci, ci, vp, vp, ci, vp, vp]
+        lib.s3od_train_colsum2_workspace_bytes.argtypes = [ci, ci]
+        lib.s3od_train_colsum2_workspace_bytes.restype = ctypes.c_size_t
+        lib.s3od_train_colsum2.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp]
         lib.s3od_train_ln_backward_workspace_bytes.argtypes = [ci, ci]
         lib.s3od_train_ln_backward_workspace_bytes.restype = ctypes.c_size_t
         lib.s3od_train_ln_backward.argtypes = [vp, vp, vp, vp, vp, ci, ci, cf, vp, vp, vp, vp]
@@ -605,6 +608,15 @@ class EncoderBlockStep:
                  "s3od_train_colsum")
         return out
 
+    def _colsum2(self, a, b, colscale_a=None):
+        """(sum_r a*b, colscale_a * sum_r a) per column, one pass over a."""
+        M, C = a.shape
+        ws = torch.empty(self.lib.s3od_train_colsum2_workspace_bytes(M, C), dtype=torch.uint8, device=self.dev)
+        out_ab, out_a = torch.empty(C, dtype=torch.float32, device=self.dev), torch.empty(C, dtype=torch.float32, device=self.dev)
+        self._ck(self.lib.s3od_train_colsum2(a.data_ptr(), b.data_ptr(), M, C, colscale_a.data_ptr() if colscale_a is not None else None,
+                                             out_ab.data_ptr(), out_a.data_ptr(), ws.data_ptr(), self._st()), "s3od_train_colsum2")
+        return out_ab, out_a
+
     def _ln_backward(self, x, gamma, dy, dres):
         M, D = x.shape
         ws = torch.empty(self.lib.s3od_train_ln_backward_workspace_bytes(M, D), dtype=torch.uint8, device=self.dev)
@@ -667,8 +679,7 @@ class EncoderBlockStep:
         with torch.cuda.device(self.dev):
             st = self._st()
             # ---- MLP branch: x2 = x1 + ls2 * (down(gelu(up(LN2(x1)))))
-            grads["layer_scale2.lambda1"] = self._colsum(dx2, s["y"])
-            grads["mlp.down_proj.bias"] = self._colsum(dx2, None, w["ls2"])
+            grads["layer_scale2.lambda1"], grads["mlp.down_proj.bias"] = self._colsum2(dx2, s["y"], w["ls2"])      # sum dx2 y, ls2 sum dx2
             dy = self._scale_cast(dx2, w["ls2"])
             dhmid = self._gemm(dy, wt["down.w"], M, I, D)                                   # dgrad: dY W
             grads["mlp.down_proj.weight"] = self._wgrad(dy, s["hmid"], M, D, I)                        # wgrad: dY^T X
@@ -681,8 +692,7 @@ class EncoderBlockStep:
             grads["mlp.up_proj.weight"] = self._wgrad(dhpre, s["xn2"], M, I, D)
             dx1, grads["norm2.weight"], grads["norm2.bias"] = self._ln_backward(s["x1"], w["ln2.w"], dxn2, dx2)
             # ---- attention branch: x1 = x0 + ls1 * o_proj(attn(LN1(x0)))
-            grads["layer_scale1.lambda1"] = self._colsum(dx1, s["o"])
-            grads["attention.o_proj.bias"] = self._colsum(dx1, None, w["ls1"])
+            grads["layer_scale1.lambda1"], grads["attention.o_proj.bias"] = self._colsum2(dx1, s["o"], w["ls1"])
             do = self._scale_cast(dx1, w["ls1"])
             dctx = self._gemm(do, wt["o.w"], M, D, D)
             grads["attention.o_proj.weight"] = self._wgrad(do, s["ctx"], M, D, D)

@@ -177,6 +177,9 @@ def test_training_glue_kernels_transpose_colsum_splitk(vitb_sd):
         sc = torch.randn(cols, device="cuda", generator=g)
         assert float((blk._colsum(a) - a.double().sum(0).float()).abs().max()) <= 1e-4 * math.sqrt(rows)
         assert float((blk._colsum(a, b, sc) - ((a.double() * b.double()).sum(0) * sc.double()).float()).abs().max()) <= 3e-4 * math.sqrt(rows)
+        ab, a1 = blk._colsum2(a, b, sc)                                                  # both sums in one pass
+        assert float((ab - (a.double() * b.double()).sum(0).float()).abs().max()) <= 3e-4 * math.sqrt(rows)
+        assert float((a1 - (a.double().sum(0) * sc.double()).float()).abs().max()) <= 3e-4 * math.sqrt(rows)
     for rows, n_out, n_in in ((4101, 768, 768), (9000, 64, 640), (700, 256, 128), (700, 96, 128), (65, 192, 64), (16404, 2304, 768)):
         dy = torch.randn(rows, n_out, device="cuda", generator=g).to(torch.bfloat16)
         x = torch.randn(rows, n_in, device="cuda", generator=g).to(torch.bfloat16)
