@@ -18,7 +18,11 @@
 // each - the tcgen05.ld .16x256b layout of the forward kernel; with 8 warps = one per 16 rows the exponential phase of a step took 2.3 x
 // its SFU time, the one CTA per SM has nothing else to hide latency with); warp 16: MMA issuer; warp 17: TMA producer (X, Y once;
 // U, W through a ring).
-// Tensor memory (512 columns): S 0..95 | dP 96..191 | P buffers 192, 240 | dA buffers 288, 336 | acc_ds 384..447 | acc_p 448..511.
+// Tensor memory (512 columns): two (S, dP) buffers of 96 + 96 columns | acc_ds 384..447 | acc_p 448..511.  The bf16 P and dA of
+// a step are written IN PLACE over the S and dP columns the same warp has just read (24 packed columns at the start of its
+// 48-column half), so both S / dP buffers fit beside the accumulators: the score MMAs of step j + 1 run while the warps are
+// still exponentiating step j, and buffer j & 1 is overwritten by the score MMAs of step j + 2 only behind the accumulate
+// MMAs of step j in the (in-order) tensor pipe.  With one S / dP buffer the kernel ran at 2.2 x its exp2 / MMA bound.
 // All operands are [B*H, npad, 64] bf16 with npad % 384 == 0 and zero rows behind the sequence; L is +inf there, which makes
 // P (and with it dA) exactly 0 for padding queries; padding keys have K = 0 rows, so whatever dA holds there adds nothing to dQ,
 // and their own rows of dK / dV are never read.
@@ -69,11 +73,10 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
   uint64_t* x_full = bars;                            // X and Y have landed
   uint64_t* u_full = bars + 1;                        // kAttnBwdStages
   uint64_t* u_empty = u_full + kAttnBwdStages;        // the accumulate MMAs that read the stage have completed
-  uint64_t* s_full = u_empty + kAttnBwdStages;        // S and dP of the step are in TMEM
-  uint64_t* s_empty = s_full + 1;                     // one arrival per softmax thread: both are in registers
-  uint64_t* p_full = s_empty + 1;                     // [2] one arrival per softmax thread: P / dA buffer j & 1 written
-  uint64_t* p_empty = p_full + 2;                     // [2] the accumulate MMAs of the step have completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+  uint64_t* s_full = u_empty + kAttnBwdStages;        // [2] S and dP of step j are in buffer j & 1
+  uint64_t* p_full = s_full + 2;                      // [2] one arrival per softmax thread: P / dA of step j written into buffer j & 1
+  uint64_t* acc_done = p_full + 2;                    // every accumulate MMA has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,12 +99,11 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
         mbar_init(&u_full[i], 1);
         mbar_init(&u_empty[i], 1);
       }
-      mbar_init(s_full, 1);
-      mbar_init(s_empty, 32 * kAttnBwdSoftmaxWarps);
+      mbar_init(&s_full[0], 1);
+      mbar_init(&s_full[1], 1);
       mbar_init(&p_full[0], 32 * kAttnBwdSoftmaxWarps);
       mbar_init(&p_full[1], 32 * kAttnBwdSoftmaxWarps);
-      mbar_init(&p_empty[0], 1);
-      mbar_init(&p_empty[1], 1);
+      mbar_init(acc_done, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kColDp = kAttnKvTile, kColP = 192, kColDs = 288, kColAccDs = 384, kColAccP = 448;
+  constexpr uint32_t kColDp = kAttnKvTile, kColBuf = 2 * kAttnKvTile, kColAccDs = 384, kColAccP = 448;      // buffer b: S at b * 192, dP behind it
 
   if (warp == kWarpTma) {
     if (lane == 0) {
@@ -140,18 +142,18 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
     const uint64_t y_desc = make_sdesc_sw128(smem_u32(sY));
     int ks_st = 0;
     uint32_t ks_par = 0;
-    auto issue_s = [&](int j) {
+    auto issue_s = [&](int j) {                       // S and dP of step j into buffer j & 1
       mbar_wait(&u_full[ks_st], ks_par);
-      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);     // S and dP of the previous step are in registers
       tc_fence_after();
       const uint64_t u_desc = make_sdesc_sw128(smem_u32(sU + ks_st * 2 * kAttnBwdUBytes));
       const uint64_t w_desc = make_sdesc_sw128(smem_u32(sU + ks_st * 2 * kAttnBwdUBytes + kAttnBwdUBytes));
+      const uint32_t tmem_s = tmem_base + (j & 1) * kColBuf;
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, x_desc + 2 * k, u_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_s, x_desc + 2 * k, u_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + kColDp, y_desc + 2 * k, w_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_s + kColDp, y_desc + 2 * k, w_desc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
       }
       __syncwarp();
       if (++ks_st == kAttnBwdStages) {
@@ -161,27 +163,30 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
     };
     mbar_wait(x_full, 0);
     issue_s(0);
+    if (T > 1) issue_s(1);
     int st = 0;
     for (int j = 0; j < T; ++j) {
-      if (j + 1 < T) issue_s(j + 1);
-      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);        // P and dA of step j are in place (and its S / dP have been consumed)
       tc_fence_after();
       const uint64_t u_mn = make_sdesc_sw128_mn(smem_u32(sU + st * 2 * kAttnBwdUBytes));
       const uint64_t w_mn = make_sdesc_sw128_mn(smem_u32(sU + st * 2 * kAttnBwdUBytes + kAttnBwdUBytes));
-      const uint32_t buf = (j & 1) * (kAttnKvTile / 2);
+      const uint32_t tmem_p = tmem_base + (j & 1) * kColBuf;             // P over the S columns, dA over the dP columns
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < kAttnKvTile / 16; ++ks) {
-          // A: 16 streamed rows = 8 packed TMEM columns per step;  B: the same 16 rows = 2048 B of the MN-major tile
-          umma_bf16_ts(tmem_base + kColAccDs, tmem_base + kColDs + buf + 8 * ks, u_mn + 128 * ks, idesc_acc, (j | ks) != 0 ? 1u : 0u);
-          if (kColStats)
-            umma_bf16_ts(tmem_base + kColAccP, tmem_base + kColP + buf + 8 * ks, w_mn + 128 * ks, idesc_acc, (j | ks) != 0 ? 1u : 0u);
+          // A: 16 streamed rows = 8 packed TMEM columns: rows 0..47 of the step at columns 0..23, rows 48..95 at columns 48..71
+          // (each softmax warp writes into its own 48-column half);  B: the same 16 rows = 2048 B of the MN-major tile
+          const uint32_t a_col = 8 * ks + (ks >= 3 ? 24 : 0);
+          umma_bf16_ts(tmem_base + kColAccDs, tmem_p + kColDp + a_col, u_mn + 128 * ks, idesc_acc, (j | ks) != 0 ? 1u : 0u);
+          if (kColStats) umma_bf16_ts(tmem_base + kColAccP, tmem_p + a_col, w_mn + 128 * ks, idesc_acc, (j | ks) != 0 ? 1u : 0u);
         }
         umma_commit(&u_empty[st]);
-        umma_commit(&p_empty[j & 1]);
+        if (j == T - 1) umma_commit(acc_done);
       }
       __syncwarp();
       if (++st == kAttnBwdStages) st = 0;
+      // buffer j & 1 is free again BEHIND the accumulate MMAs just issued: the tensor pipe executes in issue order
+      if (j + 2 < T) issue_s(j + 2);
     }
   } else {
     // ===================== P = exp2(S - L), dA = P (dP - Delta) =====================
@@ -191,7 +196,6 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
     const int q2 = 2 * (lane & 3);
     const uint32_t s_addr = tmem_base + (static_cast<uint32_t>(lane_base) << 16);
     const uint32_t s_half = s_addr + 48 * col_half;    // fp32 columns of this warp
-    const uint32_t w_half = 24 * col_half;             // the same columns as packed bf16 pairs
     const float* lse = p.lse + static_cast<size_t>(bh) * p.npad;
     const float* delta = p.delta + static_cast<size_t>(bh) * p.npad;
     float nl_a = 0.0f, nl_b = 0.0f, nd_a = 0.0f, nd_b = 0.0f;       // row statistics (negated): rows row_a, row_a + 8 of the CTA's tile
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
     uint32_t wp[kRegs / 2], wd[kRegs / 2];
 
     for (int j = 0; j < T; ++j) {
-      const uint32_t buf = (j & 1) * (kAttnKvTile / 2);
+      const uint32_t buf = (j & 1) * kColBuf;          // this step's S / dP buffer
       // column statistics of this step: issued before the wait so that their latency hides behind it
       float2 l2[kRegs / 4], d2[kRegs / 4];
       if (kColStats) {
@@ -218,18 +222,17 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
           d2[i] = __ldg(delta_c + 4 * i);
         }
       }
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      tmem_ld_16x256_x4<0>(s_half, rs);
-      tmem_ld_16x256_x2<16>(s_half + 32, rs);
-      tmem_ld_16x256_x4<0>(s_half + kColDp, rd);
-      tmem_ld_16x256_x2<16>(s_half + kColDp + 32, rd);
+      tmem_ld_16x256_x4<0>(s_half + buf, rs);
+      tmem_ld_16x256_x2<16>(s_half + buf + 32, rs);
+      tmem_ld_16x256_x4<0>(s_half + buf + kColDp, rd);
+      tmem_ld_16x256_x2<16>(s_half + buf + kColDp + 32, rd);
       tmem_ld_wait16<0>(rs);
       tmem_ld_wait8<16>(rs);
       tmem_ld_wait16<0>(rd);
       tmem_ld_wait8<16>(rd);
-      tc_fence_before();
-      mbar_arrive(s_empty);                            // the next S / dP may overwrite tensor memory
+      __syncwarp();                                    // every lane holds its scores: the in-place stores below overwrite other lanes' columns
 #pragma unroll
       for (int i = 0; i < kRegs / 4; ++i) {
         // this thread's columns 48 col_half + 8 i + q2 + {0, 1} of rows a (registers 4 i, 4 i + 1) and b (4 i + 2, 4 i + 3)
@@ -257,13 +260,12 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
         wd[2 * i] = pack_bf16x2(g0, g1);
         wd[2 * i + 1] = pack_bf16x2(g2, g3);
       }
-      if (j >= 2) mbar_wait(&p_empty[j & 1], ((j - 2) >> 1) & 1);     // the accumulate MMAs of step j - 2 have read this buffer
-      tc_fence_after();
-      tmem_st_16x128_x4<0>(s_addr + kColDs + buf + w_half, wd);
-      tmem_st_16x128_x2<8>(s_addr + kColDs + buf + w_half + 16, wd);
+      // in place: 24 packed columns at the start of this warp's own 48-column half of dP (dA) and of S (P)
+      tmem_st_16x128_x4<0>(s_half + buf + kColDp, wd);
+      tmem_st_16x128_x2<8>(s_half + buf + kColDp + 16, wd);
       if (kColStats) {
-        tmem_st_16x128_x4<0>(s_addr + kColP + buf + w_half, wp);
-        tmem_st_16x128_x2<8>(s_addr + kColP + buf + w_half + 16, wp);
+        tmem_st_16x128_x4<0>(s_half + buf, wp);
+        tmem_st_16x128_x2<8>(s_half + buf + 16, wp);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads, 1) attention_bwd_kernel(const
     }
 
     // ---- epilogue: accumulators -> fp32 [B*H, npad, 64]
-    mbar_wait(&p_empty[(T - 1) & 1], ((T - 1) >> 1) & 1);
+    mbar_wait(acc_done, 0);
     tc_fence_after();
     const size_t row0 = static_cast<size_t>(bh) * p.npad + tile * kAttnTile;
     auto store_acc = [&](uint32_t col, float* out, float scale) {       // this warp: 32 of the accumulator's 64 columns
