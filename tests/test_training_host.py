@@ -116,3 +116,19 @@ def test_single_process_allreduce_is_a_no_op():
     red.finish()
     assert sorted(red.launch_order) == list(range(lay.num_buckets)) and red.world == 1
     assert torch.equal(flat, torch.arange(lay.total, dtype=torch.float32))
+
+
+def test_weight_gradient_split_plans():
+    """Host logic of the split-K weight-gradient GEMMs (training.wgrad_plan / wgrad_plan_tn): every split keeps whole 64-row blocks,
+    the (split, tile) items never exceed one wave of the 148 SMs, and short contractions are not split at all."""
+    from s3od_b200.training import wgrad_plan, wgrad_plan_tn
+    for n_out, n_in, rows in ((768, 768, 4101), (2304, 768, 16404), (768, 3072, 4101), (64, 640, 262144), (256, 2304, 65536), (96, 128, 700), (768, 768, 100)):
+        splits, kpad = wgrad_plan(n_out, n_in, rows, 148)
+        assert splits >= 1 and kpad >= rows and kpad % (64 * splits) == 0 and kpad - rows < 64 * splits
+        tiles = ((n_out + 127) // 128 + 1) // 2 * (n_in // (256 if n_in % 256 == 0 else 128))
+        assert splits == 1 or splits * tiles <= 74
+        s_tn = wgrad_plan_tn(n_out, n_in, rows, 148)
+        tiles_tn = ((n_out + 127) // 128) * ((n_in + 255) // 256)
+        assert s_tn >= 1 and (s_tn == 1 or (s_tn * tiles_tn <= 148 and rows // s_tn >= 256))
+    assert wgrad_plan(768, 768, 100, 148)[0] == 1 and wgrad_plan_tn(768, 768, 100, 148) == 1
+    assert wgrad_plan_tn(768, 768, 16404, 148) == 8          # 18 output tiles -> 8 splits = 144 items
