@@ -212,6 +212,53 @@ def test_implicit_conv_weight_gradient(B, H, W, cin, cout):
     assert err <= 2e-3 * math.sqrt(B * H * W), (err, float(ref.abs().max()))
 
 
+def test_weight_gradient_kernels_stay_inside_their_buffers():
+    """Guard bands around the outputs and workspaces of the transpose-free / implicit weight-gradient kernels (partial tiles in M and N,
+    ragged contraction lengths, several k-splits): every output element is written, nothing outside it is touched."""
+    import ctypes
+    from s3od_b200.training_head import _Ops
+    o = _Ops("cuda:0")
+    lib, st = o.lib, o.st()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    guard, sentinel = 4096, -12345.0
+
+    def guarded(n):
+        buf = torch.full((n + 2 * guard,), sentinel, device="cuda")
+        return buf, buf[guard:guard + n]
+
+    def check(buf, n, what):
+        assert bool((buf[:guard] == sentinel).all()) and bool((buf[guard + n:] == sentinel).all()), what + ": wrote outside its buffer"
+        assert not bool((buf[guard:guard + n] == sentinel).any()), what + ": left output elements unwritten"
+
+    for rows, m, n, splits in ((1000, 64, 640, 3), (70, 192, 64, 1), (4101, 128, 256, 7), (513, 320, 576, 2)):
+        a = torch.randn(rows, m, device="cuda", generator=g).to(torch.bfloat16)
+        b = torch.randn(rows, n, device="cuda", generator=g).to(torch.bfloat16)
+        cb, c = guarded(m * n)
+        wb, w = guarded(splits * m * n)
+        assert lib.s3od_op_wgrad_gemm_f32(a.data_ptr(), m, b.data_ptr(), n, c.data_ptr(), m, n, rows, splits, w.data_ptr(), st) == 0
+        torch.cuda.synchronize()
+        check(cb, m * n, f"wgrad {rows}x{m}x{n}")
+        assert bool((wb[:guard] == sentinel).all()) and bool((wb[guard + splits * m * n:] == sentinel).all())
+        ref = a.float().t() @ b.float()
+        assert float((c.view(m, n) - ref).abs().max()) <= 2e-3 * math.sqrt(rows)
+    for B, H, W, cin, cout, splits in ((1, 9, 21, 64, 64, 2), (2, 16, 16, 128, 192, 1), (1, 33, 7, 64, 128, 5)):
+        x = torch.randn(B, H, W, cin, device="cuda", generator=g).to(torch.bfloat16)
+        dy = torch.randn(B, H, W, cout, device="cuda", generator=g).to(torch.bfloat16)
+        n_el = cout * 9 * cin
+        cb, c = guarded(n_el)
+        wb, w = guarded(splits * n_el)
+        assert lib.s3od_op_conv3x3_wgrad_f32(dy.data_ptr(), x.data_ptr(), c.data_ptr(), B, H, W, cin, cout, splits, w.data_ptr(), st) == 0
+        torch.cuda.synchronize()
+        check(cb, n_el, f"conv wgrad {B}x{H}x{W} {cin}->{cout}")
+        assert bool((wb[:guard] == sentinel).all()) and bool((wb[guard + splits * n_el:] == sentinel).all())
+    # argument checks
+    a = torch.zeros(64, 96, dtype=torch.bfloat16, device="cuda")
+    c = torch.zeros(96 * 64, device="cuda")
+    assert lib.s3od_op_wgrad_gemm_f32(a.data_ptr(), 96, a.data_ptr(), 96, c.data_ptr(), 96, 96, 64, 1, None, st) != 0          # widths not multiples of 64
+    a = torch.zeros(1024, 64, dtype=torch.bfloat16, device="cuda")
+    assert lib.s3od_op_wgrad_gemm_f32(a.data_ptr(), 64, a.data_ptr(), 64, c.data_ptr(), 64, 64, 1024, 4, None, st) != 0      # splits without a workspace
+
+
 @pytest.mark.parametrize("n", [3, 1])
 def test_grouped_mask_head_backward_two_stage(n):
     """s3od_train_small_linear_backward_ws at a full-resolution row count (two-stage weight gradient) against torch and against
